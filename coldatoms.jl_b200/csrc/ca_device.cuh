@@ -1,0 +1,693 @@
+// ca_device.cuh -- per-trajectory device code of the one-atom path (samplers, beams, Lindblad RHS, DP5).
+//
+// Everything here is `__host__ __device__` and free of warp intrinsics, so the very same source is run
+// (a) by the sm_100a kernels in ca_kernels.cu and (b) on the CPU by tests/hostemu (test-only harness that
+// lets the build container, which has no GPU, check this code against the oracle).
+//
+// Reference map (file:line relative to the reference repository):
+//   Philox sampler      <- samples_generate, harmonic branch      src/atom_sampler.jl:84-96
+//   phase-noise tables  <- ϕ                                       src/lasernoise_sampler.jl:31-37
+//   beams               <- A, A_phase (src/utilities.jl:27-48), Ω (src/rydberg_model.jl:51-74),
+//                          simple_flattopHG/LG_field (src/arbitrary_beams.jl:50-81)
+//   coefficients        <- GenerateHamiltonian closures            src/rydberg_model.jl:152-188
+//   RHS                 <- QuantumOptics dmaster_h! on operators/J src/rydberg_model.jl:25,126-130
+//   DP5 + controller    <- OrdinaryDiffEq DP5 / PIController (see oracle/coldatoms_oracle.c header)
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#include "../../include/coldatoms_b200.h"
+
+#if defined(__CUDACC__)
+#define CA_HD __host__ __device__ __forceinline__
+#else
+#define CA_HD inline
+#endif
+
+namespace ca {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTwoPi = 6.28318530717958647692528676655900577;
+constexpr int kMaxModes = 17;  // flat-top orders up to 32
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10: counter = (traj_lo, traj_hi, draw, stream), key = (seed_lo, seed_hi)
+// ---------------------------------------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+CA_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+CA_HD U4 philox(uint64_t seed, uint64_t index, uint32_t draw, uint32_t stream) {
+    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = draw, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+CA_HD double u53(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+CA_HD double u53_open(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+CA_HD void sincos_d(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Derived (device) model: everything that is constant over the ensemble, precomputed on the host.
+// ---------------------------------------------------------------------------------------------------
+struct DevBeam {
+    double hO;        // Ω0/2
+    double cs, sn;    // cosθ, sinθ
+    double w0, z0, inv_z0, inv_w0sq, k;  // k = 2 z0 / w0^2
+    double sqz_inv;   // 1/sqz
+    int kind, nx, ny, nl;                // HG: nx = n/2, ny = m/2 ; LG: nl = l/2
+    double cx[kMaxModes], cy[kMaxModes]; // HG_coeff(i, n/2), HG_coeff(j, m/2) or LG_coeff(p, l/2) in cx
+};
+
+struct DevModel {
+    DevBeam red, blue;
+    double aDx, aDz, bDx, bDz;  // Δ_D = aDx Vx + aDz Vz ; δ_D = bDx Vx + bDz Vz
+    double dsign;               // -1: H_pp = -Δ_D-Δ0 (1-atom) ; +1: CZ convention
+    double Delta0, delta0;
+    double G0, G1, Gl, Gr;      // gated decay rates
+    double wr, wz;              // trap frequencies
+    double sig[6];              // sampler standard deviations
+    double U0, w0, z0, mfac;    // mfac = m / vconst^2
+    double ecut;                // U0 (1 - 1e-2)
+    double center[2][3];
+    double c6, xi, tau;
+    double dtn, inv_dtn;        // phase-noise node spacing
+    int n_nodes;
+    int atom_motion, free_motion, laser_noise;
+    int vz_from_vy, doppler_z_legacy, rho2_mode;
+    int rows;                   // bit0: ψ0 has a |0> component, bit1: |l> component
+    double rho0[25];            // Hermitian-packed initial state (see pack order below)
+};
+
+// Hermitian packing of a 5x5 matrix into 25 reals: diag (0,1,r,p,l) then upper off-diagonals
+// (0,1),(0,r),(0,p),(0,l),(1,r),(1,p),(1,l),(r,p),(r,l),(p,l) as (re,im).
+constexpr int kNV = 50;  // packed ρ (25) + packed second moment (25)
+
+// ---------------------------------------------------------------------------------------------------
+// Beams.  Returns Ω(x,y,z) e^{iφ} / 2 (the Hamiltonian coefficient) for noise phase φ.
+// Gaussian: with s = z'/z0, q = 1+s², g = x'²/(w0² q):  A·A_phase = e^{-g(1+is)} (1+is)/q  exactly
+// (w0/w = q^-½, e^{i atan s} = (1+is) q^-½, curvature phase = -s g): one exp + one sincos, no atan.
+// ---------------------------------------------------------------------------------------------------
+CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, double phi, double* re, double* im) {
+    if (b.kind == CA_BEAM_GAUSS) {
+        double r2 = x * x + y * y;
+        double xr2, zr;
+        if (b.sn == 0.0 && b.cs == 1.0) { xr2 = r2; zr = z; }
+        else { double rp = sqrt(r2); double xr = rp * b.cs - z * b.sn; zr = rp * b.sn + z * b.cs; xr2 = xr * xr; }
+        double s = zr * b.inv_z0;
+        double iq = 1.0 / (1.0 + s * s);
+        double g = xr2 * b.inv_w0sq * iq;
+        double e = b.hO * iq * exp(-g);
+        double sn, cs;
+        sincos_d(phi - s * g, &sn, &cs);
+        *re = e * (cs - s * sn);
+        *im = e * (sn + s * cs);
+    } else if (b.kind == CA_BEAM_UNIFORM) {
+        double sn, cs;
+        sincos_d(phi, &sn, &cs);
+        *re = b.hO * cs; *im = b.hO * sn;
+    } else {
+        // flat-top HG / LG (arbitrary_beams.jl:50-81): E = Ω (w0/w) e^{-i phase0} Σ c HG HG e^{-i(i+j+1)at}
+        double s = z * b.inv_z0;
+        double q = 1.0 + s * s;
+        double iq = 1.0 / q;
+        double rq = sqrt(iq);                // w0/w
+        double iw2 = b.inv_w0sq * iq;        // 1/w^2
+        double r2 = x * x + y * y;
+        double phase0 = b.k * z + s * r2 * iw2;  // k z + (k/2) z r²/(z²+zr²) = k z + s r²/w²
+        // g1 = e^{-i atan s} = (1 - i s) rq ; g2 = g1²
+        double g1r = rq, g1i = -s * rq;
+        double Sr, Si;
+        if (b.kind == CA_BEAM_FLATTOP_HG) {
+            double g2r = g1r * g1r - g1i * g1i, g2i = 2.0 * g1r * g1i;
+            double sums[2][2];
+#pragma unroll
+            for (int ax = 0; ax < 2; ++ax) {
+                double u = ax == 0 ? x : y * b.sqz_inv;   // HG(y, w*sqz, j)
+                int nmax = ax == 0 ? b.nx : b.ny;
+                const double* cf = ax == 0 ? b.cx : b.cy;
+                double xi = sqrt(2.0 * iw2) * u;          // sqrt(2) u / w
+                double h0 = 1.0, h1 = 2.0 * xi;           // H_0, H_1
+                double pr = 1.0, pi = 0.0;                // g2^a
+                double ar = cf[0], ai = 0.0;
+                for (int a = 1; a <= nmax; ++a) {
+                    // advance Hermite two orders: H_{2a}
+                    double h2 = 2.0 * xi * h1 - 2.0 * (2 * a - 1) * h0;       // H_{2a}
+                    double h3 = 2.0 * xi * h2 - 2.0 * (2 * a) * h1;           // H_{2a+1}
+                    h0 = h2; h1 = h3;
+                    double t = pr * g2r - pi * g2i; pi = pr * g2i + pi * g2r; pr = t;
+                    ar += cf[a] * h2 * pr; ai += cf[a] * h2 * pi;
+                }
+                double ex = exp(-u * u * iw2);
+                sums[ax][0] = ar * ex; sums[ax][1] = ai * ex;
+            }
+            Sr = sums[0][0] * sums[1][0] - sums[0][1] * sums[1][1];
+            Si = sums[0][0] * sums[1][1] + sums[0][1] * sums[1][0];
+        } else {
+            double u = 2.0 * r2 * iw2;
+            double l0 = 1.0, l1 = 1.0 - u;
+            double pr = 1.0, pi = 0.0;
+            double ar = b.cx[0], ai = 0.0;
+            for (int p = 1; p <= b.nl; ++p) {
+                double lp = l1;  // L_p
+                double t = pr * g1r - pi * g1i; pi = pr * g1i + pi * g1r; pr = t;
+                ar += b.cx[p] * lp * pr; ai += b.cx[p] * lp * pi;
+                double l2 = ((2.0 * p + 1.0 - u) * l1 - p * l0) / (p + 1.0);
+                l0 = l1; l1 = l2;
+            }
+            double ex = exp(-r2 * iw2);
+            Sr = ar * ex; Si = ai * ex;
+        }
+        // E/2 = hO rq g1 S e^{i(phi - phase0)}
+        double tr = g1r * Sr - g1i * Si, ti = g1r * Si + g1i * Sr;
+        double sn, cs;
+        sincos_d(phi - phase0, &sn, &cs);
+        double f = b.hO * rq;
+        *re = f * (tr * cs - ti * sn);
+        *im = f * (tr * sn + ti * cs);
+    }
+}
+
+// IEEE operations without FMA contraction: the sampler's rejection test and the recapture indicator are
+// evaluated in the reference's operation order so that they round exactly like the oracle (-ffp-contract=off).
+#if defined(__CUDA_ARCH__)
+#define CA_MUL(a, b) __dmul_rn((a), (b))
+#define CA_ADD(a, b) __dadd_rn((a), (b))
+#define CA_DIV(a, b) __ddiv_rn((a), (b))
+#else
+#define CA_MUL(a, b) ((a) * (b))
+#define CA_ADD(a, b) ((a) + (b))
+#define CA_DIV(a, b) ((a) / (b))
+#endif
+
+// A(x,y,z,w0,z0) at θ=0, n=1: utilities.jl:27-31, literal operation order
+CA_HD double trap_A_literal(double x, double y, double z, double w0, double z0) {
+    double xt = sqrt(CA_ADD(CA_MUL(x, x), CA_MUL(y, y)));
+    double zz = CA_DIV(z, z0);
+    double w = CA_MUL(w0, sqrt(CA_ADD(1.0, CA_MUL(zz, zz))));
+    return CA_MUL(CA_DIV(w0, w), exp(-CA_DIV(CA_MUL(xt, xt), CA_MUL(w, w))));
+}
+// K = m/vconst^2 * (vx^2 + vy^2 + vz^2) / 2 : atom_sampler.jl:35-39 (mfac = m/vconst^2)
+CA_HD double kinetic_literal(double mfac, double vx, double vy, double vz) {
+    double s = CA_ADD(CA_ADD(CA_MUL(vx, vx), CA_MUL(vy, vy)), CA_MUL(vz, vz));
+    return CA_DIV(CA_MUL(mfac, s), 2.0);
+}
+
+struct SamplerConsts { double sig[6]; double U0, w0, z0, mfac, ecut; };
+
+// One atom sample (atom_sampler.jl:84-96): attempts a = 0,1,..; 3 Philox calls per attempt, Box-Muller pairs
+// (x,y),(z,vx),(vy,vz); accept iff K + U0(1 - A²) < ecut.  Returns the number of attempts (or -1).
+CA_HD int sample_atom_literal(const SamplerConsts& sc, uint64_t seed, uint64_t index, uint32_t stream, double* out) {
+    for (uint32_t a = 0; a < 100000u; ++a) {
+#pragma unroll
+        for (uint32_t c = 0; c < 3; ++c) {
+            U4 w = philox(seed, index, a * 3u + c, stream);
+            double u1 = u53_open(w.x, w.y), u2 = u53(w.z, w.w);
+            double r = sqrt(CA_MUL(-2.0, log(u1)));
+            double sn, cs;
+            sincos_d(CA_MUL(kTwoPi, u2), &sn, &cs);
+            out[2 * c] = CA_MUL(sc.sig[2 * c], CA_MUL(r, cs));
+            out[2 * c + 1] = CA_MUL(sc.sig[2 * c + 1], CA_MUL(r, sn));
+        }
+        double A = trap_A_literal(out[0], out[1], out[2], sc.w0, sc.z0);
+        double en = CA_ADD(CA_MUL(sc.U0, CA_ADD(1.0, -CA_MUL(A, A))), kinetic_literal(sc.mfac, out[3], out[4], out[5]));
+        if (en < sc.ecut) return (int)a + 1;
+    }
+    return -1;
+}
+
+// Phase-noise trace (lasernoise_sampler.jl:31-37 on the uniform node grid of rydberg_model.jl:216):
+// out[j*stride] = Σ_k a_k cos(2π f_k j dtn + φ_k), j = 0..n_nodes-1, φ_k ~ U[0,2π) from Philox (two per call) or
+// host-supplied.  Nodes are produced CH at a time with the Reinsch-stabilised cosine recurrence
+// (c += d; d += σ c; σ = -4 sin²(δ/2)): 3 flop per (node, frequency) plus one sincos per (chunk, frequency).
+template <int CH>
+CA_HD void gen_noise_trace(const double* __restrict__ f, const double* __restrict__ amp, int nf, int n_nodes, double dtn,
+                           const double* __restrict__ phases, uint64_t seed, uint64_t gi, uint32_t stream, double* __restrict__ out,
+                           int stride) {
+    for (int c0 = 0; c0 < n_nodes; c0 += CH) {
+        double acc[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) acc[j] = 0.0;
+        double t0 = c0 * dtn;
+        double ph_next = 0.0;
+        for (int k = 0; k < nf; ++k) {
+            double ph;
+            if (phases) ph = phases[k];
+            else if (k & 1) ph = ph_next;
+            else { U4 w = philox(seed, gi, (uint32_t)(k >> 1), stream); ph = kTwoPi * u53(w.x, w.y); ph_next = kTwoPi * u53(w.z, w.w); }
+            double om = kTwoPi * f[k];
+            double s0, c0v, sh, ch;
+            sincos_d(om * t0 + ph, &s0, &c0v);
+            sincos_d(0.5 * om * dtn, &sh, &ch);
+            double a = amp[k];
+            double sig = -4.0 * sh * sh;
+            double c = a * c0v;
+            double d = -2.0 * a * (s0 * ch + c0v * sh) * sh;  // c_1 - c_0 = -2 a sin(θ0 + δ/2) sin(δ/2)
+            acc[0] += c;
+#pragma unroll
+            for (int j = 1; j < CH; ++j) { c += d; d += sig * c; acc[j] += c; }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+            if (c0 + j < n_nodes) out[(size_t)(c0 + j) * stride] = acc[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lindblad right-hand side on the reduced state (exact):
+//   core block {1,r,p}: u[0..8] = n1, nr, np, Re/Im ρ1r, Re/Im ρ1p, Re/Im ρrp
+//   spectator rows x ∈ {0, l}: v = (ρx1, ρxr, ρxp) as 6 reals each (only if ψ0 has that component)
+//   populations ρ00, ρll are pure quadratures of (np, nr); ρ0l is constant.
+// H (basis 1,r,p) = [[0,0,A],[0,-dr,B*],[A*,B,-dp]], A = Ωr/2 (σ1p), B = Ωb/2 (σpr).
+// ---------------------------------------------------------------------------------------------------
+struct Coef { double Ar, Ai, Br, Bi, dp, dr; };
+struct Rates { double G0, G1, Gl, Gr, Gp, gp2, gr2; };
+
+template <int NS>
+CA_HD void lindblad_rhs(const Coef& c, const Rates& g, const double* u, double* du) {
+    const double n1 = u[0], nr = u[1], np = u[2], xr = u[3], xi = u[4], yr = u[5], yi = u[6], zr = u[7], zi = u[8];
+    const double imAy = c.Ai * yr - c.Ar * yi;  // Im(A conj(y))
+    const double imBz = c.Br * zi + c.Bi * zr;  // Im(B z)
+    du[0] = 2.0 * imAy + g.G1 * np;
+    du[1] = -2.0 * imBz - g.Gr * nr;
+    du[2] = 2.0 * (imBz - imAy) - g.Gp * np;
+    {   // ρ1r : W = A z* - y B + dr x ; dρ = -iW - Γr/2 ρ
+        double Wr = c.Ar * zr + c.Ai * zi - yr * c.Br + yi * c.Bi + c.dr * xr;
+        double Wi = c.Ai * zr - c.Ar * zi - yr * c.Bi - yi * c.Br + c.dr * xi;
+        du[3] = Wi - g.gr2 * xr; du[4] = -Wr - g.gr2 * xi;
+    }
+    {   // ρ1p : W = A (np - n1) - x B* + dp y
+        double dn = np - n1;
+        double Wr = c.Ar * dn - xr * c.Br - xi * c.Bi + c.dp * yr;
+        double Wi = c.Ai * dn - xi * c.Br + xr * c.Bi + c.dp * yi;
+        du[5] = Wi - g.gp2 * yr; du[6] = -Wr - g.gp2 * yi;
+    }
+    {   // ρrp : W = B* (np - nr) - x* A + (dp - dr) z
+        double dm = np - nr, dpr = c.dp - c.dr, gz = g.gp2 + g.gr2;
+        double Wr = c.Br * dm - xr * c.Ar - xi * c.Ai + dpr * zr;
+        double Wi = -c.Bi * dm - xr * c.Ai + xi * c.Ar + dpr * zi;
+        du[7] = Wi - gz * zr; du[8] = -Wr - gz * zi;
+    }
+#pragma unroll
+    for (int o = 9; o + 6 <= NS; o += 6) {  // spectator rows: dv_j = i Σ_k v_k H_kj - γ_j/2 v_j
+        const double v1r = u[o], v1i = u[o + 1], vrr = u[o + 2], vri = u[o + 3], vpr = u[o + 4], vpi = u[o + 5];
+        // dv1 = i vp A*
+        double t1r = vpr * c.Ar + vpi * c.Ai, t1i = vpi * c.Ar - vpr * c.Ai;  // vp A*
+        du[o] = -t1i; du[o + 1] = t1r;
+        // dvr = i(-dr vr + vp B) - Γr/2 vr
+        double t2r = -c.dr * vrr + vpr * c.Br - vpi * c.Bi, t2i = -c.dr * vri + vpr * c.Bi + vpi * c.Br;
+        du[o + 2] = -t2i - g.gr2 * vrr; du[o + 3] = t2r - g.gr2 * vri;
+        // dvp = i(v1 A + vr B* - dp vp) - Γp/2 vp
+        double t3r = v1r * c.Ar - v1i * c.Ai + vrr * c.Br + vri * c.Bi - c.dp * vpr;
+        double t3i = v1r * c.Ai + v1i * c.Ar + vri * c.Br - vrr * c.Bi - c.dp * vpi;
+        du[o + 4] = -t3i - g.gp2 * vpr; du[o + 5] = t3r - g.gp2 * vpi;
+    }
+}
+
+// Dormand-Prince 5(4) tableau and Hairer's dense-output weights (see oracle).
+namespace dp {
+constexpr double a21 = 1.0 / 5.0, a31 = 3.0 / 40.0, a32 = 9.0 / 40.0, a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0,
+                 a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0, a54 = -212.0 / 729.0,
+                 a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0, a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0,
+                 b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+constexpr double c2 = 0.2, c3 = 0.3, c4 = 0.8, c5 = 8.0 / 9.0;
+constexpr double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0, e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0, d4 = -10690763975.0 / 1880347072.0,
+                 d5 = 701980252875.0 / 199316789632.0, d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+}  // namespace dp
+
+struct OdeOpts {
+    double rtol, atol, dt0, dtmax;
+    long long maxiters;
+    int adaptive, dense;
+};
+
+// Per-trajectory integrator state. NS = 9 (+6 per spectator row).
+template <int NS>
+struct Lane1 {
+    // trajectory
+    double x0, y0, z0, vx, vy, vz, vzq;  // vzq: velocity used for "Vz" (vy when the B1 quirk is on)
+    double dpc, drc;                      // constant detunings (free motion) incl. Δ0, δ0
+    // noise cache
+    const double* tab;                    // table base for this lane: tab[(trace*n_nodes + node)*stride]
+    int stride, jc;
+    double pr0, prs, pb0, pbs, tj;
+    // integrator
+    double t, h, dt, lnq_old;
+    double y[NS], k1[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS], un[NS];
+    double P[2], Pn[2], g1[2], g7[2], SD[2];
+    Coef cf1;                             // coefficients at t (FSAL partner of k1)
+    Coef cf7;
+    long long iters;
+    int n_rhs, n_acc, n_rej;
+    int status;
+
+    CA_HD void coefficients(const DevModel& m, double tt, Coef& c) {
+        double X, Y, Z, Vx, Vz;
+        if (m.free_motion) {
+            X = x0 + vx * tt; Y = y0 + vy * tt; Z = z0 + vz * tt;
+            c.dp = dpc; c.dr = drc;
+        } else {  // R, V: atom_sampler.jl:125-143
+            double sr, cr, sz, cz;
+            sincos_d(m.wr * tt, &sr, &cr);
+            sincos_d(m.wz * tt, &sz, &cz);
+            X = x0 * cr + vx / m.wr * sr; Y = y0 * cr + vy / m.wr * sr; Z = z0 * cz + vz / m.wz * sz;
+            Vx = vx * cr - x0 * m.wr * sr;
+            Vz = vzq * cz - z0 * m.wz * sz;
+            double Dd = m.aDx * Vx + m.aDz * Vz, dd = m.bDx * Vx + m.bDz * Vz;
+            if (m.doppler_z_legacy) { double Vzt = vz * cz - z0 * m.wz * sz; Dd = m.aDz * Vzt; dd = m.bDz * Vzt; }
+            c.dp = m.Delta0 - m.dsign * Dd; c.dr = m.delta0 - m.dsign * dd;
+        }
+        double pr = 0.0, pb = 0.0;
+        if (tab) {
+            int j = (int)(tt * m.inv_dtn);
+            j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+            if (j != jc) {
+                jc = j;
+                tj = j * m.dtn;
+                const double* p = tab + (size_t)j * stride;
+                double a0 = p[0], a1 = p[stride];
+                const double* q = p + (size_t)m.n_nodes * stride;
+                double b0 = q[0], b1 = q[stride];
+                pr0 = a0; prs = (a1 - a0) * m.inv_dtn; pb0 = b0; pbs = (b1 - b0) * m.inv_dtn;
+            }
+            double w = tt - tj;
+            pr = pr0 + w * prs; pb = pb0 + w * pbs;
+        }
+        if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
+        beam_half_omega(m.red, X, Y, Z, pr, &c.Ar, &c.Ai);
+        beam_half_omega(m.blue, X, Y, Z, pb, &c.Br, &c.Bi);
+    }
+
+    // error-norm contribution helpers (DiffEqBase: |err| / (atol + rtol max(|u0|,|u1|)), complex modulus)
+    static CA_HD double nrm_real(double e, double a, double b, double atol, double rtol) {
+        double sc = atol + rtol * fmax(fabs(a), fabs(b));
+        double r = e / sc;
+        return r * r;
+    }
+    static CA_HD double nrm_cplx(double er, double ei, double ar, double ai, double br, double bi, double atol, double rtol) {
+        double sc = atol + rtol * sqrt(fmax(ar * ar + ai * ai, br * br + bi * bi));
+        return 2.0 * (er * er + ei * ei) / (sc * sc);  // both (i,j) and (j,i) entries of the full matrix
+    }
+
+    CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
+                    double t0) {
+        if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
+        else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
+        vzq = m.vz_from_vy ? vy : vz;
+        {
+            double Dd = m.aDx * vx + m.aDz * vzq, dd = m.bDx * vx + m.bDz * vzq;
+            if (m.doppler_z_legacy) { Dd = m.aDz * vz; dd = m.bDz * vz; }
+            dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
+        }
+        tab = table; stride = tstride; jc = -1; pr0 = prs = pb0 = pbs = tj = 0.0;
+        // initial state
+        y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
+        y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
+        y[5] = m.rho0[5 + 10]; y[6] = m.rho0[5 + 11];    // (1,p)
+        y[7] = m.rho0[5 + 14]; y[8] = m.rho0[5 + 15];    // (r,p)
+        if (NS >= 15) {
+            if (m.rows & 1) {  // row 0: (0,1),(0,r),(0,p)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) y[9 + q] = m.rho0[5 + q];
+            } else {           // only row l present: ρ_l1 = conj ρ_1l etc.
+                y[9] = m.rho0[5 + 12]; y[10] = -m.rho0[5 + 13]; y[11] = m.rho0[5 + 16]; y[12] = -m.rho0[5 + 17];
+                y[13] = m.rho0[5 + 18]; y[14] = -m.rho0[5 + 19];
+            }
+        }
+        if (NS >= 21) {
+            y[15] = m.rho0[5 + 12]; y[16] = -m.rho0[5 + 13]; y[17] = m.rho0[5 + 16]; y[18] = -m.rho0[5 + 17];
+            y[19] = m.rho0[5 + 18]; y[20] = -m.rho0[5 + 19];
+        }
+        P[0] = m.rho0[0]; P[1] = m.rho0[4];
+        t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; status = 0;
+        lnq_old = log(1e-4);
+        coefficients(m, t, cf1);
+        lindblad_rhs<NS>(cf1, g, y, k1);
+        g1[0] = g.G0 * y[2]; g1[1] = g.Gl * y[2] + g.Gr * y[1];
+        n_rhs = 1;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) un[i] = y[i];
+        Pn[0] = P[0]; Pn[1] = P[1];
+        dt = oo.dt0;
+        if (dt <= 0.0) {  // OrdinaryDiffEq ode_determine_initdt (Hairer hinit), norm over all 25 matrix entries
+            double d0 = 0.0, d1 = 0.0;
+            auto acc_r = [&](double a, double fa) { double sk = oo.atol + fabs(a) * oo.rtol; d0 += (a / sk) * (a / sk); d1 += (fa / sk) * (fa / sk); };
+            auto acc_c = [&](double ar, double ai, double fr, double fi) {
+                double sk = oo.atol + sqrt(ar * ar + ai * ai) * oo.rtol;
+                d0 += 2.0 * (ar * ar + ai * ai) / (sk * sk); d1 += 2.0 * (fr * fr + fi * fi) / (sk * sk);
+            };
+            acc_r(y[0], k1[0]); acc_r(y[1], k1[1]); acc_r(y[2], k1[2]); acc_r(P[0], g1[0]); acc_r(P[1], g1[1]);
+#pragma unroll
+            for (int i = 3; i < NS; i += 2) acc_c(y[i], y[i + 1], k1[i], k1[i + 1]);
+            {   // the constant ρ0l coherence contributes to d0 only
+                double ar = m.rho0[5 + 6], ai = m.rho0[5 + 7];
+                double sk = oo.atol + sqrt(ar * ar + ai * ai) * oo.rtol;
+                d0 += 2.0 * (ar * ar + ai * ai) / (sk * sk);
+            }
+            d0 = sqrt(d0 / 25.0); d1 = sqrt(d1 / 25.0);
+            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            dt0 = fmin(dt0, oo.dtmax);
+            double us[NS], f1[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) us[i] = y[i] + dt0 * k1[i];
+            Coef c2;
+            coefficients(m, t + dt0, c2);
+            lindblad_rhs<NS>(c2, g, us, f1);
+            n_rhs++;
+            double d2 = 0.0;
+            auto dif_r = [&](double a, double df) { double sk = oo.atol + fabs(a) * oo.rtol; d2 += (df / sk) * (df / sk); };
+            dif_r(y[0], f1[0] - k1[0]); dif_r(y[1], f1[1] - k1[1]); dif_r(y[2], f1[2] - k1[2]);
+            dif_r(P[0], g.G0 * us[2] - g1[0]); dif_r(P[1], g.Gl * us[2] + g.Gr * us[1] - g1[1]);
+#pragma unroll
+            for (int i = 3; i < NS; i += 2) {
+                double sk = oo.atol + sqrt(y[i] * y[i] + y[i + 1] * y[i + 1]) * oo.rtol;
+                double dr = f1[i] - k1[i], di = f1[i + 1] - k1[i + 1];
+                d2 += 2.0 * (dr * dr + di * di) / (sk * sk);
+            }
+            d2 = sqrt(d2 / 25.0) / dt0;
+            double mx = fmax(d1, d2);
+            double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+            dt = fmin(100.0 * dt0, fmin(dt1, oo.dtmax));
+        }
+    }
+
+    // time at the end of the last accepted step (== t before the first step)
+    CA_HD double t_new() const { return t + h; }
+
+    // Commit the pending accepted step (FSAL) and attempt one new step towards `tstop`.
+    CA_HD void attempt(const DevModel& m, const Rates& g, const OdeOpts& oo, double tstop) {
+        if (h != 0.0) {  // commit: y <- un, k1 <- k7, t <- t+h
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { y[i] = un[i]; k1[i] = k7[i]; }
+            P[0] = Pn[0]; P[1] = Pn[1]; g1[0] = g7[0]; g1[1] = g7[1];
+            cf1 = cf7;
+            t = tcommit;
+            h = 0.0;
+        }
+        if (++iters > oo.maxiters) { status = CA_ERR_MAXITERS; return; }
+        double hh = fmin(dt, oo.dtmax);
+        bool clipped = false;
+        if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
+        double us[NS], k2[NS];
+        Coef c;
+        double SB0, SB1, SE0, SE1, SD0, SD1, gg0, gg1;
+        // stage 1 contributions of the population quadratures
+        SB0 = dp::b1 * g1[0]; SB1 = dp::b1 * g1[1]; SE0 = dp::e1 * g1[0]; SE1 = dp::e1 * g1[1]; SD0 = dp::d1 * g1[0]; SD1 = dp::d1 * g1[1];
+        // stage 2
+#pragma unroll
+        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a21 * k1[i]);
+        coefficients(m, t + dp::c2 * hh, c);
+        lindblad_rhs<NS>(c, g, us, k2);
+        // stage 3
+#pragma unroll
+        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a31 * k1[i] + dp::a32 * k2[i]);
+        coefficients(m, t + dp::c3 * hh, c);
+        lindblad_rhs<NS>(c, g, us, k3);
+        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
+        SB0 += dp::b3 * gg0; SB1 += dp::b3 * gg1; SE0 += dp::e3 * gg0; SE1 += dp::e3 * gg1; SD0 += dp::d3 * gg0; SD1 += dp::d3 * gg1;
+        // stage 4
+#pragma unroll
+        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a41 * k1[i] + dp::a42 * k2[i] + dp::a43 * k3[i]);
+        coefficients(m, t + dp::c4 * hh, c);
+        lindblad_rhs<NS>(c, g, us, k4);
+        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
+        SB0 += dp::b4 * gg0; SB1 += dp::b4 * gg1; SE0 += dp::e4 * gg0; SE1 += dp::e4 * gg1; SD0 += dp::d4 * gg0; SD1 += dp::d4 * gg1;
+        // stage 5
+#pragma unroll
+        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a51 * k1[i] + dp::a52 * k2[i] + dp::a53 * k3[i] + dp::a54 * k4[i]);
+        coefficients(m, t + dp::c5 * hh, c);
+        lindblad_rhs<NS>(c, g, us, k5);
+        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
+        SB0 += dp::b5 * gg0; SB1 += dp::b5 * gg1; SE0 += dp::e5 * gg0; SE1 += dp::e5 * gg1; SD0 += dp::d5 * gg0; SD1 += dp::d5 * gg1;
+        // stage 6 (t + h); its coefficients are shared with stage 7 and with the next step's stage 1
+        double tn = clipped ? tstop : t + hh;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+            us[i] = y[i] + hh * (dp::a61 * k1[i] + dp::a62 * k2[i] + dp::a63 * k3[i] + dp::a64 * k4[i] + dp::a65 * k5[i]);
+        coefficients(m, tn, cf7);
+        lindblad_rhs<NS>(cf7, g, us, k6);
+        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
+        SB0 += dp::b6 * gg0; SB1 += dp::b6 * gg1; SE0 += dp::e6 * gg0; SE1 += dp::e6 * gg1; SD0 += dp::d6 * gg0; SD1 += dp::d6 * gg1;
+        // new state and stage 7
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+            un[i] = y[i] + hh * (dp::b1 * k1[i] + dp::b3 * k3[i] + dp::b4 * k4[i] + dp::b5 * k5[i] + dp::b6 * k6[i]);
+        lindblad_rhs<NS>(cf7, g, un, k7);
+        g7[0] = g.G0 * un[2]; g7[1] = g.Gl * un[2] + g.Gr * un[1];
+        SE0 += dp::e7 * g7[0]; SE1 += dp::e7 * g7[1]; SD0 += dp::d7 * g7[0]; SD1 += dp::d7 * g7[1];
+        Pn[0] = P[0] + hh * SB0; Pn[1] = P[1] + hh * SB1;
+        n_rhs += 6;
+        bool accept = true;
+        if (oo.adaptive) {
+            double s = nrm_real(hh * SE0, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(hh * SE1, P[1], Pn[1], oo.atol, oo.rtol);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double e = hh * (dp::e1 * k1[i] + dp::e3 * k3[i] + dp::e4 * k4[i] + dp::e5 * k5[i] + dp::e6 * k6[i] + dp::e7 * k7[i]);
+                s += nrm_real(e, y[i], un[i], oo.atol, oo.rtol);
+            }
+#pragma unroll
+            for (int i = 3; i < NS; i += 2) {
+                double er = hh * (dp::e1 * k1[i] + dp::e3 * k3[i] + dp::e4 * k4[i] + dp::e5 * k5[i] + dp::e6 * k6[i] + dp::e7 * k7[i]);
+                double ei = hh * (dp::e1 * k1[i + 1] + dp::e3 * k3[i + 1] + dp::e4 * k4[i + 1] + dp::e5 * k5[i + 1] + dp::e6 * k6[i + 1] + dp::e7 * k7[i + 1]);
+                s += nrm_cplx(er, ei, y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
+            }
+            double EEst2 = s * (1.0 / 25.0);
+            if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; return; }
+            // PI controller: q = EEst^β1 / qold^β2 / γ clipped to [1/qmax, 1/qmin]; β1 = 0.17, β2 = 0.04
+            const double beta1 = 0.17, beta2 = 0.04, gam = 0.9, qmin = 0.2, qmax = 10.0;
+            const double ln_qoldinit = -9.210340371976182;  // log(1e-4)
+            double q, lnE = 0.0;
+            if (EEst2 == 0.0) q = 1.0 / qmax;
+            else { lnE = 0.5 * log(EEst2); q = exp(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
+            if (EEst2 <= 1.0) {
+                lnq_old = (EEst2 == 0.0) ? ln_qoldinit : fmax(lnE, ln_qoldinit);
+                double prop = hh / q;
+                dt = clipped ? fmax(dt, prop) : prop;
+            } else {
+                accept = false;
+                double q11 = exp(beta1 * lnE);
+                dt = hh / fmin(1.0 / qmin, q11 / gam);
+                n_rej++;
+                if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; return; }
+            }
+        } else {
+            dt = oo.dt0;
+        }
+        if (accept) {
+            n_acc++;
+            h = hh; tcommit = tn;
+            SD[0] = SD0; SD[1] = SD1;
+        }
+    }
+
+    double tcommit;
+
+    // State at time T inside the last accepted step [t, t+h] (Hairer contd5), Hermitian-packed ρ into out[0..24].
+    CA_HD void state_at(const DevModel& m, double T, double* out) const {
+        double s[NS], p0, p1;
+        if (h == 0.0 || T >= tcommit) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) s[i] = un[i];
+            p0 = Pn[0]; p1 = Pn[1];
+        } else {
+            double th = (T - t) / h, th1 = 1.0 - th;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                double r2 = un[i] - y[i];
+                double r3 = h * k1[i] - r2;
+                double r4 = r2 - h * k7[i] - r3;
+                double r5 = h * (dp::d1 * k1[i] + dp::d3 * k3[i] + dp::d4 * k4[i] + dp::d5 * k5[i] + dp::d6 * k6[i] + dp::d7 * k7[i]);
+                s[i] = y[i] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+            }
+            {
+                double r2 = Pn[0] - P[0], r3 = h * g1[0] - r2, r4 = r2 - h * g7[0] - r3, r5 = h * SD[0];
+                p0 = P[0] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+                r2 = Pn[1] - P[1]; r3 = h * g1[1] - r2; r4 = r2 - h * g7[1] - r3; r5 = h * SD[1];
+                p1 = P[1] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 25; ++i) out[i] = 0.0;
+        out[0] = p0; out[1] = s[0]; out[2] = s[1]; out[3] = s[2]; out[4] = p1;
+        out[5 + 8] = s[3]; out[5 + 9] = s[4]; out[5 + 10] = s[5]; out[5 + 11] = s[6]; out[5 + 14] = s[7]; out[5 + 15] = s[8];
+        out[5 + 6] = m.rho0[5 + 6]; out[5 + 7] = m.rho0[5 + 7];  // ρ0l is constant
+        if (NS >= 15) {
+            if (m.rows & 1) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) out[5 + q] = s[9 + q];
+            } else {
+                out[5 + 12] = s[9]; out[5 + 13] = -s[10]; out[5 + 16] = s[11]; out[5 + 17] = -s[12]; out[5 + 18] = s[13]; out[5 + 19] = -s[14];
+            }
+        }
+        if (NS >= 21) {
+            out[5 + 12] = s[15]; out[5 + 13] = -s[16]; out[5 + 16] = s[17]; out[5 + 17] = -s[18]; out[5 + 18] = s[19]; out[5 + 19] = -s[20];
+        }
+    }
+};
+
+// Second moment of a Hermitian-packed 5x5 matrix: packed ρ·ρ (CA_RHO2_MATSQ) or |ρ_ij|² (CA_RHO2_ABS2).
+// FULL=false: only the block structure of the rows-free case (ρ00, ρll scalars + 3x3 core) is non-zero.
+template <bool FULL>
+CA_HD void second_moment(const double* p, int mode, double* o) {
+    // unpack upper triangle: idx(a,b), a<b
+    constexpr int off[5][5] = {{-1, 0, 1, 2, 3}, {-1, -1, 4, 5, 6}, {-1, -1, -1, 7, 8}, {-1, -1, -1, -1, 9}, {-1, -1, -1, -1, -1}};
+    if (mode == CA_RHO2_ABS2) {
+#pragma unroll
+        for (int a = 0; a < 5; ++a) o[a] = p[a] * p[a];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) { o[5 + 2 * q] = p[5 + 2 * q] * p[5 + 2 * q] + p[6 + 2 * q] * p[6 + 2 * q]; o[6 + 2 * q] = 0.0; }
+        return;
+    }
+    double re[5][5], im[5][5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            if (a == b) { re[a][b] = p[a]; im[a][b] = 0.0; }
+            else if (a < b) { re[a][b] = p[5 + 2 * off[a][b]]; im[a][b] = p[6 + 2 * off[a][b]]; }
+            else { re[a][b] = p[5 + 2 * off[b][a]]; im[a][b] = -p[6 + 2 * off[b][a]]; }
+        }
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = a; b < 5; ++b) {
+            bool core_ab = (a >= 1 && a <= 3 && b >= 1 && b <= 3);
+            bool live = FULL || core_ab || (a == b);
+            double sr = 0.0, si = 0.0;
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    bool kin = FULL || (core_ab ? (k >= 1 && k <= 3) : (k == a));
+                    if (kin) { sr += re[a][k] * re[k][b] - im[a][k] * im[k][b]; si += re[a][k] * im[k][b] + im[a][k] * re[k][b]; }
+                }
+            }
+            if (a == b) o[a] = sr;
+            else { o[5 + 2 * off[a][b]] = sr; o[6 + 2 * off[a][b]] = si; }
+        }
+}
+
+}  // namespace ca

@@ -1,0 +1,708 @@
+// ca_kernels.cu -- sm_100a kernels and the C ABI (include/coldatoms_b200.h) of the one-atom path,
+// the samplers and release-recapture.  The two-atom kernel lives in ca_lindblad2.cu.
+//
+// Kernels (SURVEY §8a "Kernel <-> reference mapping"):
+//   k_lindblad1<NS,SWEEP>  K1+K2+K3 fused: Philox atom sampler, phase-noise table generation and the DP5
+//                          Lindblad integrator, one trajectory per thread, state in registers; observables
+//                          reduced by warp shuffles and accumulated with fp64 RED atomics.
+//   k_finalize             K6: packed sums -> full column-major complex matrices, scaled by 1/N.
+//   k_release_recapture    K5.
+//   k_sample_atoms, k_phase_noise, k_eval_beam   exposed samplers / beam code for tests and helpers.
+//   k_dfma_peak            FP64 FMA-chain microbenchmark (roofline denominator).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ca_host.h"
+#include "ca_device.cuh"
+
+namespace ca {
+
+// ----------------------------------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K1+K2+K3: fused one-atom ensemble kernel
+// ----------------------------------------------------------------------------------------------------
+constexpr int kThreads1 = 128;
+constexpr int kNoiseChunk = 64;
+
+struct R1Params {
+    DevModel model;            // single-point runs: lives in the constant bank with the other params
+    const DevModel* models;    // sweeps: one per point
+    const double* tspans;      // [n_points][nt]
+    const double* samples;     // NULL or [n_points*n_per_point][6]
+    const double* phases_red;  // NULL or [.][nf]
+    const double* phases_blue;
+    const double* f;           // [nf]
+    const double* amp_red;
+    const double* amp_blue;
+    const double* nz_ch;       // cos(π f dtn) per frequency (single-point) -- unused for sweeps
+    const double* nz_sh;
+    double* scratch;           // per-warp phase-noise tables: [warps][2][n_nodes][32]
+    double* accum;             // [n_points][nt][kNV]
+    unsigned long long* counters;  // n_rhs, n_accept, n_reject, n_attempts, status(max |err|)
+    OdeOpts ode;
+    long long n_per_point, traj_offset, groups_per_point, n_groups;
+    unsigned long long seed;
+    int n_points, nt, nf, n_nodes_max;
+};
+
+template <int NS, bool SWEEP>
+__global__ void __launch_bounds__(kThreads1, 2) k_lindblad1(const __grid_constant__ R1Params P) {
+    __shared__ DevModel sm_models[SWEEP ? kThreads1 / 32 : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wg = (long long)blockIdx.x * (kThreads1 / 32) + warp;
+    const long long W = (long long)gridDim.x * (kThreads1 / 32);
+    long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0;
+    int worst = 0;
+    for (long long g = wg; g < P.n_groups; g += W) {
+        const int pt = (int)(g / P.groups_per_point);
+        const long long il = (g - (long long)pt * P.groups_per_point) * 32 + lane;
+        const bool valid = il < P.n_per_point;
+        const long long li = (long long)pt * P.n_per_point + il;  // index into host-supplied arrays
+        const uint64_t gi = (uint64_t)(P.traj_offset + li);
+        if (SWEEP) {
+            __syncwarp();
+            const int nw = (int)(sizeof(DevModel) / sizeof(double));
+            const double* src = reinterpret_cast<const double*>(P.models + pt);
+            double* dst = reinterpret_cast<double*>(&sm_models[warp]);
+            for (int q = lane; q < nw; q += 32) dst[q] = src[q];
+            __syncwarp();
+        }
+        const DevModel* mp;
+        if constexpr (SWEEP) mp = &sm_models[warp]; else mp = &P.model;
+        const DevModel& m = *mp;
+        Rates rt;
+        rt.G0 = m.G0; rt.G1 = m.G1; rt.Gl = m.Gl; rt.Gr = m.Gr; rt.Gp = m.G0 + m.G1 + m.Gl; rt.gp2 = 0.5 * rt.Gp; rt.gr2 = 0.5 * m.Gr;
+        const double* tsp = P.tspans + (size_t)pt * P.nt;
+        // ---- K1: atom sample
+        double smp[6] = {0, 0, 0, 0, 0, 0};
+        if (valid && m.atom_motion) {
+            if (P.samples) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) smp[q] = P.samples[li * 6 + q];
+            } else {
+                SamplerConsts sc;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) sc.sig[q] = m.sig[q];
+                sc.U0 = m.U0; sc.w0 = m.w0; sc.z0 = m.z0; sc.mfac = m.mfac; sc.ecut = m.ecut;
+                int att = sample_atom_literal(sc, P.seed, gi, 0u, smp);
+                if (att < 0) worst = max(worst, -CA_ERR_NONFINITE); else tot_att += att;
+            }
+        }
+        // ---- K2: phase-noise tables for this warp's 32 trajectories
+        double* tab = nullptr;
+        if (m.laser_noise && P.nf > 0) {
+            tab = P.scratch + (size_t)wg * 2 * P.n_nodes_max * 32 + lane;
+            if (valid) {
+                gen_noise_trace<kNoiseChunk>(P.f, P.amp_red, P.nf, m.n_nodes, m.dtn, P.phases_red ? P.phases_red + li * P.nf : nullptr,
+                                             P.seed, gi, 2u, tab, 32);
+                gen_noise_trace<kNoiseChunk>(P.f, P.amp_blue, P.nf, m.n_nodes, m.dtn, P.phases_blue ? P.phases_blue + li * P.nf : nullptr,
+                                             P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32);
+            }
+            __syncwarp();
+        }
+        // ---- K3: integrate
+        Lane1<NS> L;
+        L.init(m, rt, P.ode, smp, tab, 32, tsp[0]);
+        const double tend = tsp[P.nt - 1];
+        double* acc_pt = P.accum + (size_t)pt * P.nt * kNV;
+        for (int j = 0; j < P.nt; ++j) {
+            const double T = tsp[j];
+            const double tstop = P.ode.dense ? tend : T;
+            while (true) {
+                const bool need = valid && L.status == 0 && L.tcommit < T;
+                if (!__any_sync(0xffffffffu, need)) break;
+                if (need) L.attempt(m, rt, P.ode, tstop);
+            }
+            double v[kNV];
+            L.state_at(m, T, v);
+            second_moment<(NS > 9)>(v, m.rho2_mode, v + 25);
+            const bool ok = valid && L.status == 0;
+            double mine0 = 0.0, mine1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < kNV; ++q) {
+                double s = warp_sum(ok ? v[q] : 0.0);
+                if (q < 32) { if (lane == q) mine0 = s; }
+                else { if (lane == q - 32) mine1 = s; }
+            }
+            atomicAdd(acc_pt + (size_t)j * kNV + lane, mine0);
+            if (lane < kNV - 32) atomicAdd(acc_pt + (size_t)j * kNV + 32 + lane, mine1);
+        }
+        if (valid) { tot_rhs += L.n_rhs; tot_acc += L.n_acc; tot_rej += L.n_rej; if (L.status) worst = max(worst, -L.status); }
+    }
+    // ---- statistics
+    tot_rhs = (long long)warp_sum((double)tot_rhs); tot_acc = (long long)warp_sum((double)tot_acc);
+    tot_rej = (long long)warp_sum((double)tot_rej); tot_att = (long long)warp_sum((double)tot_att);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (lane == 0) {
+        atomicAdd(P.counters + 0, (unsigned long long)tot_rhs);
+        atomicAdd(P.counters + 1, (unsigned long long)tot_acc);
+        atomicAdd(P.counters + 2, (unsigned long long)tot_rej);
+        atomicAdd(P.counters + 3, (unsigned long long)tot_att);
+        if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
+    }
+}
+
+// K6: packed Hermitian sums -> column-major complex d x d matrices scaled by `scale`.
+__global__ void k_finalize5(const double* __restrict__ accum, long long n_mats, double scale, double* __restrict__ rho, double* __restrict__ rho2) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mats * 2) return;
+    const long long mat = i >> 1;
+    const int which = (int)(i & 1);
+    const double* p = accum + mat * kNV + which * 25;
+    double* o = (which ? rho2 : rho) + mat * 50;
+    const int off[5][5] = {{-1, 0, 1, 2, 3}, {-1, -1, 4, 5, 6}, {-1, -1, -1, 7, 8}, {-1, -1, -1, -1, 9}, {-1, -1, -1, -1, -1}};
+    for (int b = 0; b < 5; ++b)
+        for (int a = 0; a < 5; ++a) {
+            double re, im;
+            if (a == b) { re = p[a]; im = 0.0; }
+            else if (a < b) { re = p[5 + 2 * off[a][b]]; im = p[6 + 2 * off[a][b]]; }
+            else { re = p[5 + 2 * off[b][a]]; im = -p[6 + 2 * off[b][a]]; }
+            o[2 * (a + 5 * b)] = re * scale; o[2 * (a + 5 * b) + 1] = im * scale;
+        }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K5: release and recapture (basic_experiments.jl:25-47, :72-81)
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_release_recapture(SamplerConsts sc, const double* __restrict__ tspan, int nt, long long n,
+                                                           long long traj_offset, unsigned long long seed, double thresh,
+                                                           const double* __restrict__ samples, unsigned long long* __restrict__ counts,
+                                                           unsigned char* __restrict__ indicators, unsigned long long* __restrict__ attempts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    double c[6] = {0, 0, 0, 0, 0, 0};
+    int att = 0;
+    if (valid) {
+        if (samples) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) c[q] = samples[i * 6 + q];
+        } else att = sample_atom_literal(sc, seed, (uint64_t)(traj_offset + i), 0u, c);
+    }
+    const double kin = kinetic_literal(sc.mfac, c[3], c[4], c[5]);
+    bool alive = valid;
+    for (int j = 0; j < nt; ++j) {
+        if (alive) {
+            const double t = tspan[j];
+            const double x = __dadd_rn(c[0], __dmul_rn(c[3], t)), y = __dadd_rn(c[1], __dmul_rn(c[4], t)), z = __dadd_rn(c[2], __dmul_rn(c[5], t));
+            const double A = trap_A_literal(x, y, z, sc.w0, sc.z0);
+            const double pot = __dmul_rn(sc.U0, __dadd_rn(1.0, -__dmul_rn(A, A)));
+            alive = __dadd_rn(kin, pot) < thresh;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (indicators && valid) indicators[i * nt + j] = alive ? 1 : 0;
+        if (lane == 0 && mask) atomicAdd(counts + j, (unsigned long long)__popc(mask));
+        if (!mask && !indicators) break;
+    }
+    if (attempts) {
+        double a = warp_sum((double)att);
+        if (lane == 0 && a > 0) atomicAdd(attempts, (unsigned long long)a);
+    }
+}
+
+__global__ void k_sample_atoms(SamplerConsts sc, long long n, long long traj_offset, unsigned long long seed, unsigned stream,
+                               double* __restrict__ out, unsigned long long* __restrict__ attempts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c[6];
+    int att = sample_atom_literal(sc, seed, (uint64_t)(traj_offset + i), stream, c);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) out[i * 6 + q] = c[q];
+    if (att > 0) atomicAdd(attempts, (unsigned long long)att);
+}
+
+// ϕ tables: one thread per trajectory, output phi[i][node] (lasernoise_sampler.jl:31-37 on a uniform grid)
+__global__ void __launch_bounds__(128) k_phase_noise(const double* __restrict__ f, const double* __restrict__ amp, int nf, int n_nodes, double dtn,
+                                                     const double* __restrict__ phases, long long n, long long traj_offset,
+                                                     unsigned long long seed, unsigned stream, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gen_noise_trace<kNoiseChunk>(f, amp, nf, n_nodes, dtn, phases ? phases + i * nf : nullptr, seed, (uint64_t)(traj_offset + i), stream,
+                                 out + (size_t)i * n_nodes, 1);
+}
+
+__global__ void k_eval_beam(DevBeam b, const double* __restrict__ xyz, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double re, im;
+    beam_half_omega(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0, &re, &im);
+    out[2 * i] = 2.0 * re; out[2 * i + 1] = 2.0 * im;
+}
+
+// FP64 FMA-chain microbenchmark: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) out[0] = s;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------------
+#define CA_CUDA(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess) {                                                                            \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                                  \
+            return CA_ERR_CUDA;                                                                             \
+        }                                                                                                   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CA_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return CA_ERR_NOMEM; }
+        cap = want;
+        return CA_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace ca
+
+struct ca_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ca::DevBuf scratch, accum, out, counters, in_samples, in_ph[4], in_f, in_models, in_tspan, misc;
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+namespace ca {
+
+static int ensure_pinned(ca_ctx* c, size_t bytes) {
+    if (bytes <= c->pinned_cap) return CA_OK;
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr; c->pinned_cap = 0;
+    CA_CUDA(cudaMallocHost(&c->pinned, bytes + bytes / 4));
+    c->pinned_cap = bytes + bytes / 4;
+    return CA_OK;
+}
+
+static int upload(ca_ctx* c, DevBuf& b, const void* host, size_t bytes) {
+    int rc = b.ensure(bytes);
+    if (rc) return rc;
+    CA_CUDA(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return CA_OK;
+}
+
+cudaStream_t ctx_stream(ca_ctx* c) { return c->stream; }
+int ctx_sm_count(ca_ctx* c) { return c->sm_count; }
+
+template <int NS, bool SWEEP>
+static int launch_lindblad1(ca_ctx* c, const R1Params& P, int grid) {
+    k_lindblad1<NS, SWEEP><<<grid, kThreads1, 0, c->stream>>>(P);
+    CA_CUDA(cudaGetLastError());
+    return CA_OK;
+}
+
+// Shared driver of ca_rydberg1_run (n_points = 1) and ca_rydberg1_sweep.
+static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const double* tspans, int nt, int n_points,
+                  long long n_per_point, long long traj_offset, long long n_total, uint64_t seed, const double* samples,
+                  const double* phases_red, const double* phases_blue, const double* f, const double* amp_red,
+                  const double* amp_blue, int nf, const ca_ode_opts* ode, int out_flags, bool last_only, double* rho, double* rho2,
+                  ca_stats* stats) {
+    if (!c) { set_error("null context"); return CA_ERR_ARG; }
+    if (!models || !psi0s || !tspans || nt < 1 || n_points < 1 || n_per_point < 0 || !rho || !rho2) { set_error("bad argument"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    std::vector<DevModel> dm(n_points);
+    int rows = 0;
+    bool any_noise = false;
+    int n_nodes_max = 2;
+    for (int p = 0; p < n_points; ++p) {
+        const double* ts = tspans + (size_t)p * nt;
+        for (int j = 1; j < nt; ++j)
+            if (!(ts[j] > ts[j - 1])) { set_error("tspan must be strictly increasing"); return CA_ERR_ARG; }
+        int rc = derive_model(models[p], psi0s + 10 * (size_t)p, 5, ts[0], ts[nt - 1], &dm[p]);
+        if (rc) return rc;
+        rows |= dm[p].rows;
+        if (dm[p].laser_noise) {
+            if (!f || !amp_red || !amp_blue || nf < 1) { set_error("laser_noise=true needs f and amplitudes"); return CA_ERR_ARG; }
+            any_noise = true;
+            if (ts[0] < 0) { set_error("laser noise is tabulated on [0, tspan[end]]: tspan[0] must be >= 0"); return CA_ERR_ARG; }
+        }
+        n_nodes_max = std::max(n_nodes_max, dm[p].n_nodes);
+    }
+    OdeOpts oo;
+    fill_ode(ode, tspans[0], tspans[nt - 1], &oo);
+    if (n_points > 1 && !(ode && ode->dtmax > 0)) oo.dtmax = 1e300;  // per-point horizons differ
+    if (!oo.adaptive && !(oo.dt0 > 0)) { set_error("adaptive=false needs dt > 0"); return CA_ERR_ARG; }
+
+    R1Params P;
+    std::memset(&P, 0, sizeof P);
+    P.model = dm[0];
+    P.ode = oo;
+    P.n_points = n_points; P.nt = nt; P.nf = any_noise ? nf : 0;
+    P.n_per_point = n_per_point; P.traj_offset = traj_offset; P.seed = seed;
+    P.groups_per_point = (n_per_point + 31) / 32;
+    P.n_groups = P.groups_per_point * n_points;
+    P.n_nodes_max = n_nodes_max;
+    const bool sweep = n_points > 1;
+
+    int rc;
+    CA_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = upload(c, c->in_tspan, tspans, sizeof(double) * (size_t)nt * n_points))) return rc;
+    P.tspans = (const double*)c->in_tspan.p;
+    if (sweep) {
+        if ((rc = upload(c, c->in_models, dm.data(), sizeof(DevModel) * (size_t)n_points))) return rc;
+        P.models = (const DevModel*)c->in_models.p;
+    }
+    const long long n_all = n_per_point * n_points;
+    if (samples) { if ((rc = upload(c, c->in_samples, samples, sizeof(double) * 6 * (size_t)n_all))) return rc; P.samples = (const double*)c->in_samples.p; }
+    if (any_noise) {
+        std::vector<double> fa((size_t)3 * nf);
+        std::memcpy(fa.data(), f, sizeof(double) * nf);
+        std::memcpy(fa.data() + nf, amp_red, sizeof(double) * nf);
+        std::memcpy(fa.data() + 2 * (size_t)nf, amp_blue, sizeof(double) * nf);
+        if ((rc = ensure_pinned(c, sizeof(double) * 3 * (size_t)nf))) return rc;
+        std::memcpy(c->pinned, fa.data(), sizeof(double) * 3 * (size_t)nf);
+        if ((rc = c->in_f.ensure(sizeof(double) * 3 * (size_t)nf))) return rc;
+        CA_CUDA(cudaMemcpyAsync(c->in_f.p, c->pinned, sizeof(double) * 3 * (size_t)nf, cudaMemcpyHostToDevice, c->stream));
+        CA_CUDA(cudaStreamSynchronize(c->stream));  // pinned staging buffer is reused below
+        P.f = (const double*)c->in_f.p; P.amp_red = P.f + nf; P.amp_blue = P.f + 2 * (size_t)nf;
+        if (phases_red) { if ((rc = upload(c, c->in_ph[0], phases_red, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_red = (const double*)c->in_ph[0].p; }
+        if (phases_blue) { if ((rc = upload(c, c->in_ph[1], phases_blue, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_blue = (const double*)c->in_ph[1].p; }
+    }
+    // grid: persistent warps, 2 CTAs of 128 threads per SM
+    const int wpb = kThreads1 / 32;
+    long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
+    int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, 2LL * c->sm_count));
+    if (any_noise) {
+        if ((rc = c->scratch.ensure(sizeof(double) * (size_t)grid * wpb * 2 * n_nodes_max * 32))) return rc;
+        P.scratch = (double*)c->scratch.p;
+    }
+    const size_t n_mats = (size_t)n_points * nt;
+    if ((rc = c->accum.ensure(sizeof(double) * n_mats * kNV))) return rc;
+    if ((rc = c->counters.ensure(sizeof(unsigned long long) * 8))) return rc;
+    CA_CUDA(cudaMemsetAsync(c->accum.p, 0, sizeof(double) * n_mats * kNV, c->stream));
+    CA_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
+    P.accum = (double*)c->accum.p;
+    P.counters = (unsigned long long*)c->counters.p;
+
+    int launches = 0;
+    CA_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    if (n_all > 0) {
+        const int ns = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
+        if (ns == 9) rc = sweep ? launch_lindblad1<9, true>(c, P, grid) : launch_lindblad1<9, false>(c, P, grid);
+        else if (ns == 15) rc = sweep ? launch_lindblad1<15, true>(c, P, grid) : launch_lindblad1<15, false>(c, P, grid);
+        else rc = sweep ? launch_lindblad1<21, true>(c, P, grid) : launch_lindblad1<21, false>(c, P, grid);
+        if (rc) return rc;
+        ++launches;
+    }
+    CA_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    // K6 finalize
+    const double div = (out_flags & CA_OUT_SUMS) ? 1.0 : 1.0 / (double)(n_total > 0 ? n_total : std::max<long long>(1, n_per_point));
+    const size_t out_mats = last_only ? (size_t)n_points : n_mats;
+    double *d_rho, *d_rho2;
+    if (out_flags & CA_OUT_DEVICE) { d_rho = rho; d_rho2 = rho2; }
+    else {
+        if ((rc = c->out.ensure(sizeof(double) * 100 * n_mats))) return rc;
+        d_rho = (double*)c->out.p; d_rho2 = d_rho + 50 * n_mats;
+    }
+    if (last_only && !(out_flags & CA_OUT_DEVICE)) {
+        k_finalize5<<<(unsigned)((n_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)n_mats, div, d_rho, d_rho2);
+    } else if (last_only) {
+        // device output of a sweep: finalize into scratch then gather the last time point of each point
+        if ((rc = c->out.ensure(sizeof(double) * 100 * n_mats))) return rc;
+        double* t1 = (double*)c->out.p;
+        k_finalize5<<<(unsigned)((n_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)n_mats, div, t1, t1 + 50 * n_mats);
+        for (int p = 0; p < n_points; ++p) {
+            CA_CUDA(cudaMemcpyAsync(d_rho + 50 * (size_t)p, t1 + 50 * ((size_t)p * nt + nt - 1), 400, cudaMemcpyDeviceToDevice, c->stream));
+            CA_CUDA(cudaMemcpyAsync(d_rho2 + 50 * (size_t)p, t1 + 50 * n_mats + 50 * ((size_t)p * nt + nt - 1), 400, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    } else {
+        k_finalize5<<<(unsigned)((n_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)n_mats, div, d_rho, d_rho2);
+    }
+    CA_CUDA(cudaGetLastError());
+    ++launches;
+    CA_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    if (out_flags & CA_OUT_DEVICE) {
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->n_traj = n_all; stats->n_launches = launches; }
+        return CA_OK;
+    }
+    if ((rc = ensure_pinned(c, sizeof(double) * 100 * n_mats + 64))) return rc;
+    double* hp = (double*)c->pinned;
+    CA_CUDA(cudaMemcpyAsync(hp, d_rho, sizeof(double) * 100 * n_mats, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long* hc = (unsigned long long*)(hp + 100 * n_mats);
+    CA_CUDA(cudaMemcpyAsync(hc, c->counters.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    if (last_only) {
+        for (int p = 0; p < n_points; ++p) {
+            std::memcpy(rho + 50 * (size_t)p, hp + 50 * ((size_t)p * nt + nt - 1), 400);
+            std::memcpy(rho2 + 50 * (size_t)p, hp + 50 * n_mats + 50 * ((size_t)p * nt + nt - 1), 400);
+        }
+    } else {
+        std::memcpy(rho, hp, sizeof(double) * 50 * n_mats);
+        std::memcpy(rho2, hp + 50 * n_mats, sizeof(double) * 50 * n_mats);
+    }
+    (void)out_mats;
+    int status = hc[4] ? -(int)hc[4] : 0;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->n_traj = n_all; stats->n_rhs = (int64_t)hc[0]; stats->n_accept = (int64_t)hc[1]; stats->n_reject = (int64_t)hc[2];
+        stats->n_sample_attempts = (int64_t)hc[3]; stats->n_launches = launches; stats->status = status;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); stats->kernel_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); stats->total_ms = ms;
+    }
+    if (status == CA_ERR_MAXITERS) { set_error("a trajectory hit maxiters"); return status; }
+    if (status) { set_error("a trajectory produced a non-finite state or the step size underflowed"); return status; }
+    return CA_OK;
+}
+
+}  // namespace ca
+
+// ----------------------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------------------
+using namespace ca;
+
+extern "C" {
+
+int ca_version(void) { return CA_VERSION; }
+const char* ca_last_error(void) { return get_error(); }
+
+int ca_init(int device, ca_ctx** out) {
+    if (!out) { set_error("null out pointer"); return CA_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { set_error(std::string("no CUDA device: ") + cudaGetErrorString(e)); return CA_ERR_NODEVICE; }
+    if (device < 0 || device >= n) { set_error("device index out of range"); return CA_ERR_ARG; }
+    cudaDeviceProp prop;
+    CA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device ") + prop.name + " is not sm_100 (this library ships sm_100a code only)");
+        return CA_ERR_NODEVICE;
+    }
+    CA_CUDA(cudaSetDevice(device));
+    ca_ctx* c = new ca_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    CA_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev) CA_CUDA(cudaEventCreate(&ev));
+    *out = c;
+    return CA_OK;
+}
+
+int ca_finalize(ca_ctx* c) {
+    if (!c) return CA_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->scratch, &c->accum, &c->out, &c->counters, &c->in_samples, &c->in_ph[0], &c->in_ph[1], &c->in_ph[2], &c->in_ph[3],
+                      &c->in_f, &c->in_models, &c->in_tspan, &c->misc};
+    for (auto* b : bufs) b->release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return CA_OK;
+}
+
+int ca_set_stream(ca_ctx* c, void* s) {
+    if (!c) { set_error("null context"); return CA_ERR_ARG; }
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return CA_OK;
+}
+
+int ca_synchronize(ca_ctx* c) {
+    if (!c) { set_error("null context"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    return CA_OK;
+}
+
+int ca_measure_fp64_peak(ca_ctx* c, double* tflops, double* sm_mhz_est) {
+    if (!c || !tflops) { set_error("bad argument"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    int rc = c->misc.ensure(64);
+    if (rc) return rc;
+    const int iters = 4096, blocks = c->sm_count * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        CA_CUDA(cudaEventRecord(c->ev[0], c->stream));
+        k_dfma_peak<<<blocks, threads, 0, c->stream>>>((double*)c->misc.p, iters, 1.0000001, 1e-9);
+        CA_CUDA(cudaEventRecord(c->ev[1], c->stream));
+        CA_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CA_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (sm_mhz_est) *sm_mhz_est = (*tflops * 1e12) / (2.0 * 64.0 * c->sm_count) / 1e6;  // 64 DFMA/clk/SM
+    return CA_OK;
+}
+
+int ca_rydberg1_run(ca_ctx* ctx, const ca_model* model, const double* tspan, int32_t nt, const double* psi0, int64_t n_traj,
+                    int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples, const double* phases_red,
+                    const double* phases_blue, const double* f, const double* amp_red, const double* amp_blue, int32_t nf,
+                    const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats) {
+    return run_r1(ctx, model, psi0, tspan, nt, 1, n_traj, traj_offset, n_total, seed, samples, phases_red, phases_blue, f, amp_red,
+                  amp_blue, nf, ode, out_flags, false, rho, rho2, stats);
+}
+
+int ca_rydberg1_sweep(ca_ctx* ctx, const ca_model* models, const double* psi0s, const double* t_end, int32_t n_points,
+                      int64_t n_traj_per_point, int64_t traj_offset, int64_t n_total, uint64_t seed, const double* f,
+                      const double* amp_red, const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags, double* rho,
+                      double* rho2, ca_stats* stats) {
+    if (!t_end || n_points < 1) { set_error("bad argument"); return CA_ERR_ARG; }
+    std::vector<double> ts((size_t)2 * n_points);
+    for (int p = 0; p < n_points; ++p) { ts[2 * p] = 0.0; ts[2 * p + 1] = t_end[p]; }
+    return run_r1(ctx, models, psi0s, ts.data(), 2, n_points, n_traj_per_point, traj_offset, n_total, seed, nullptr, nullptr, nullptr, f,
+                  amp_red, amp_blue, nf, ode, out_flags, true, rho, rho2, stats);
+}
+
+int ca_release_recapture(ca_ctx* c, const double* trap, const double* atom, const double* tspan, int32_t nt, int64_t n,
+                         int64_t traj_offset, int64_t n_total, double eps, uint64_t seed, const double* samples, int32_t out_flags,
+                         double* probs, uint8_t* indicators, ca_stats* stats) {
+    if (!c || !trap || !atom || !tspan || nt < 1 || n < 0 || !probs) { set_error("bad argument"); return CA_ERR_ARG; }
+    if (out_flags & CA_OUT_DEVICE) { set_error("CA_OUT_DEVICE is not supported by ca_release_recapture"); return CA_ERR_UNSUPPORTED; }
+    CA_CUDA(cudaSetDevice(c->device));
+    ca_model m;
+    std::memset(&m, 0, sizeof m);
+    m.atom_m = atom[0]; m.atom_T = atom[1]; m.trap_U0 = trap[0]; m.trap_w0 = trap[1]; m.trap_z0 = trap[2];
+    m.red.kind = m.blue.kind = CA_BEAM_UNIFORM; m.blue.w0 = m.blue.z0 = 1.0;
+    DevModel d;
+    int rc = derive_model(m, nullptr, 0, 0.0, 1.0, &d);
+    if (rc) return rc;
+    SamplerConsts sc;
+    for (int q = 0; q < 6; ++q) sc.sig[q] = d.sig[q];
+    sc.U0 = d.U0; sc.w0 = d.w0; sc.z0 = d.z0; sc.mfac = d.mfac; sc.ecut = d.ecut;
+    CA_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = upload(c, c->in_tspan, tspan, sizeof(double) * nt))) return rc;
+    const double* d_samples = nullptr;
+    if (samples && n > 0) { if ((rc = upload(c, c->in_samples, samples, sizeof(double) * 6 * (size_t)n))) return rc; d_samples = (const double*)c->in_samples.p; }
+    if ((rc = c->counters.ensure(sizeof(unsigned long long) * ((size_t)nt + 8)))) return rc;
+    CA_CUDA(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * ((size_t)nt + 8), c->stream));
+    unsigned long long* d_counts = (unsigned long long*)c->counters.p;
+    unsigned char* d_ind = nullptr;
+    if (indicators && n > 0) { if ((rc = c->out.ensure((size_t)n * nt))) return rc; d_ind = (unsigned char*)c->out.p; }
+    const double thresh = trap[0] * (1.0 - eps);
+    CA_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    if (n > 0) {
+        k_release_recapture<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(sc, (const double*)c->in_tspan.p, nt, n, traj_offset, seed, thresh,
+                                                                                d_samples, d_counts, d_ind, d_counts + nt);
+        CA_CUDA(cudaGetLastError());
+    }
+    CA_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = ensure_pinned(c, sizeof(unsigned long long) * ((size_t)nt + 8)))) return rc;
+    CA_CUDA(cudaMemcpyAsync(c->pinned, d_counts, sizeof(unsigned long long) * ((size_t)nt + 8), cudaMemcpyDeviceToHost, c->stream));
+    if (d_ind) CA_CUDA(cudaMemcpyAsync(indicators, d_ind, (size_t)n * nt, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    const unsigned long long* hc = (const unsigned long long*)c->pinned;
+    const double div = (out_flags & CA_OUT_SUMS) ? 1.0 : (double)(n_total > 0 ? n_total : std::max<long long>(1, n));
+    for (int j = 0; j < nt; ++j) probs[j] = (double)hc[j] / div;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->n_traj = n; stats->n_sample_attempts = (int64_t)hc[nt]; stats->n_launches = n > 0 ? 1 : 0;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); stats->kernel_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); stats->total_ms = ms;
+    }
+    return CA_OK;
+}
+
+int ca_sample_atoms(ca_ctx* c, const double* trap, const double* atom, int64_t n, int64_t traj_offset, uint64_t seed, int32_t stream_id,
+                    double eps, double* samples_out, int64_t* attempts_out) {
+    if (!c || !trap || !atom || n < 0 || !samples_out) { set_error("bad argument"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    ca_model m;
+    std::memset(&m, 0, sizeof m);
+    m.atom_m = atom[0]; m.atom_T = atom[1]; m.trap_U0 = trap[0]; m.trap_w0 = trap[1]; m.trap_z0 = trap[2];
+    m.red.kind = m.blue.kind = CA_BEAM_UNIFORM; m.blue.w0 = m.blue.z0 = 1.0;
+    DevModel d;
+    int rc = derive_model(m, nullptr, 0, 0.0, 1.0, &d);
+    if (rc) return rc;
+    SamplerConsts sc;
+    for (int q = 0; q < 6; ++q) sc.sig[q] = d.sig[q];
+    sc.U0 = d.U0; sc.w0 = d.w0; sc.z0 = d.z0; sc.mfac = d.mfac; sc.ecut = trap[0] * (1.0 - eps);
+    if (n == 0) { if (attempts_out) *attempts_out = 0; return CA_OK; }
+    if ((rc = c->out.ensure(sizeof(double) * 6 * (size_t)n))) return rc;
+    if ((rc = c->counters.ensure(64))) return rc;
+    CA_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    k_sample_atoms<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(sc, n, traj_offset, seed, (unsigned)stream_id, (double*)c->out.p,
+                                                                       (unsigned long long*)c->counters.p);
+    CA_CUDA(cudaGetLastError());
+    CA_CUDA(cudaMemcpyAsync(samples_out, c->out.p, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long att = 0;
+    CA_CUDA(cudaMemcpyAsync(&att, c->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    if (attempts_out) *attempts_out = (int64_t)att;
+    return CA_OK;
+}
+
+int ca_phase_noise(ca_ctx* c, const double* tnodes, int32_t n_nodes, const double* f, const double* amp, int32_t nf, int64_t n,
+                   int64_t traj_offset, uint64_t seed, int32_t stream_id, const double* phases, double* phi_out) {
+    if (!c || !tnodes || n_nodes < 2 || !f || !amp || nf < 1 || n < 0 || !phi_out) { set_error("bad argument"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    // the device generator works on the uniform grid the reference uses (rydberg_model.jl:216): check it
+    const double dtn = (tnodes[n_nodes - 1] - tnodes[0]) / (n_nodes - 1);
+    if (tnodes[0] != 0.0) { set_error("tnodes must start at 0"); return CA_ERR_UNSUPPORTED; }
+    for (int j = 0; j < n_nodes; ++j)
+        if (std::fabs(tnodes[j] - j * dtn) > 1e-9 * std::fabs(tnodes[n_nodes - 1])) { set_error("tnodes must be uniformly spaced"); return CA_ERR_UNSUPPORTED; }
+    if (n == 0) return CA_OK;
+    int rc;
+    std::vector<double> fa((size_t)2 * nf);
+    std::memcpy(fa.data(), f, sizeof(double) * nf);
+    std::memcpy(fa.data() + nf, amp, sizeof(double) * nf);
+    if ((rc = upload(c, c->in_f, fa.data(), sizeof(double) * 2 * (size_t)nf))) return rc;
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    const double* d_ph = nullptr;
+    if (phases) { if ((rc = upload(c, c->in_ph[0], phases, sizeof(double) * (size_t)nf * n))) return rc; d_ph = (const double*)c->in_ph[0].p; }
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)n * n_nodes))) return rc;
+    k_phase_noise<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const double*)c->in_f.p, (const double*)c->in_f.p + nf, nf, n_nodes, dtn, d_ph, n,
+                                                                     traj_offset, seed, (unsigned)stream_id, (double*)c->out.p);
+    CA_CUDA(cudaGetLastError());
+    CA_CUDA(cudaMemcpyAsync(phi_out, c->out.p, sizeof(double) * (size_t)n * n_nodes, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    return CA_OK;
+}
+
+int ca_eval_beam(ca_ctx* c, const ca_beam* beam, const double* xyz, int64_t n, double* out) {
+    if (!c || !beam || !xyz || n < 0 || !out) { set_error("bad argument"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    DevBeam b;
+    int rc = derive_beam(*beam, &b);
+    if (rc) return rc;
+    if (n == 0) return CA_OK;
+    if ((rc = upload(c, c->in_samples, xyz, sizeof(double) * 3 * (size_t)n))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * 2 * (size_t)n))) return rc;
+    k_eval_beam<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(b, (const double*)c->in_samples.p, n, (double*)c->out.p);
+    CA_CUDA(cudaGetLastError());
+    CA_CUDA(cudaMemcpyAsync(out, c->out.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    return CA_OK;
+}
+
+}  // extern "C"

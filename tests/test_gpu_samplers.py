@@ -1,0 +1,96 @@
+"""GPU tests: Philox samplers, phase-noise tables, beams (golden vector), release-recapture (bit-exact indicators)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TRAP = [1000.0, 1.0, np.pi * 1.0 ** 2 / 0.852]
+ATOM = [86.9091835, 50.0]
+
+
+def test_sample_atoms_matches_oracle_philox(ctx, oracle):
+    s, att = ctx.sample_atoms(TRAP, ATOM, 5000, traj_offset=17, seed=3, stream=1)
+    o, oatt = oracle.sample_atoms(TRAP, ATOM, 5000, offset=17, seed=3, stream=1)
+    assert att == oatt
+    assert np.abs(s - o).max() < 1e-13 * max(1.0, np.abs(o).max())
+
+
+def test_sample_atoms_moments(ctx, pkg):
+    """Sampler moments: variances (T w0²/4U0, same, T z0²/2U0, vconst² T/m x3), zero means."""
+    n = 200000
+    s, att = ctx.sample_atoms(TRAP, ATOM, n, seed=1)
+    U0, w0, z0 = TRAP
+    m, T = ATOM
+    sig = np.array([np.sqrt(T * w0 ** 2 / (4 * U0))] * 2 + [np.sqrt(T * z0 ** 2 / (2 * U0))] + [pkg.vconst * np.sqrt(T / m)] * 3)
+    assert np.all(np.abs(s.mean(0)) < 5 * sig / np.sqrt(n))
+    assert np.allclose(s.std(0), sig, rtol=0.01)  # the energy cut removes ~nothing at T/U0 = 0.05
+    assert att >= n and att < 1.001 * n
+
+
+def test_phase_noise_tables(ctx, oracle, pkg):
+    cfg, _ = pkg.get_default_configs()
+    tn = np.arange(1001) * (2.5 / 1000)
+    n = 9
+    rng = np.random.default_rng(0)
+    ph = rng.uniform(0, 2 * np.pi, (n, len(cfg.f)))
+    tab = ctx.phase_noise(tn, cfg.f, cfg.red_laser_phase_amplitudes, n, phases=ph)
+    for i in range(n):
+        ref = oracle.phi(tn, cfg.f, cfg.red_laser_phase_amplitudes, ph[i])
+        assert np.abs(tab[i] - ref).max() < 1e-12
+    # device-drawn phases = oracle's Philox phases
+    tab = ctx.phase_noise(tn, cfg.f, cfg.red_laser_phase_amplitudes, 3, traj_offset=5, seed=77, stream=3)
+    for i in range(3):
+        ref = oracle.phi(tn, cfg.f, cfg.red_laser_phase_amplitudes, oracle.phase_draw(77, 5 + i, 3, len(cfg.f)))
+        assert np.abs(tab[i] - ref).max() < 1e-12
+    # rms ~ sqrt(sum a²/2)
+    big = ctx.phase_noise(tn, cfg.f, cfg.red_laser_phase_amplitudes, 2000, seed=5)
+    assert abs(big.std() - np.sqrt(np.sum(np.asarray(cfg.red_laser_phase_amplitudes) ** 2) / 2)) < 0.02 * big.std()
+
+
+def test_beam_golden_vector_on_device(ctx, pkg):
+    """The reference's only deterministic known answers (notebooks/modeling.ipynb cell 13), on the device beam code."""
+    g = json.load(open(os.path.join(HERE, "golden", "beam_profiles.json")))
+    x = np.array(g["x"])
+    xyz = np.stack([x, 0 * x, 0 * x], 1)
+    for i in range(0, 10, 2):
+        s = max(i, 1)
+        b = pkg.beam_from_params([1, 1 / s ** 0.5, 5, "simp_flattop_HG", i, i, 1.0], arb_bms=True)
+        assert np.abs(np.abs(ctx.eval_beam(b, xyz)) ** 2 - np.array(g["traces"][f"HG_{i}"])).max() < 1e-13
+        b = pkg.beam_from_params([1, 1 / s ** 0.5, 5, "simp_flattop_LG", i, i], arb_bms=True)
+        assert np.abs(np.abs(ctx.eval_beam(b, xyz)) ** 2 + 0.001 - np.array(g["traces"][f"LG_{i}"])).max() < 1e-13
+
+
+def test_beams_off_axis_match_oracle(ctx, oracle, pkg):
+    rng = np.random.default_rng(3)
+    xyz = rng.normal(size=(500, 3)) * [1.5, 1.5, 30.0]
+    for p in ([2.0, 1.3, 7.0, "simp_flattop_HG", 6, 4, 1.3], [2.0, 1.3, 7.0, "simp_flattop_LG", 8, 0],
+              [3.0, 10.0, 661.0, 0.3, 1], [3.0, 50.0, 9879.0, np.pi / 2, 1]):
+        b = pkg.beam_from_params(p, arb_bms=len(p) > 5)
+        d, o = ctx.eval_beam(b, xyz), oracle.eval_beam(b, xyz)
+        assert np.abs(d - o).max() < 1e-12 * max(1.0, np.abs(o).max())
+
+
+def test_release_recapture_bit_exact(ctx, oracle):
+    tspan = np.arange(0.0, 51.0)
+    n = 10000
+    samples, _ = oracle.sample_atoms(TRAP, ATOM, n, seed=21)
+    probs, ind, _ = ctx.release_recapture(TRAP, ATOM, tspan, n, samples=samples, want_indicators=True)
+    oprobs, oind = oracle.release_recapture(TRAP, ATOM, tspan, n, samples=samples, want_indicators=True)
+    assert np.array_equal(ind, oind)          # recapture indicators bit-exact (north star)
+    assert np.array_equal(probs, oprobs)
+    assert probs[0] == 1.0 and np.all(np.diff(probs) <= 0)  # monotone mask (basic_experiments.jl:39-44)
+    # on-device sampling path
+    p2, _, st = ctx.release_recapture(TRAP, ATOM, tspan, n, seed=8)
+    o2, _ = oracle.release_recapture(TRAP, ATOM, tspan, n, seed=8)
+    assert np.array_equal(p2, o2)
+    # anchor curve of SURVEY App. C (N = 1e5: P(5,10,20,30,50) = .961 .721 .356 .205 .097), statistical tolerance
+    p3, _, _ = ctx.release_recapture(TRAP, ATOM, tspan, 100000, seed=1)
+    assert np.allclose(p3[[5, 10, 20, 30, 50]], [0.961, 0.721, 0.356, 0.205, 0.097], atol=0.006)
+    # empty input and ragged sizes
+    p0, _, _ = ctx.release_recapture(TRAP, ATOM, tspan, 0)
+    assert np.all(p0 == 0)
+    p1, i1, _ = ctx.release_recapture(TRAP, ATOM, tspan, 33, samples=samples[:33], want_indicators=True)
+    assert np.array_equal(i1, oind[:33])
