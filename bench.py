@@ -208,7 +208,7 @@ def main():
     value = n_total * args.steps / (ms * 1e-3)
 
     # roofline of the dominant kernel: one extra step through the host-output path to read the device counters
-    ctx.set_stream(0)
+    ctx.reset_stream()
     torch.cuda.synchronize(dev)
     _, _, st = run(model, cfg.tspan, cfg.ψ0, n_per, traj_offset=rank * n_per, n_total=n_total, seed=999, **kw)
     flops = algorithmic_flops(cfg, natoms, st, n_per)

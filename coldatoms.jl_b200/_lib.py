@@ -20,7 +20,7 @@ _lock = threading.Lock()
 
 # every symbol include/coldatoms_b200.h declares
 EXPORTS = [
-    "ca_version", "ca_last_error", "ca_init", "ca_finalize", "ca_set_stream", "ca_synchronize",
+    "ca_version", "ca_last_error", "ca_init", "ca_finalize", "ca_set_stream", "ca_reset_stream", "ca_synchronize",
     "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg1_sweep", "ca_release_recapture",
     "ca_sample_atoms", "ca_phase_noise", "ca_eval_beam",
 ]
@@ -93,7 +93,11 @@ class Context:
             pass
 
     def set_stream(self, stream_ptr):
+        """Run on a caller-owned CUDA stream handle (0 = legacy default stream, e.g. torch's default current stream)."""
         _check(load().ca_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def reset_stream(self):
+        _check(load().ca_reset_stream(self._h))
 
     def synchronize(self):
         _check(load().ca_synchronize(self._h))

@@ -90,7 +90,7 @@ def _allreduce_mean(ctx, run, nt, d, n_total):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         out = (buf / float(n_total)).cpu().numpy()
     finally:
-        ctx.set_stream(0)
+        ctx.reset_stream()
     cm = out[..., 0] + 1j * out[..., 1]
     return cm[0].transpose(0, 2, 1).copy(), cm[1].transpose(0, 2, 1).copy(), st
 

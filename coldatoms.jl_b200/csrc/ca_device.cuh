@@ -359,8 +359,6 @@ struct Lane1 {
     double t, h, dt, lnq_old;
     double y[NS], k1[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
-    Coef cf1;                             // coefficients at t (FSAL partner of k1)
-    Coef cf7;
     long long iters;
     int n_rhs, n_acc, n_rej;
     int status;
@@ -445,8 +443,9 @@ struct Lane1 {
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
         t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; status = 0;
         lnq_old = log(1e-4);
-        coefficients(m, t, cf1);
-        lindblad_rhs<NS>(cf1, g, y, k1);
+        Coef cf0;
+        coefficients(m, t, cf0);
+        lindblad_rhs<NS>(cf0, g, y, k1);
         g1[0] = g.G0 * y[2]; g1[1] = g.Gl * y[2] + g.Gr * y[1];
         n_rhs = 1;
 #pragma unroll
@@ -504,7 +503,6 @@ struct Lane1 {
 #pragma unroll
             for (int i = 0; i < NS; ++i) { y[i] = un[i]; k1[i] = k7[i]; }
             P[0] = Pn[0]; P[1] = Pn[1]; g1[0] = g7[0]; g1[1] = g7[1];
-            cf1 = cf7;
             t = tcommit;
             h = 0.0;
         }
@@ -512,53 +510,91 @@ struct Lane1 {
         double hh = fmin(dt, oo.dtmax);
         bool clipped = false;
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
-        double us[NS], k2[NS];
-        Coef c;
-        double SB0, SB1, SE0, SE1, SD0, SD1, gg0, gg1;
-        // stage 1 contributions of the population quadratures
-        SB0 = dp::b1 * g1[0]; SB1 = dp::b1 * g1[1]; SE0 = dp::e1 * g1[0]; SE1 = dp::e1 * g1[1]; SD0 = dp::d1 * g1[0]; SD1 = dp::d1 * g1[1];
-        // stage 2
+        // Stages 2..7 run through ONE copy of the coefficient + RHS code (a rolled loop; the per-stage linear
+        // combinations are switch cases so every array index stays a compile-time constant and the state stays in
+        // registers).  Keeping the loop body small matters: fully unrolled the step is far larger than the
+        // instruction caches.  Stage 6 and 7 share their coefficients (c6 = c7 = 1) and stage 7 is the next
+        // step's stage 1 (FSAL).
+        double us[NS], ko[NS], k2[NS];
+        Coef cf7;
+        const double tn = clipped ? tstop : t + hh;
+        // population quadratures: ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr, accumulated with the b/e/d weights
+        double SB0 = dp::b1 * g1[0], SB1 = dp::b1 * g1[1], SE0 = dp::e1 * g1[0], SE1 = dp::e1 * g1[1], SD0 = dp::d1 * g1[0],
+               SD1 = dp::d1 * g1[1];
+#pragma unroll 1
+        for (int s = 2; s <= 7; ++s) {
+            double ts, wb, we, wd;
+            switch (s) {
+                case 2:
 #pragma unroll
-        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a21 * k1[i]);
-        coefficients(m, t + dp::c2 * hh, c);
-        lindblad_rhs<NS>(c, g, us, k2);
-        // stage 3
+                    for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a21 * k1[i]);
+                    ts = t + dp::c2 * hh; wb = 0.0; we = 0.0; wd = 0.0;
+                    break;
+                case 3:
 #pragma unroll
-        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a31 * k1[i] + dp::a32 * k2[i]);
-        coefficients(m, t + dp::c3 * hh, c);
-        lindblad_rhs<NS>(c, g, us, k3);
-        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
-        SB0 += dp::b3 * gg0; SB1 += dp::b3 * gg1; SE0 += dp::e3 * gg0; SE1 += dp::e3 * gg1; SD0 += dp::d3 * gg0; SD1 += dp::d3 * gg1;
-        // stage 4
+                    for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a31 * k1[i] + dp::a32 * k2[i]);
+                    ts = t + dp::c3 * hh; wb = dp::b3; we = dp::e3; wd = dp::d3;
+                    break;
+                case 4:
 #pragma unroll
-        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a41 * k1[i] + dp::a42 * k2[i] + dp::a43 * k3[i]);
-        coefficients(m, t + dp::c4 * hh, c);
-        lindblad_rhs<NS>(c, g, us, k4);
-        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
-        SB0 += dp::b4 * gg0; SB1 += dp::b4 * gg1; SE0 += dp::e4 * gg0; SE1 += dp::e4 * gg1; SD0 += dp::d4 * gg0; SD1 += dp::d4 * gg1;
-        // stage 5
+                    for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a41 * k1[i] + dp::a42 * k2[i] + dp::a43 * k3[i]);
+                    ts = t + dp::c4 * hh; wb = dp::b4; we = dp::e4; wd = dp::d4;
+                    break;
+                case 5:
 #pragma unroll
-        for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a51 * k1[i] + dp::a52 * k2[i] + dp::a53 * k3[i] + dp::a54 * k4[i]);
-        coefficients(m, t + dp::c5 * hh, c);
-        lindblad_rhs<NS>(c, g, us, k5);
-        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
-        SB0 += dp::b5 * gg0; SB1 += dp::b5 * gg1; SE0 += dp::e5 * gg0; SE1 += dp::e5 * gg1; SD0 += dp::d5 * gg0; SD1 += dp::d5 * gg1;
-        // stage 6 (t + h); its coefficients are shared with stage 7 and with the next step's stage 1
-        double tn = clipped ? tstop : t + hh;
+                    for (int i = 0; i < NS; ++i)
+                        us[i] = y[i] + hh * (dp::a51 * k1[i] + dp::a52 * k2[i] + dp::a53 * k3[i] + dp::a54 * k4[i]);
+                    ts = t + dp::c5 * hh; wb = dp::b5; we = dp::e5; wd = dp::d5;
+                    break;
+                case 6:
 #pragma unroll
-        for (int i = 0; i < NS; ++i)
-            us[i] = y[i] + hh * (dp::a61 * k1[i] + dp::a62 * k2[i] + dp::a63 * k3[i] + dp::a64 * k4[i] + dp::a65 * k5[i]);
-        coefficients(m, tn, cf7);
-        lindblad_rhs<NS>(cf7, g, us, k6);
-        gg0 = g.G0 * us[2]; gg1 = g.Gl * us[2] + g.Gr * us[1];
-        SB0 += dp::b6 * gg0; SB1 += dp::b6 * gg1; SE0 += dp::e6 * gg0; SE1 += dp::e6 * gg1; SD0 += dp::d6 * gg0; SD1 += dp::d6 * gg1;
-        // new state and stage 7
+                    for (int i = 0; i < NS; ++i)
+                        us[i] = y[i] + hh * (dp::a61 * k1[i] + dp::a62 * k2[i] + dp::a63 * k3[i] + dp::a64 * k4[i] + dp::a65 * k5[i]);
+                    ts = tn; wb = dp::b6; we = dp::e6; wd = dp::d6;
+                    break;
+                default:
 #pragma unroll
-        for (int i = 0; i < NS; ++i)
-            un[i] = y[i] + hh * (dp::b1 * k1[i] + dp::b3 * k3[i] + dp::b4 * k4[i] + dp::b5 * k5[i] + dp::b6 * k6[i]);
-        lindblad_rhs<NS>(cf7, g, un, k7);
-        g7[0] = g.G0 * un[2]; g7[1] = g.Gl * un[2] + g.Gr * un[1];
-        SE0 += dp::e7 * g7[0]; SE1 += dp::e7 * g7[1]; SD0 += dp::d7 * g7[0]; SD1 += dp::d7 * g7[1];
+                    for (int i = 0; i < NS; ++i) us[i] = un[i];
+                    ts = tn; wb = 0.0; we = dp::e7; wd = dp::d7;
+                    break;
+            }
+            if (s <= 6) coefficients(m, ts, cf7);
+            lindblad_rhs<NS>(cf7, g, us, ko);
+            {
+                const double gg0 = g.G0 * us[2], gg1 = g.Gl * us[2] + g.Gr * us[1];
+                SB0 += wb * gg0; SB1 += wb * gg1; SE0 += we * gg0; SE1 += we * gg1; SD0 += wd * gg0; SD1 += wd * gg1;
+                g7[0] = gg0; g7[1] = gg1;
+            }
+            switch (s) {
+                case 2:
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) k2[i] = ko[i];
+                    break;
+                case 3:
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) k3[i] = ko[i];
+                    break;
+                case 4:
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) k4[i] = ko[i];
+                    break;
+                case 5:
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) k5[i] = ko[i];
+                    break;
+                case 6:
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) {
+                        k6[i] = ko[i];
+                        un[i] = y[i] + hh * (dp::b1 * k1[i] + dp::b3 * k3[i] + dp::b4 * k4[i] + dp::b5 * k5[i] + dp::b6 * k6[i]);
+                    }
+                    break;
+                default:
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) k7[i] = ko[i];
+                    break;
+            }
+        }
         Pn[0] = P[0] + hh * SB0; Pn[1] = P[1] + hh * SB1;
         n_rhs += 6;
         bool accept = true;

@@ -530,7 +530,13 @@ int ca_finalize(ca_ctx* c) {
 
 int ca_set_stream(ca_ctx* c, void* s) {
     if (!c) { set_error("null context"); return CA_ERR_ARG; }
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;
+    return CA_OK;
+}
+
+int ca_reset_stream(ca_ctx* c) {
+    if (!c) { set_error("null context"); return CA_ERR_ARG; }
+    c->stream = c->own_stream;
     return CA_OK;
 }
 

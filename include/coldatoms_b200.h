@@ -141,8 +141,10 @@ const char* ca_last_error(void);
 /* Create a context on one CUDA device (sm_100 required). One context per process and GPU. */
 int ca_init(int device, ca_ctx** out);
 int ca_finalize(ca_ctx* ctx);
-/* Run on a caller-owned stream (e.g. torch's current stream); NULL restores the context's own stream. */
+/* Run on a caller-owned CUDA stream (e.g. torch's current stream; NULL is the legacy default stream, as in CUDA).
+ * ca_reset_stream restores the context's own non-blocking stream. */
 int ca_set_stream(ca_ctx* ctx, void* cuda_stream);
+int ca_reset_stream(ca_ctx* ctx);
 int ca_synchronize(ca_ctx* ctx);
 /* Measured FP64 FMA throughput of the device in TFLOP/s (2 flop per DFMA); roofline denominator. */
 int ca_measure_fp64_peak(ca_ctx* ctx, double* tflops, double* sm_mhz_est);

@@ -1,0 +1,134 @@
+"""CPU tests of the DEVICE SOURCE (coldatoms.jl_b200/csrc/ca_device.cuh is __host__ __device__): the per-lane
+sampler, phase-noise recurrence, beam code, reduced Lindblad RHS and DP5 are compiled for the host by the
+test-only harness tests/hostemu and compared with the oracle.  The GPU tests repeat this through the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+dp = C.POINTER(C.c_double)
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+@pytest.fixture(scope="module")
+def he():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "hostemu"), "-s"])
+    return C.CDLL(os.path.join(HERE, "hostemu", "libhostemu.so"))
+
+
+def unpack(v):
+    nt = v.shape[0]
+    M = np.zeros((nt, 5, 5), complex)
+    for a in range(5):
+        M[:, a, a] = v[:, a]
+    q = 0
+    for a in range(5):
+        for b in range(a + 1, 5):
+            M[:, a, b] = v[:, 5 + 2 * q] + 1j * v[:, 6 + 2 * q]
+            M[:, b, a] = np.conj(M[:, a, b])
+            q += 1
+    return M
+
+
+def he_traj(he, model, tspan, psi0, sample, pr, pb, f, ar, ab, ode, seed=1, gi=0):
+    tspan = np.ascontiguousarray(tspan, float)
+    nt = len(tspan)
+    out = np.zeros((nt, 50))
+    st = (C.c_longlong * 3)()
+    psi = np.ascontiguousarray(np.asarray(psi0, complex)).view(float)
+    arrs = [None if a is None else np.ascontiguousarray(a, float) for a in (sample, pr, pb, f, ar, ab)]
+    nf = 0 if f is None else len(f)
+    rc = he.he_rydberg1_traj(C.byref(model), P(tspan), nt, P(psi), P(arrs[0]), P(arrs[1]), P(arrs[2]), P(arrs[3]), P(arrs[4]), P(arrs[5]), nf,
+                             C.byref(ode), C.c_ulonglong(seed), C.c_ulonglong(gi), P(out), st)
+    assert rc == 0, rc
+    return unpack(out[:, :25]), unpack(out[:, 25:]), list(st)
+
+
+@pytest.mark.parametrize("psi", ["1", "0+i1", "l", "general"])
+@pytest.mark.parametrize("free", [True, False])
+def test_lane_matches_oracle(pkg, oracle, he, r1cfg, psi, free):
+    cfg = r1cfg.copy()
+    cfg.free_motion = free
+    psi0 = {"1": pkg.ket_1, "0+i1": (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2), "l": (pkg.ket_l + pkg.ket_p) / np.sqrt(2),
+            "general": (pkg.ket_0 + pkg.ket_1 + pkg.ket_l + 0.5j * pkg.ket_r) / np.sqrt(3.25)}[psi]
+    rng = np.random.default_rng(1)
+    samples, _ = oracle.sample_atoms(cfg.trap_params, cfg.atom_params, 2)
+    ph = rng.uniform(0, 2 * np.pi, (2, 397))
+    model = pkg.model_from_config(cfg)
+    for ode, tol in [(pkg._abi.ode_opts(), 1e-11), (pkg._abi.ode_opts(dt=2e-4, adaptive=False), 1e-12),
+                     (pkg._abi.ode_opts(dense=False), 1e-11)]:
+        r1, r2, st = he_traj(he, model, cfg.tspan, psi0, samples[1], ph[0], ph[1], cfg.f, cfg.red_laser_phase_amplitudes,
+                             cfg.blue_laser_phase_amplitudes, ode)
+        o1, o2, ost = oracle.rydberg1_run(model, cfg.tspan, psi0, 1, samples=samples[1:2], phases_red=ph[0:1], phases_blue=ph[1:2], f=cfg.f,
+                                          amp_red=cfg.red_laser_phase_amplitudes, amp_blue=cfg.blue_laser_phase_amplitudes, ode=ode)
+        assert st == [ost["n_rhs"], ost["n_accept"], ost["n_reject"]]
+        assert np.abs(r1 - o1).max() < tol and np.abs(r2 - o2).max() < tol
+
+
+def test_lane_abs2_mode_and_cz_sign(pkg, oracle, he, r1cfg):
+    cfg = r1cfg.copy()
+    model = pkg.model_from_config(cfg, rho2_mode=pkg._abi.CA_RHO2_ABS2, compat=0)
+    model.detuning_sign = pkg._abi.CA_SIGN_CZ
+    samples, _ = oracle.sample_atoms(cfg.trap_params, cfg.atom_params, 1, seed=5)
+    ode = pkg._abi.ode_opts(dt=2e-4, adaptive=False)
+    psi0 = (pkg.ket_0 + pkg.ket_1) / np.sqrt(2)
+    r1, r2, _ = he_traj(he, model, cfg.tspan, psi0, samples[0], None, None, cfg.f, cfg.red_laser_phase_amplitudes,
+                        cfg.blue_laser_phase_amplitudes, ode, seed=77, gi=12)
+    o1, o2, _ = oracle.rydberg1_run(model, cfg.tspan, psi0, 1, traj_offset=12, seed=77, samples=samples, f=cfg.f,
+                                    amp_red=cfg.red_laser_phase_amplitudes, amp_blue=cfg.blue_laser_phase_amplitudes, ode=ode)
+    assert np.abs(r1 - o1).max() < 1e-12 and np.abs(r2 - o2).max() < 1e-12
+
+
+def test_lane_arbitrary_beams(pkg, oracle, he):
+    """simulation_blue_intens semantics (uniform red, flat-top HG / LG blue, Doppler from vz, two decay channels)."""
+    abi = pkg._abi
+    for blue in ([2 * np.pi * 96, 2 / np.sqrt(4), 26.4 / 4, "simp_flattop_HG", 4, 4, 1.0], [2 * np.pi * 96, 2.0, 26.4, "simp_flattop_LG", 6, 0]):
+        m = abi.ca_model()
+        m.atom_m, m.atom_T, m.trap_U0, m.trap_w0, m.trap_z0 = 86.9091835, 70.0, 1000.0, 1.1, 4.6
+        m.red = pkg.beam_from_params([2 * np.pi * 96, 100.0, 39517.0], arb_bms=True)
+        m.blue = pkg.beam_from_params(blue, arb_bms=True)
+        m.Delta0, m.delta0 = 2 * np.pi * 1500, 0.0
+        m.Gamma1, m.Gamma0 = 2 * np.pi * 1.5, 2 * np.pi * 4.5
+        m.atom_motion = m.free_motion = m.decay_intermediate = 1
+        m.doppler_kind, m.parallel, m.n_noise_nodes = abi.CA_DOPPLER_Z, 0, 1001
+        tspan = np.linspace(0, 0.3, 7)
+        samples, _ = oracle.sample_atoms([1000.0, 1.1, 4.6], [86.9091835, 70.0], 1, seed=3)
+        ode = abi.ode_opts()
+        r1, r2, st = he_traj(he, m, tspan, pkg.ket_1, samples[0], None, None, None, None, None, ode)
+        o1, o2, ost = oracle.rydberg1_run(m, tspan, pkg.ket_1, 1, samples=samples, ode=ode)
+        assert st[0] == ost["n_rhs"]
+        assert np.abs(r1 - o1).max() < 1e-10 and np.abs(r2 - o2).max() < 1e-10
+
+
+def test_noise_recurrence_and_sampler(pkg, oracle, he):
+    cfg, _ = pkg.get_default_configs()
+    f, amp = np.ascontiguousarray(cfg.f), np.ascontiguousarray(cfg.red_laser_phase_amplitudes)
+    n_nodes, dtn = 1001, 2.5 / 1000
+    out = np.zeros(n_nodes)
+    he.he_noise_trace(P(f), P(amp), len(f), n_nodes, C.c_double(dtn), None, C.c_ulonglong(9), C.c_ulonglong(3), C.c_uint(2), P(out))
+    ref = oracle.phi(np.arange(n_nodes) * dtn, f, amp, oracle.phase_draw(9, 3, 2, len(f)))
+    assert np.abs(out - ref).max() < 1e-13
+    trap, atom = np.array([1000.0, 1.0, 3.7]), np.array([86.9091835, 100.0])
+    o, _ = oracle.sample_atoms(trap, atom, 50, offset=4, seed=2, stream=1)
+    for i in range(50):
+        s = np.zeros(6)
+        he.he_sample_atom(P(trap), P(atom), C.c_ulonglong(2), C.c_ulonglong(4 + i), C.c_uint(1), C.c_double(1e-2), P(s))
+        assert np.array_equal(s, o[i])  # same operation order on the host: bit-identical
+
+
+def test_device_beam_code(pkg, oracle, he):
+    rng = np.random.default_rng(3)
+    xyz = np.ascontiguousarray(rng.normal(size=(300, 3)) * [1.5, 1.5, 30.0])
+    for p in ([2.0, 1.3, 7.0, "simp_flattop_HG", 6, 4, 1.3], [2.0, 1.3, 7.0, "simp_flattop_LG", 8, 0], [3.0, 10.0, 661.0, 0.3, 1],
+              [3.0, 50.0, 9879.0, np.pi / 2, 1], [3.0, 10.0, 661.0, 0.0, 1]):
+        b = pkg.beam_from_params(p, arb_bms=len(p) > 5)
+        out = np.zeros((len(xyz), 2))
+        assert he.he_eval_beam(C.byref(b), P(xyz), C.c_longlong(len(xyz)), P(out)) == 0
+        o = oracle.eval_beam(b, xyz)
+        assert np.abs(out[:, 0] + 1j * out[:, 1] - o).max() < 1e-12 * max(1.0, np.abs(o).max())
