@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -293,6 +294,7 @@ struct ca_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     ca::DevBuf scratch, accum, out, counters, in_samples, in_ph[4], in_f, in_models, in_tspan, misc;
+    std::map<int, ca::DevBuf> extra;  // buffers of other translation units (ca_lindblad2.cu), by id
     void* pinned = nullptr;
     size_t pinned_cap = 0;
 };
@@ -317,6 +319,13 @@ static int upload(ca_ctx* c, DevBuf& b, const void* host, size_t bytes) {
 
 cudaStream_t ctx_stream(ca_ctx* c) { return c->stream; }
 int ctx_sm_count(ca_ctx* c) { return c->sm_count; }
+int ctx_device(ca_ctx* c) { return c->device; }
+cudaEvent_t ctx_event(ca_ctx* c, int i) { return c->ev[i]; }
+void* ctx_buf(ca_ctx* c, int which, size_t bytes) {
+    DevBuf& b = c->extra[which];
+    if (b.ensure(bytes ? bytes : 8)) return nullptr;
+    return b.p;
+}
 
 template <int NS, bool SWEEP>
 static int launch_lindblad1(ca_ctx* c, const R1Params& P, int grid) {
@@ -521,6 +530,7 @@ int ca_finalize(ca_ctx* c) {
     DevBuf* bufs[] = {&c->scratch, &c->accum, &c->out, &c->counters, &c->in_samples, &c->in_ph[0], &c->in_ph[1], &c->in_ph[2], &c->in_ph[3],
                       &c->in_f, &c->in_models, &c->in_tspan, &c->misc};
     for (auto* b : bufs) b->release();
+    for (auto& kv : c->extra) kv.second.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
