@@ -1,0 +1,242 @@
+# NeutralAtomsB200.jl -- drop-in `ccall` shim: the reference's ensemble drivers on top of libcoldatoms_b200.so.
+#
+# Usage (in a Julia session that has the reference package loaded):
+#
+#     using NeutralAtoms                      # the unmodified reference (module name of this snapshot)
+#     include("NeutralAtomsB200.jl")          # defines module NeutralAtomsB200
+#     using .NeutralAtomsB200
+#     NeutralAtomsB200.init!("/path/to/libcoldatoms_b200.so"; device = 0)
+#     ρ, ρ2 = NeutralAtomsB200.simulation(cfg)            # same signature/return as NeutralAtoms.simulation
+#     NeutralAtomsB200.override!()                          # optional: make NeutralAtoms.simulation & co. call the GPU path
+#
+# Every function keeps the reference's signature, argument meaning and return shapes:
+#   simulation(cfg::RydbergConfig; temperature_calibrate=false, ode_kwargs...)   src/rydberg_model.jl:194-265
+#   simulation_czlp(cfg::CZLPConfig; ode_kwargs...)                              src/cz_model.jl:107-171
+#   simulation_blue_intens(tspan, ψ0, atom_params, trap_params, samples, ...)    src/rydberg_model_arb_bms.jl:15-86
+#   release_recapture(tspan, trap_params, atom_params, N; ...)                   src/basic_experiments.jl:72-81
+#   samples_generate(trap_params, atom_params, N; harmonic=true, ...)            src/atom_sampler.jl:80-96
+#   ϕ(tspan, f, amplitudes)                                                      src/lasernoise_sampler.jl:31-37
+# The ensemble loop (rydberg_model.jl:260-262, cz_model.jl:151), the samplers and every master_dynamic call run
+# inside ONE ccall.  There is no CUDA.jl fallback and no CPU fallback: if the library or a B200 is missing, init!
+# throws.  Julia is not available in the build container of this repository, so this file is exercised off-box
+# only (tests/julia_parity.jl); the same C ABI is driven by the Python mirror in the test-suite.
+module NeutralAtomsB200
+
+using NeutralAtoms
+using QuantumOptics
+using Libdl
+
+export simulation, simulation_czlp, simulation_blue_intens, release_recapture, samples_generate, ϕ
+
+# ---- mirror of include/coldatoms_b200.h ---------------------------------------------------------------
+struct CaBeam
+    Omega0::Float64; w0::Float64; z0::Float64; theta::Float64; n::Float64; sqz::Float64
+    kind::Int32; hg_n::Int32; hg_m::Int32; lg_l::Int32; _pad::Int32
+end
+struct CaModel
+    atom_m::Float64; atom_T::Float64
+    trap_U0::Float64; trap_w0::Float64; trap_z0::Float64
+    red::CaBeam; blue::CaBeam
+    Delta0::Float64; delta0::Float64
+    Gamma0::Float64; Gamma1::Float64; Gammal::Float64; Gammar::Float64
+    atom_motion::Int32; free_motion::Int32; laser_noise::Int32
+    decay_intermediate::Int32; decay_rydberg::Int32
+    doppler_kind::Int32; parallel::Int32; detuning_sign::Int32
+    compat::Int32; rho2_mode::Int32; n_noise_nodes::Int32; _pad::Int32
+    center1::NTuple{3,Float64}; center2::NTuple{3,Float64}
+    c6::Float64; xi::Float64
+end
+struct CaOde
+    reltol::Float64; abstol::Float64; dt::Float64; dtmax::Float64
+    maxiters::Int64; adaptive::Int32; dense::Int32
+end
+mutable struct CaStats
+    n_traj::Int64; n_rhs::Int64; n_accept::Int64; n_reject::Int64; n_sample_attempts::Int64
+    kernel_ms::Float64; total_ms::Float64; noise_ms::Float64
+    n_launches::Int32; status::Int32
+    CaStats() = new(0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
+end
+
+const BEAM_GAUSS, BEAM_HG, BEAM_LG, BEAM_UNIFORM = Int32(0), Int32(1), Int32(2), Int32(3)
+const DOPPLER_XZ, DOPPLER_Z = Int32(0), Int32(1)
+const SIGN_RYDBERG1, SIGN_CZ = Int32(0), Int32(1)
+const COMPAT_DEFAULT = Int32(1)
+
+const LIB = Ref{Ptr{Cvoid}}(C_NULL)
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+const SEED = Ref{UInt64}(0xC01DA705)
+
+sym(name) = Libdl.dlsym(LIB[], name)
+lasterr() = unsafe_string(ccall(sym(:ca_last_error), Cstring, ()))
+check(rc) = rc == 0 ? nothing : error("coldatoms_b200 error $rc: $(lasterr())")
+
+"Load the library and create the context on `device`. Throws if there is no sm_100 GPU (no fallback)."
+function init!(path::AbstractString; device::Integer = 0)
+    LIB[] = Libdl.dlopen(path)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall(sym(:ca_init), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx))
+    CTX[] = ctx[]
+    return nothing
+end
+finalize!() = (CTX[] != C_NULL && ccall(sym(:ca_finalize), Cint, (Ptr{Cvoid},), CTX[]); CTX[] = C_NULL; nothing)
+seed!(s::Integer) = (SEED[] = UInt64(s); nothing)
+function next_seed()   # successive calls draw independent ensembles, like Julia's advancing global RNG
+    SEED[] += 0x9E3779B97F4A7C15
+    z = SEED[]
+    z = (z ⊻ (z >> 30)) * 0xBF58476D1CE4E5B9
+    z = (z ⊻ (z >> 27)) * 0x94D049BB133111EB
+    return z ⊻ (z >> 31)
+end
+
+# Ω dispatch on the laser_params vector (src/rydberg_model.jl:51-74; Ω_red/Ω_blue of rydberg_model_arb_bms.jl:1-13)
+function beam(p; arb_bms = false)
+    Ω0, w0, z0 = Float64(p[1]), Float64(p[2]), Float64(p[3])
+    if length(p) == 3
+        return CaBeam(Ω0, w0, z0, 0.0, 1.0, 1.0, arb_bms ? BEAM_UNIFORM : BEAM_GAUSS, 0, 0, 0, 0)
+    elseif length(p) == 5
+        return CaBeam(Ω0, w0, z0, Float64(p[4]), Float64(p[5]), 1.0, BEAM_GAUSS, 0, 0, 0, 0)
+    elseif length(p) in (6, 7)
+        tag, n, m = p[4], Int32(p[5]), Int32(p[6])
+        if n == 0 && m == 0 && !arb_bms
+            return CaBeam(Ω0, w0, z0, 0.0, 1.0, 1.0, BEAM_GAUSS, 0, 0, 0, 0)
+        elseif tag == "simp_flattop_LG"
+            return CaBeam(Ω0, w0, z0, 0.0, 1.0, 1.0, BEAM_LG, 0, 0, n, 0)
+        elseif tag == "simp_flattop_HG" && length(p) == 7
+            return CaBeam(Ω0, w0, z0, 0.0, 1.0, Float64(p[7]), BEAM_HG, n, m, 0, 0)
+        end
+    end
+    error("unsupported laser_params $p")   # the reference silently returns `nothing` here
+end
+
+function model(cfg; two_atom = false)
+    c1 = two_atom ? Tuple(Float64.(cfg.atom_centers[1])) : (0.0, 0.0, 0.0)
+    c2 = two_atom ? Tuple(Float64.(cfg.atom_centers[2])) : (0.0, 0.0, 0.0)
+    CaModel(cfg.atom_params[1], cfg.atom_params[2], cfg.trap_params[1], cfg.trap_params[2], cfg.trap_params[3],
+            beam(cfg.red_laser_params), beam(cfg.blue_laser_params), cfg.detuning_params[1], cfg.detuning_params[2],
+            cfg.decay_params[1], cfg.decay_params[2], cfg.decay_params[3], cfg.decay_params[4],
+            cfg.atom_motion, cfg.free_motion, cfg.laser_noise, cfg.spontaneous_decay_intermediate, cfg.spontaneous_decay_rydberg,
+            DOPPLER_XZ, 0, two_atom ? SIGN_CZ : SIGN_RYDBERG1, COMPAT_DEFAULT, 0, 1001, 0, c1, c2,
+            two_atom ? cfg.c6 : 0.0, two_atom ? cfg.ξ : 0.0)
+end
+
+# `ode_kwargs...` are forwarded verbatim to OrdinaryDiffEq by the reference (rydberg_model.jl:255); the subset the
+# library understands: reltol, abstol, dt, dtmax, maxiters, adaptive (alg = DP5, Tsit5 accepted as alias)
+function ode(; reltol = 1e-6, abstol = 1e-8, dt = 0.0, dtmax = 0.0, maxiters = 100000, adaptive = true, alg = nothing, kw...)
+    isempty(kw) || error("unsupported ode_kwargs: $(keys(kw))")
+    CaOde(reltol, abstol, dt, dtmax, maxiters, adaptive, 1)
+end
+
+# column-major d×d complex blocks -> Vector{Operator} on basis b (what master_dynamic returns)
+function operators(buf::Vector{ComplexF64}, d::Int, nt::Int, b)
+    [Operator(b, b, reshape(buf[(j-1)*d*d+1:j*d*d], d, d)) for j in 1:nt]
+end
+
+null() = Ptr{Float64}(C_NULL)
+
+function run1(m::CaModel, tspan, ψ0data, n; samples = nothing, seed = next_seed(), f = nothing, ar = nothing, ab = nothing, o = ode())
+    nt = length(tspan)
+    ρ = zeros(ComplexF64, 25 * nt); ρ2 = zeros(ComplexF64, 25 * nt)
+    st = CaStats()
+    smp = samples === nothing ? null() : pointer(samples)
+    nf = f === nothing ? 0 : length(f)
+    GC.@preserve samples f ar ab begin
+        check(ccall(sym(:ca_rydberg1_run), Cint,
+            (Ptr{Cvoid}, Ref{CaModel}, Ptr{Float64}, Int32, Ptr{ComplexF64}, Int64, Int64, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
+            CTX[], m, Float64.(tspan), nt, ComplexF64.(ψ0data), n, 0, n, seed, smp, null(), null(),
+            f === nothing ? null() : pointer(f), ar === nothing ? null() : pointer(ar), ab === nothing ? null() : pointer(ab),
+            nf, o, 0, ρ, ρ2, st))
+    end
+    return ρ, ρ2, st
+end
+
+"`simulation(cfg::RydbergConfig; temperature_calibrate=false, ode_kwargs...)` -- src/rydberg_model.jl:194-265"
+function simulation(cfg::NeutralAtoms.RydbergConfig; temperature_calibrate = false, ode_kwargs...)
+    cfg_t = temperature_calibrate ? NeutralAtoms.calibrate_two_photon(cfg) : deepcopy(cfg)
+    noise = cfg_t.laser_noise
+    ρ, ρ2, _ = run1(model(cfg_t), cfg_t.tspan, cfg_t.ψ0.data, cfg_t.n_samples;
+                    f = noise ? cfg_t.f : nothing, ar = noise ? cfg_t.red_laser_phase_amplitudes : nothing,
+                    ab = noise ? cfg_t.blue_laser_phase_amplitudes : nothing, o = ode(; ode_kwargs...))
+    b = cfg_t.ψ0.basis
+    return operators(ρ, 5, length(cfg_t.tspan), b), operators(ρ2, 5, length(cfg_t.tspan), b)
+end
+
+"`simulation_blue_intens(...)` -- src/rydberg_model_arb_bms.jl:15-86 (semantics of SURVEY App. B7)"
+function simulation_blue_intens(tspan, ψ0, atom_params, trap_params, samples, red_laser_params, blue_laser_params,
+                                detuning_params, decay_params; atom_motion = true, free_motion = true,
+                                spontaneous_decay = true, parallel = false)
+    Γg, Γgt = spontaneous_decay ? decay_params : [0.0, 0.0]
+    m = CaModel(atom_params[1], atom_params[2], trap_params[1], trap_params[2], trap_params[3],
+                beam(red_laser_params[1:3]; arb_bms = true), beam(blue_laser_params; arb_bms = true),
+                detuning_params[1], detuning_params[2], Γgt, Γg, 0.0, 0.0, atom_motion, free_motion, false, true, false,
+                DOPPLER_Z, parallel, SIGN_RYDBERG1, 0, 0, 1001, 0, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 0.0, 0.0)
+    flat = collect(Iterators.flatten(samples))            # Vector{Vector} -> n×6 row-major
+    ρ, ρ2, _ = run1(m, tspan, ψ0.data, length(samples); samples = flat)
+    b = ψ0.basis
+    return operators(ρ, 5, length(tspan), b), operators(ρ2, 5, length(tspan), b)
+end
+
+"`simulation_czlp(cfg::CZLPConfig; ode_kwargs...)` -- src/cz_model.jl:107-171"
+function simulation_czlp(cfg::NeutralAtoms.CZLPConfig; ode_kwargs...)
+    nt = length(cfg.tspan)
+    ρ = zeros(ComplexF64, 625 * nt); ρ2 = zeros(ComplexF64, 625 * nt)
+    st = CaStats()
+    noise = cfg.laser_noise
+    f, ar, ab = cfg.f, cfg.red_laser_phase_amplitudes, cfg.blue_laser_phase_amplitudes
+    GC.@preserve f ar ab begin
+        check(ccall(sym(:ca_rydberg2_run), Cint,
+            (Ptr{Cvoid}, Ref{CaModel}, Ptr{Float64}, Int32, Ptr{ComplexF64}, Int64, Int64, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
+             Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
+            CTX[], model(cfg; two_atom = true), Float64.(cfg.tspan), nt, ComplexF64.(cfg.ψ0.data), cfg.n_samples, 0, cfg.n_samples,
+            next_seed(), null(), null(), Ptr{Ptr{Float64}}(C_NULL), noise ? pointer(f) : null(), noise ? pointer(ar) : null(),
+            noise ? pointer(ab) : null(), noise ? length(f) : 0, ode(; ode_kwargs...), 0, ρ, ρ2, st))
+    end
+    b = cfg.ψ0.basis
+    mk(buf) = [Operator(b, b, reshape(buf[(j-1)*625+1:j*625], 25, 25)) for j in 1:nt]
+    return mk(ρ), mk(ρ2)
+end
+
+"`release_recapture(tspan, trap_params, atom_params, N; freq, skip, eps, harmonic)` -- src/basic_experiments.jl:72-81"
+function release_recapture(tspan, trap_params, atom_params, N; freq = 10, skip = 1000, eps = 1e-3, harmonic = true)
+    harmonic || error("release_recapture(harmonic=false) needs the Metropolis sampler, which is not on the GPU path")
+    probs = zeros(Float64, length(tspan))
+    st = CaStats()
+    check(ccall(sym(:ca_release_recapture), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Int32,
+         Ptr{Float64}, Ptr{UInt8}, Ref{CaStats}),
+        CTX[], Float64.(trap_params), Float64.(atom_params), Float64.(tspan), length(tspan), N, 0, N, eps, next_seed(), null(), 0,
+        probs, Ptr{UInt8}(C_NULL), st))
+    return probs, 1.0
+end
+
+"`samples_generate(trap_params, atom_params, N; harmonic=true)` -- src/atom_sampler.jl:80-96 -> (Vector{Vector{Float64}}, 1)"
+function samples_generate(trap_params, atom_params, N; freq = 10, skip = 1000, harmonic = true, eps = 1e-2)
+    harmonic || error("samples_generate(harmonic=false) (Metropolis) is not on the GPU path")
+    out = zeros(Float64, 6, N)
+    att = Ref{Int64}(0)
+    check(ccall(sym(:ca_sample_atoms), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, UInt64, Int32, Float64, Ptr{Float64}, Ref{Int64}),
+        CTX[], Float64.(trap_params), Float64.(atom_params), N, 0, next_seed(), 0, eps, out, att))
+    return [out[:, i] for i in 1:N], 1
+end
+
+"`ϕ(tspan, f, amplitudes)` -- src/lasernoise_sampler.jl:31-37 (tspan must be a uniform grid starting at 0)"
+function ϕ(tspan, f, amplitudes)
+    out = zeros(Float64, length(tspan))
+    check(ccall(sym(:ca_phase_noise), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int64, UInt64, Int32, Ptr{Float64}, Ptr{Float64}),
+        CTX[], Float64.(tspan), length(tspan), Float64.(f), Float64.(amplitudes), length(f), 1, 0, next_seed(), 2, null(), out))
+    return out
+end
+
+"Route the reference's own entry points through the GPU path (fidelity.jl and user scripts keep working unchanged)."
+function override!()
+    @eval NeutralAtoms begin
+        simulation(cfg::RydbergConfig; kw...) = Main.NeutralAtomsB200.simulation(cfg; kw...)
+        simulation_czlp(cfg::CZLPConfig; kw...) = Main.NeutralAtomsB200.simulation_czlp(cfg; kw...)
+        release_recapture(tspan, trap_params, atom_params, N; kw...) = Main.NeutralAtomsB200.release_recapture(tspan, trap_params, atom_params, N; kw...)
+    end
+    return nothing
+end
+
+end # module
