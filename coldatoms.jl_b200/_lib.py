@@ -12,7 +12,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcoldatoms_b200.so")
+LIB_PATH = os.environ.get("COLDATOMS_B200_LIB", os.path.join(_HERE, "csrc", "libcoldatoms_b200.so"))  # env override: A/B builds
 
 dp = C.POINTER(C.c_double)
 _lib = None

@@ -71,6 +71,131 @@ CA_HD void sincos_d(double a, double* s, double* c) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Lean fp64 math for the hot loop.  All literals live in ONE constant-memory struct so that they reach the
+// FP64 pipe as c[bank][offset] operands (the CUDA math library materialises each 64-bit literal with two UMOVs:
+// 15% of all issued instructions in the first profile).  Accuracy ~1 ulp; arguments outside the fast range fall
+// back to the library.
+// ---------------------------------------------------------------------------------------------------
+struct MathConsts {
+    double log2e, ln2_hi, ln2_lo, magic;                 // exp
+    double ex[14];                                       // 1/k!
+    double two_over_pi, pio2_hi, pio2_mid, pio2_lo;      // sincos
+    double sn[6], cs[6];                                 // fdlibm kernel_sin / kernel_cos minimax coefficients
+    // Dormand-Prince 5(4)
+    double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, b1, b3, b4, b5, b6;
+    double c2, c3, c4, c5, e1, e3, e4, e5, e6, e7, d1, d3, d4, d5, d6, d7;
+    // the same tableau as rows indexed by stage (rolled stage loop): ra[s][j] = a_sj, rc[s] = c_s, rb/re/rd[j] = b_j, e_j, d_j
+    double ra[8][8], rc[8], rb[8], re[8], rd[8];
+};
+#define CA_MATH_CONSTS_INIT                                                                                                      \
+    {1.4426950408889634, 0.6931471805599453, 2.3190468138462996e-17, 6755399441055744.0,                                         \
+     {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800,              \
+      1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0},                                                                      \
+     0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,                                     \
+     {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,          \
+      -2.50507602534068634195e-08, 1.58969099521155010221e-10},                                                                  \
+     {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,          \
+      2.08757232129817482790e-09, -1.13596475577881948265e-11},                                                                  \
+     1.0 / 5.0, 3.0 / 40.0, 9.0 / 40.0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 19372.0 / 6561.0, -25360.0 / 2187.0,              \
+     64448.0 / 6561.0, -212.0 / 729.0, 9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,        \
+     35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0, 0.2, 0.3, 0.8, 8.0 / 9.0, 71.0 / 57600.0,       \
+     -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0, -12715105075.0 / 11282082432.0,             \
+     87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0, 701980252875.0 / 199316789632.0,                              \
+     -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0,                                                                       \
+     {{0}, {0}, {0, 1.0 / 5.0}, {0, 3.0 / 40.0, 9.0 / 40.0}, {0, 44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0},                        \
+      {0, 19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0},                                               \
+      {0, 9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0}, {0}},                             \
+     {0, 0, 0.2, 0.3, 0.8, 8.0 / 9.0, 1.0, 1.0},                                                                                 \
+     {0, 35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0, 0},                                      \
+     {0, 71.0 / 57600.0, 0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0},                     \
+     {0, -12715105075.0 / 11282082432.0, 0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,                        \
+      701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0}}
+#if defined(__CUDACC__)
+static __constant__ MathConsts c_mc = CA_MATH_CONSTS_INIT;
+#endif
+static const MathConsts h_mc = CA_MATH_CONSTS_INIT;
+#if defined(__CUDA_ARCH__)
+#define MC c_mc
+#else
+#define MC h_mc
+#endif
+
+CA_HD double rcp_d(double x) {  // 1/x for normal x (no special cases): MUFU seed + 2 Newton steps
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+CA_HD double sqrt_d(double x) {  // sqrt for x >= 0 (0 -> 0)
+#if defined(__CUDA_ARCH__)
+    if (!(x > 0.0)) return 0.0;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    double d = fma(-g, g, x);
+    return fma(d, h, g);
+#else
+    return sqrt(x);
+#endif
+}
+CA_HD double exp_d(double x) {
+    if (!(x > -700.0 && x < 700.0)) return exp(x);
+    const double t = fma(x, MC.log2e, MC.magic);
+    const double n = t - MC.magic;
+    double r = fma(-n, MC.ln2_hi, x);
+    r = fma(-n, MC.ln2_lo, r);
+    // degree-13 Taylor polynomial in Estrin form (|r| <= ln2/2: truncation 4e-18)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = fma(MC.ex[1], r, MC.ex[0]), p23 = fma(MC.ex[3], r, MC.ex[2]), p45 = fma(MC.ex[5], r, MC.ex[4]),
+                 p67 = fma(MC.ex[7], r, MC.ex[6]), p89 = fma(MC.ex[9], r, MC.ex[8]), pab = fma(MC.ex[11], r, MC.ex[10]),
+                 pcd = fma(MC.ex[13], r, MC.ex[12]);
+    const double q0 = fma(p23, r2, p01), q1 = fma(p67, r2, p45), q2 = fma(pab, r2, p89);
+    const double s0 = fma(q1, r4, q0), s1 = fma(pcd, r4, q2);
+    const double p = fma(s1, r8, s0);
+#if defined(__CUDA_ARCH__)
+    const int k = __double2loint(t);
+    return p * __hiloint2double((k + 1023) << 20, 0);
+#else
+    return ldexp(p, (int)n);
+#endif
+}
+CA_HD void sincos_fast(double a, double* sn, double* cs) {
+    if (!(fabs(a) < 1.0e6)) { sincos_d(a, sn, cs); return; }
+    const double t = fma(a, MC.two_over_pi, MC.magic);
+    const double n = t - MC.magic;
+    double r = fma(-n, MC.pio2_hi, a);
+    r = fma(-n, MC.pio2_mid, r);
+    r = fma(-n, MC.pio2_lo, r);
+    const double z = r * r;
+    double ps = fma(MC.sn[5], z, MC.sn[4]);
+    double pc = fma(MC.cs[5], z, MC.cs[4]);
+    ps = fma(ps, z, MC.sn[3]); pc = fma(pc, z, MC.cs[3]);
+    ps = fma(ps, z, MC.sn[2]); pc = fma(pc, z, MC.cs[2]);
+    ps = fma(ps, z, MC.sn[1]); pc = fma(pc, z, MC.cs[1]);
+    ps = fma(ps, z, MC.sn[0]); pc = fma(pc, z, MC.cs[0]);
+    const double s = fma(ps * z, r, r);
+    const double c = fma(pc * z, z, fma(-0.5, z, 1.0));
+#if defined(__CUDA_ARCH__)
+    const int q = __double2loint(t);
+#else
+    const int q = (int)(long long)n;
+#endif
+    const double ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
+    *sn = (q & 2) ? -ss : ss;
+    *cs = ((q + 1) & 2) ? -cc : cc;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Derived (device) model: everything that is constant over the ensemble, precomputed on the host.
 // ---------------------------------------------------------------------------------------------------
 struct DevBeam {
@@ -116,18 +241,18 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
         double r2 = x * x + y * y;
         double xr2, zr;
         if (b.sn == 0.0 && b.cs == 1.0) { xr2 = r2; zr = z; }
-        else { double rp = sqrt(r2); double xr = rp * b.cs - z * b.sn; zr = rp * b.sn + z * b.cs; xr2 = xr * xr; }
+        else { double rp = sqrt_d(r2); double xr = rp * b.cs - z * b.sn; zr = rp * b.sn + z * b.cs; xr2 = xr * xr; }
         double s = zr * b.inv_z0;
-        double iq = 1.0 / (1.0 + s * s);
+        double iq = rcp_d(1.0 + s * s);
         double g = xr2 * b.inv_w0sq * iq;
-        double e = b.hO * iq * exp(-g);
+        double e = b.hO * iq * exp_d(-g);
         double sn, cs;
-        sincos_d(phi - s * g, &sn, &cs);
+        sincos_fast(phi - s * g, &sn, &cs);
         *re = e * (cs - s * sn);
         *im = e * (sn + s * cs);
     } else if (b.kind == CA_BEAM_UNIFORM) {
         double sn, cs;
-        sincos_d(phi, &sn, &cs);
+        sincos_fast(phi, &sn, &cs);
         *re = b.hO * cs; *im = b.hO * sn;
     } else {
         // flat-top HG / LG (arbitrary_beams.jl:50-81): E = Ω (w0/w) e^{-i phase0} Σ c HG HG e^{-i(i+j+1)at}
@@ -191,6 +316,65 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
     }
 }
 
+// Both Gaussian beams in ONE straight-line block (no branches, no library calls): the two exp / sincos dependency
+// chains are independent, so the scheduler interleaves them (ILP 2) -- with branches between them (kind dispatch,
+// range checks) each chain ran alone and the FP64 pipe idled on its latency.  Phases are assumed |φ| < 1e8.
+CA_HD void gauss_pair(const DevBeam& br, const DevBeam& bb, double x, double y, double z, double phr, double phb, double* o) {
+    const double r2 = x * x + y * y;
+    const double rp = sqrt_d(fmax(r2, 1e-300));
+    double re[2], im[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const DevBeam& b = q == 0 ? br : bb;
+        const double phi = q == 0 ? phr : phb;
+        const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
+        const double s = zr * b.inv_z0;
+        const double iq = rcp_d(fma(s, s, 1.0));
+        const double g = xr * xr * b.inv_w0sq * iq;
+        // exp(-g), g >= 0 (clamped instead of branching)
+        const double xx = fmax(-g, -700.0);
+        const double t = fma(xx, MC.log2e, MC.magic);
+        const double n = t - MC.magic;
+        double r = fma(-n, MC.ln2_hi, xx);
+        r = fma(-n, MC.ln2_lo, r);
+        const double q2 = r * r, q4 = q2 * q2, q8 = q4 * q4;
+        const double p01 = fma(MC.ex[1], r, MC.ex[0]), p23 = fma(MC.ex[3], r, MC.ex[2]), p45 = fma(MC.ex[5], r, MC.ex[4]),
+                     p67 = fma(MC.ex[7], r, MC.ex[6]), p89 = fma(MC.ex[9], r, MC.ex[8]), pab = fma(MC.ex[11], r, MC.ex[10]),
+                     pcd = fma(MC.ex[13], r, MC.ex[12]);
+        const double e0 = fma(fma(pcd, q4, fma(pab, q2, p89)), q8, fma(fma(p67, q2, p45), q4, fma(p23, q2, p01)));
+#if defined(__CUDA_ARCH__)
+        const double e = b.hO * iq * e0 * __hiloint2double((__double2loint(t) + 1023) << 20, 0);
+#else
+        const double e = b.hO * iq * ldexp(e0, (int)n);
+#endif
+        // sincos(phi - s g)
+        const double a = fma(-s, g, phi);
+        const double t2 = fma(a, MC.two_over_pi, MC.magic);
+        const double m2 = t2 - MC.magic;
+        double w = fma(-m2, MC.pio2_hi, a);
+        w = fma(-m2, MC.pio2_mid, w);
+        w = fma(-m2, MC.pio2_lo, w);
+        const double zz = w * w;
+        double ps = fma(MC.sn[5], zz, MC.sn[4]), pc = fma(MC.cs[5], zz, MC.cs[4]);
+        ps = fma(ps, zz, MC.sn[3]); pc = fma(pc, zz, MC.cs[3]);
+        ps = fma(ps, zz, MC.sn[2]); pc = fma(pc, zz, MC.cs[2]);
+        ps = fma(ps, zz, MC.sn[1]); pc = fma(pc, zz, MC.cs[1]);
+        ps = fma(ps, zz, MC.sn[0]); pc = fma(pc, zz, MC.cs[0]);
+        const double sv = fma(ps * zz, w, w);
+        const double cv = fma(pc * zz, zz, fma(-0.5, zz, 1.0));
+#if defined(__CUDA_ARCH__)
+        const int qd = __double2loint(t2);
+#else
+        const int qd = (int)(long long)m2;
+#endif
+        const double ss = (qd & 1) ? cv : sv, cc = (qd & 1) ? sv : cv;
+        const double sn = (qd & 2) ? -ss : ss, cs = ((qd + 1) & 2) ? -cc : cc;
+        re[q] = e * (cs - s * sn);
+        im[q] = e * (sn + s * cs);
+    }
+    o[0] = re[0]; o[1] = im[0]; o[2] = re[1]; o[3] = im[1];
+}
+
 // IEEE operations without FMA contraction: the sampler's rejection test and the recapture indicator are
 // evaluated in the reference's operation order so that they round exactly like the oracle (-ffp-contract=off).
 #if defined(__CUDA_ARCH__)
@@ -247,28 +431,41 @@ template <int CH>
 CA_HD void gen_noise_trace(const double* __restrict__ f, const double* __restrict__ amp, int nf, int n_nodes, double dtn,
                            const double* __restrict__ phases, uint64_t seed, uint64_t gi, uint32_t stream, double* __restrict__ out,
                            int stride) {
+    constexpr int KB = 4;  // frequencies advanced together: 4 independent c/d chains hide the FP64 latency
     for (int c0 = 0; c0 < n_nodes; c0 += CH) {
         double acc[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) acc[j] = 0.0;
-        double t0 = c0 * dtn;
-        double ph_next = 0.0;
-        for (int k = 0; k < nf; ++k) {
-            double ph;
-            if (phases) ph = phases[k];
-            else if (k & 1) ph = ph_next;
-            else { U4 w = philox(seed, gi, (uint32_t)(k >> 1), stream); ph = kTwoPi * u53(w.x, w.y); ph_next = kTwoPi * u53(w.z, w.w); }
-            double om = kTwoPi * f[k];
-            double s0, c0v, sh, ch;
-            sincos_d(om * t0 + ph, &s0, &c0v);
-            sincos_d(0.5 * om * dtn, &sh, &ch);
-            double a = amp[k];
-            double sig = -4.0 * sh * sh;
-            double c = a * c0v;
-            double d = -2.0 * a * (s0 * ch + c0v * sh) * sh;  // c_1 - c_0 = -2 a sin(θ0 + δ/2) sin(δ/2)
-            acc[0] += c;
+        const double t0 = c0 * dtn;
+        for (int k0 = 0; k0 < nf; k0 += KB) {
+            double c[KB], d[KB], sig[KB];
 #pragma unroll
-            for (int j = 1; j < CH; ++j) { c += d; d += sig * c; acc[j] += c; }
+            for (int q = 0; q < KB; q += 2) {
+                // phases of frequencies k0+q, k0+q+1 come from one Philox call (k0 and KB are even)
+                double ph0, ph1;
+                if (phases) { ph0 = k0 + q < nf ? phases[k0 + q] : 0.0; ph1 = k0 + q + 1 < nf ? phases[k0 + q + 1] : 0.0; }
+                else { U4 w = philox(seed, gi, (uint32_t)((k0 + q) >> 1), stream); ph0 = kTwoPi * u53(w.x, w.y); ph1 = kTwoPi * u53(w.z, w.w); }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = k0 + q + e;
+                    const bool live = k < nf;
+                    const double om = kTwoPi * (live ? f[k] : 0.0);
+                    const double a = live ? amp[k] : 0.0;
+                    double s0, c0v, sh, ch;
+                    sincos_fast(om * t0 + (e ? ph1 : ph0), &s0, &c0v);
+                    sincos_fast(0.5 * om * dtn, &sh, &ch);
+                    sig[q + e] = -4.0 * sh * sh;
+                    c[q + e] = a * c0v;
+                    d[q + e] = -2.0 * a * (s0 * ch + c0v * sh) * sh;  // c_1 - c_0 = -2 a sin(θ0 + δ/2) sin(δ/2)
+                }
+            }
+            acc[0] += (c[0] + c[1]) + (c[2] + c[3]);
+#pragma unroll
+            for (int j = 1; j < CH; ++j) {
+#pragma unroll
+                for (int q = 0; q < KB; ++q) { c[q] += d[q]; d[q] = fma(sig[q], c[q], d[q]); }
+                acc[j] += (c[0] + c[1]) + (c[2] + c[3]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j)
@@ -346,6 +543,12 @@ struct OdeOpts {
 };
 
 // Per-trajectory integrator state. NS = 9 (+6 per spectator row).
+//
+// Storage plan (from the first ncu profile: at 255 registers/thread only 8 warps/SM were resident and spill reloads
+// + register shuffling dominated the stalls): the DP5 stage derivatives k1..k7 live in SHARED memory, laid out
+// [slot][component][thread] (conflict-free), six slots per thread (k7 reuses k2's slot; FSAL k1 <- k7 is a toggle of
+// the slot index, not a copy).  Registers hold only y, the stage input, the stage output and y_new.  The stage loop is
+// rolled (dynamic slot / tableau indexing works in shared and constant memory), so the whole step is a few KB of code.
 template <int NS>
 struct Lane1 {
     // trajectory
@@ -356,12 +559,19 @@ struct Lane1 {
     int stride, jc;
     double pr0, prs, pb0, pbs, tj;
     // integrator
-    double t, h, dt, lnq_old;
-    double y[NS], k1[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS], un[NS];
+    double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
+    int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
+    double t, h, dt, lnq_old, tcommit;
+    double y[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
     long long iters;
     int n_rhs, n_acc, n_rej;
     int status;
+
+    CA_HD double* kptr(int j) const {     // j = 1..7
+        const int slot = (j == 1) ? p : ((j == 2 || j == 7) ? 1 - p : j - 1);
+        return kb + (size_t)slot * NS * kstride;
+    }
 
     CA_HD void coefficients(const DevModel& m, double tt, Coef& c) {
         double X, Y, Z, Vx, Vz;
@@ -370,8 +580,8 @@ struct Lane1 {
             c.dp = dpc; c.dr = drc;
         } else {  // R, V: atom_sampler.jl:125-143
             double sr, cr, sz, cz;
-            sincos_d(m.wr * tt, &sr, &cr);
-            sincos_d(m.wz * tt, &sz, &cz);
+            sincos_fast(m.wr * tt, &sr, &cr);
+            sincos_fast(m.wz * tt, &sz, &cz);
             X = x0 * cr + vx / m.wr * sr; Y = y0 * cr + vy / m.wr * sr; Z = z0 * cz + vz / m.wz * sz;
             Vx = vx * cr - x0 * m.wr * sr;
             Vz = vzq * cz - z0 * m.wz * sz;
@@ -386,33 +596,41 @@ struct Lane1 {
             if (j != jc) {
                 jc = j;
                 tj = j * m.dtn;
-                const double* p = tab + (size_t)j * stride;
-                double a0 = p[0], a1 = p[stride];
-                const double* q = p + (size_t)m.n_nodes * stride;
-                double b0 = q[0], b1 = q[stride];
+                const double* q0 = tab + (size_t)j * stride;
+                double a0 = q0[0], a1 = q0[stride];
+                const double* q1 = q0 + (size_t)m.n_nodes * stride;
+                double b0 = q1[0], b1 = q1[stride];
                 pr0 = a0; prs = (a1 - a0) * m.inv_dtn; pb0 = b0; pbs = (b1 - b0) * m.inv_dtn;
             }
             double w = tt - tj;
             pr = pr0 + w * prs; pb = pb0 + w * pbs;
         }
         if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
-        beam_half_omega(m.red, X, Y, Z, pr, &c.Ar, &c.Ai);
-        beam_half_omega(m.blue, X, Y, Z, pb, &c.Br, &c.Bi);
+        if (m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS) {
+            double o[4];
+            gauss_pair(m.red, m.blue, X, Y, Z, pr, pb, o);
+            c.Ar = o[0]; c.Ai = o[1]; c.Br = o[2]; c.Bi = o[3];
+        } else {
+            beam_half_omega(m.red, X, Y, Z, pr, &c.Ar, &c.Ai);
+            beam_half_omega(m.blue, X, Y, Z, pb, &c.Br, &c.Bi);
+        }
     }
 
     // error-norm contribution helpers (DiffEqBase: |err| / (atol + rtol max(|u0|,|u1|)), complex modulus)
     static CA_HD double nrm_real(double e, double a, double b, double atol, double rtol) {
         double sc = atol + rtol * fmax(fabs(a), fabs(b));
-        double r = e / sc;
+        double r = e * rcp_d(sc);
         return r * r;
     }
     static CA_HD double nrm_cplx(double er, double ei, double ar, double ai, double br, double bi, double atol, double rtol) {
-        double sc = atol + rtol * sqrt(fmax(ar * ar + ai * ai, br * br + bi * bi));
-        return 2.0 * (er * er + ei * ei) / (sc * sc);  // both (i,j) and (j,i) entries of the full matrix
+        double sc = atol + rtol * sqrt_d(fmax(ar * ar + ai * ai, br * br + bi * bi));
+        double isc = rcp_d(sc);
+        return 2.0 * (er * er + ei * ei) * (isc * isc);  // both (i,j) and (j,i) entries of the full matrix
     }
 
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
-                    double t0) {
+                    double t0, double* kbase, int kstr) {
+        kb = kbase; kstride = kstr; p = 0;
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
         vzq = m.vz_from_vy ? vy : vz;
@@ -443,9 +661,15 @@ struct Lane1 {
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
         t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; status = 0;
         lnq_old = log(1e-4);
+        double k1[NS];
         Coef cf0;
         coefficients(m, t, cf0);
         lindblad_rhs<NS>(cf0, g, y, k1);
+        {
+            double* k1p = kptr(1);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) k1p[i * kstride] = k1[i];
+        }
         g1[0] = g.G0 * y[2]; g1[1] = g.Gl * y[2] + g.Gr * y[1];
         n_rhs = 1;
 #pragma unroll
@@ -494,123 +718,88 @@ struct Lane1 {
         }
     }
 
-    // time at the end of the last accepted step (== t before the first step)
-    CA_HD double t_new() const { return t + h; }
-
     // Commit the pending accepted step (FSAL) and attempt one new step towards `tstop`.
     CA_HD void attempt(const DevModel& m, const Rates& g, const OdeOpts& oo, double tstop) {
-        if (h != 0.0) {  // commit: y <- un, k1 <- k7, t <- t+h
+        if (h != 0.0) {  // commit: y <- un, k1 <- k7 (slot toggle), t <- t+h
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { y[i] = un[i]; k1[i] = k7[i]; }
+            for (int i = 0; i < NS; ++i) y[i] = un[i];
             P[0] = Pn[0]; P[1] = Pn[1]; g1[0] = g7[0]; g1[1] = g7[1];
             t = tcommit;
             h = 0.0;
+            p ^= 1;
         }
         if (++iters > oo.maxiters) { status = CA_ERR_MAXITERS; return; }
         double hh = fmin(dt, oo.dtmax);
         bool clipped = false;
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
-        // Stages 2..7 run through ONE copy of the coefficient + RHS code (a rolled loop; the per-stage linear
-        // combinations are switch cases so every array index stays a compile-time constant and the state stays in
-        // registers).  Keeping the loop body small matters: fully unrolled the step is far larger than the
-        // instruction caches.  Stage 6 and 7 share their coefficients (c6 = c7 = 1) and stage 7 is the next
-        // step's stage 1 (FSAL).
-        double us[NS], ko[NS], k2[NS];
-        Coef cf7;
         const double tn = clipped ? tstop : t + hh;
+        double us[NS], ko[NS];
+        Coef cf;
         // population quadratures: ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr, accumulated with the b/e/d weights
-        double SB0 = dp::b1 * g1[0], SB1 = dp::b1 * g1[1], SE0 = dp::e1 * g1[0], SE1 = dp::e1 * g1[1], SD0 = dp::d1 * g1[0],
-               SD1 = dp::d1 * g1[1];
+        double SB0 = MC.rb[1] * g1[0], SB1 = MC.rb[1] * g1[1], SE0 = MC.re[1] * g1[0], SE1 = MC.re[1] * g1[1], SD0 = MC.rd[1] * g1[0],
+               SD1 = MC.rd[1] * g1[1];
 #pragma unroll 1
-        for (int s = 2; s <= 7; ++s) {
-            double ts, wb, we, wd;
-            switch (s) {
-                case 2:
+        for (int s = 2; s <= 6; ++s) {
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a21 * k1[i]);
-                    ts = t + dp::c2 * hh; wb = 0.0; we = 0.0; wd = 0.0;
-                    break;
-                case 3:
+            for (int i = 0; i < NS; ++i) us[i] = 0.0;
+#pragma unroll 1
+            for (int j = 1; j < s; ++j) {
+                const double w = MC.ra[s][j];
+                const double* kp = kptr(j);
+                double kv[NS];  // all loads first, then the FMAs (otherwise each FMA waits for its own LDS)
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a31 * k1[i] + dp::a32 * k2[i]);
-                    ts = t + dp::c3 * hh; wb = dp::b3; we = dp::e3; wd = dp::d3;
-                    break;
-                case 4:
+                for (int i = 0; i < NS; ++i) kv[i] = kp[i * kstride];
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) us[i] = y[i] + hh * (dp::a41 * k1[i] + dp::a42 * k2[i] + dp::a43 * k3[i]);
-                    ts = t + dp::c4 * hh; wb = dp::b4; we = dp::e4; wd = dp::d4;
-                    break;
-                case 5:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i)
-                        us[i] = y[i] + hh * (dp::a51 * k1[i] + dp::a52 * k2[i] + dp::a53 * k3[i] + dp::a54 * k4[i]);
-                    ts = t + dp::c5 * hh; wb = dp::b5; we = dp::e5; wd = dp::d5;
-                    break;
-                case 6:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i)
-                        us[i] = y[i] + hh * (dp::a61 * k1[i] + dp::a62 * k2[i] + dp::a63 * k3[i] + dp::a64 * k4[i] + dp::a65 * k5[i]);
-                    ts = tn; wb = dp::b6; we = dp::e6; wd = dp::d6;
-                    break;
-                default:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) us[i] = un[i];
-                    ts = tn; wb = 0.0; we = dp::e7; wd = dp::d7;
-                    break;
+                for (int i = 0; i < NS; ++i) us[i] = fma(w, kv[i], us[i]);
             }
-            if (s <= 6) coefficients(m, ts, cf7);
-            lindblad_rhs<NS>(cf7, g, us, ko);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) us[i] = fma(hh, us[i], y[i]);
+            coefficients(m, s == 6 ? tn : fma(MC.rc[s], hh, t), cf);
+            lindblad_rhs<NS>(cf, g, us, ko);
             {
                 const double gg0 = g.G0 * us[2], gg1 = g.Gl * us[2] + g.Gr * us[1];
-                SB0 += wb * gg0; SB1 += wb * gg1; SE0 += we * gg0; SE1 += we * gg1; SD0 += wd * gg0; SD1 += wd * gg1;
-                g7[0] = gg0; g7[1] = gg1;
+                const double wb = MC.rb[s], we = MC.re[s], wd = MC.rd[s];
+                SB0 = fma(wb, gg0, SB0); SB1 = fma(wb, gg1, SB1); SE0 = fma(we, gg0, SE0); SE1 = fma(we, gg1, SE1);
+                SD0 = fma(wd, gg0, SD0); SD1 = fma(wd, gg1, SD1);
             }
-            switch (s) {
-                case 2:
+            double* ks = kptr(s);
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) k2[i] = ko[i];
-                    break;
-                case 3:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) k3[i] = ko[i];
-                    break;
-                case 4:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) k4[i] = ko[i];
-                    break;
-                case 5:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) k5[i] = ko[i];
-                    break;
-                case 6:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) {
-                        k6[i] = ko[i];
-                        un[i] = y[i] + hh * (dp::b1 * k1[i] + dp::b3 * k3[i] + dp::b4 * k4[i] + dp::b5 * k5[i] + dp::b6 * k6[i]);
-                    }
-                    break;
-                default:
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) k7[i] = ko[i];
-                    break;
-            }
+            for (int i = 0; i < NS; ++i) ks[i * kstride] = ko[i];
         }
+        // y_new and the error combination share one pass over k1,k3..k6 (ko still holds k6)
+        double er[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { un[i] = MC.rb[6] * ko[i]; er[i] = MC.re[6] * ko[i]; }
+#pragma unroll 1
+        for (int j = 1; j <= 5; ++j) {
+            if (j == 2) continue;
+            const double wb = MC.rb[j], we = MC.re[j];
+            const double* kp = kptr(j);
+            double kv[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) kv[i] = kp[i * kstride];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { un[i] = fma(wb, kv[i], un[i]); er[i] = fma(we, kv[i], er[i]); }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) un[i] = fma(hh, un[i], y[i]);
+        lindblad_rhs<NS>(cf, g, un, ko);  // stage 7 = next step's stage 1; same coefficients as stage 6 (c6 = c7 = 1)
+        {
+            double* k7p = kptr(7);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { k7p[i * kstride] = ko[i]; er[i] = hh * fma(MC.re[7], ko[i], er[i]); }
+        }
+        g7[0] = g.G0 * un[2]; g7[1] = g.Gl * un[2] + g.Gr * un[1];
+        SE0 = fma(MC.re[7], g7[0], SE0); SE1 = fma(MC.re[7], g7[1], SE1); SD0 = fma(MC.rd[7], g7[0], SD0); SD1 = fma(MC.rd[7], g7[1], SD1);
         Pn[0] = P[0] + hh * SB0; Pn[1] = P[1] + hh * SB1;
         n_rhs += 6;
         bool accept = true;
         if (oo.adaptive) {
             double s = nrm_real(hh * SE0, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(hh * SE1, P[1], Pn[1], oo.atol, oo.rtol);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double e = hh * (dp::e1 * k1[i] + dp::e3 * k3[i] + dp::e4 * k4[i] + dp::e5 * k5[i] + dp::e6 * k6[i] + dp::e7 * k7[i]);
-                s += nrm_real(e, y[i], un[i], oo.atol, oo.rtol);
-            }
+            for (int i = 0; i < 3; ++i) s += nrm_real(er[i], y[i], un[i], oo.atol, oo.rtol);
 #pragma unroll
-            for (int i = 3; i < NS; i += 2) {
-                double er = hh * (dp::e1 * k1[i] + dp::e3 * k3[i] + dp::e4 * k4[i] + dp::e5 * k5[i] + dp::e6 * k6[i] + dp::e7 * k7[i]);
-                double ei = hh * (dp::e1 * k1[i + 1] + dp::e3 * k3[i + 1] + dp::e4 * k4[i + 1] + dp::e5 * k5[i + 1] + dp::e6 * k6[i + 1] + dp::e7 * k7[i + 1]);
-                s += nrm_cplx(er, ei, y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
-            }
+            for (int i = 3; i < NS; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
             double EEst2 = s * (1.0 / 25.0);
             if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; return; }
             // PI controller: q = EEst^β1 / qold^β2 / γ clipped to [1/qmax, 1/qmin]; β1 = 0.17, β2 = 0.04
@@ -618,15 +807,15 @@ struct Lane1 {
             const double ln_qoldinit = -9.210340371976182;  // log(1e-4)
             double q, lnE = 0.0;
             if (EEst2 == 0.0) q = 1.0 / qmax;
-            else { lnE = 0.5 * log(EEst2); q = exp(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
+            else { lnE = 0.5 * log(EEst2); q = exp_d(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
             if (EEst2 <= 1.0) {
                 lnq_old = (EEst2 == 0.0) ? ln_qoldinit : fmax(lnE, ln_qoldinit);
-                double prop = hh / q;
+                double prop = hh * rcp_d(q);
                 dt = clipped ? fmax(dt, prop) : prop;
             } else {
                 accept = false;
-                double q11 = exp(beta1 * lnE);
-                dt = hh / fmin(1.0 / qmin, q11 / gam);
+                double q11 = exp_d(beta1 * lnE);
+                dt = hh * rcp_d(fmin(1.0 / qmin, q11 * (1.0 / gam)));
                 n_rej++;
                 if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; return; }
             }
@@ -640,8 +829,6 @@ struct Lane1 {
         }
     }
 
-    double tcommit;
-
     // State at time T inside the last accepted step [t, t+h] (Hairer contd5), Hermitian-packed ρ into out[0..24].
     CA_HD void state_at(const DevModel& m, double T, double* out) const {
         double s[NS], p0, p1;
@@ -651,12 +838,14 @@ struct Lane1 {
             p0 = Pn[0]; p1 = Pn[1];
         } else {
             double th = (T - t) / h, th1 = 1.0 - th;
+            const double *k1 = kptr(1), *k3 = kptr(3), *k4 = kptr(4), *k5 = kptr(5), *k6 = kptr(6), *k7 = kptr(7);
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
+                const int o = i * kstride;
                 double r2 = un[i] - y[i];
-                double r3 = h * k1[i] - r2;
-                double r4 = r2 - h * k7[i] - r3;
-                double r5 = h * (dp::d1 * k1[i] + dp::d3 * k3[i] + dp::d4 * k4[i] + dp::d5 * k5[i] + dp::d6 * k6[i] + dp::d7 * k7[i]);
+                double r3 = h * k1[o] - r2;
+                double r4 = r2 - h * k7[o] - r3;
+                double r5 = h * (MC.rd[1] * k1[o] + MC.rd[3] * k3[o] + MC.rd[4] * k4[o] + MC.rd[5] * k5[o] + MC.rd[6] * k6[o] + MC.rd[7] * k7[o]);
                 s[i] = y[i] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
             }
             {

@@ -59,9 +59,14 @@ struct R1Params {
     int n_points, nt, nf, n_nodes_max;
 };
 
+template <int NS>
+constexpr int blocks_per_sm() { return NS == 9 ? 3 : (NS == 15 ? 2 : 1); }
+
 template <int NS, bool SWEEP>
-__global__ void __launch_bounds__(kThreads1, 2) k_lindblad1(const __grid_constant__ R1Params P) {
-    __shared__ DevModel sm_models[SWEEP ? kThreads1 / 32 : 1];
+__global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sk = reinterpret_cast<double*>(smem_raw);                                   // [6][NS][kThreads1]
+    DevModel* sm_models = reinterpret_cast<DevModel*>(sk + 6 * NS * kThreads1);         // [warps] (sweeps only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (kThreads1 / 32) + warp;
     const long long W = (long long)gridDim.x * (kThreads1 / 32);
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(kThreads1, 2) k_lindblad1(const __grid_constan
         }
         // ---- K3: integrate
         Lane1<NS> L;
-        L.init(m, rt, P.ode, smp, tab, 32, tsp[0]);
+        L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, kThreads1);
         const double tend = tsp[P.nt - 1];
         double* acc_pt = P.accum + (size_t)pt * P.nt * kNV;
         for (int j = 0; j < P.nt; ++j) {
@@ -329,7 +334,9 @@ void* ctx_buf(ca_ctx* c, int which, size_t bytes) {
 
 template <int NS, bool SWEEP>
 static int launch_lindblad1(ca_ctx* c, const R1Params& P, int grid) {
-    k_lindblad1<NS, SWEEP><<<grid, kThreads1, 0, c->stream>>>(P);
+    const size_t smem = sizeof(double) * 6 * NS * kThreads1 + (SWEEP ? sizeof(DevModel) * (kThreads1 / 32) : 0);
+    CA_CUDA(cudaFuncSetAttribute(k_lindblad1<NS, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_lindblad1<NS, SWEEP><<<grid, kThreads1, smem, c->stream>>>(P);
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
@@ -401,10 +408,12 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
         if (phases_red) { if ((rc = upload(c, c->in_ph[0], phases_red, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_red = (const double*)c->in_ph[0].p; }
         if (phases_blue) { if ((rc = upload(c, c->in_ph[1], phases_blue, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_blue = (const double*)c->in_ph[1].p; }
     }
-    // grid: persistent warps, 2 CTAs of 128 threads per SM
+    // grid: persistent warps, 3 (NS=9) / 2 / 1 CTAs of 128 threads per SM
     const int wpb = kThreads1 / 32;
+    const int ns_sel = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
+    const int bps = ns_sel == 9 ? 3 : (ns_sel == 15 ? 2 : 1);
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
-    int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, 2LL * c->sm_count));
+    int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
     if (any_noise) {
         if ((rc = c->scratch.ensure(sizeof(double) * (size_t)grid * wpb * 2 * n_nodes_max * 32))) return rc;
         P.scratch = (double*)c->scratch.p;
