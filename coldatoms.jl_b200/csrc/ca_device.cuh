@@ -316,63 +316,78 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
     }
 }
 
-// Both Gaussian beams in ONE straight-line block (no branches, no library calls): the two exp / sincos dependency
-// chains are independent, so the scheduler interleaves them (ILP 2) -- with branches between them (kind dispatch,
-// range checks) each chain ran alone and the FP64 pipe idled on its latency.  Phases are assumed |φ| < 1e8.
-CA_HD void gauss_pair(const DevBeam& br, const DevBeam& bb, double x, double y, double z, double phr, double phb, double* o) {
-    const double r2 = x * x + y * y;
-    const double rp = sqrt_d(fmax(r2, 1e-300));
-    double re[2], im[2];
+// Gaussian beams of NB evaluation points in ONE straight-line block (no branches, no library calls): the 2*NB
+// exp / sincos dependency chains are independent, so the scheduler interleaves them and the FP64 pipe stays fed
+// (with branches between them -- kind dispatch, range checks -- each chain ran alone and the pipe idled on latency).
+// o[n] = {Re Ωr/2, Im Ωr/2, Re Ωb/2, Im Ωb/2}.  Phases are assumed |φ| < 1e8.
+template <int NB>
+CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, const double* y, const double* z, const double* phr,
+                       const double* phb, double (*o)[4]) {
+    double rp[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) rp[n] = sqrt_d(fmax(x[n] * x[n] + y[n] * y[n], 1e-300));
+    // (rolling this beam loop to shrink the code was measured slower: 228 vs 209 ms; the 2*NB chains stay unrolled)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        const DevBeam& b = q == 0 ? br : bb;
-        const double phi = q == 0 ? phr : phb;
-        const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
-        const double s = zr * b.inv_z0;
-        const double iq = rcp_d(fma(s, s, 1.0));
-        const double g = xr * xr * b.inv_w0sq * iq;
-        // exp(-g), g >= 0 (clamped instead of branching)
-        const double xx = fmax(-g, -700.0);
-        const double t = fma(xx, MC.log2e, MC.magic);
-        const double n = t - MC.magic;
-        double r = fma(-n, MC.ln2_hi, xx);
-        r = fma(-n, MC.ln2_lo, r);
-        const double q2 = r * r, q4 = q2 * q2, q8 = q4 * q4;
-        const double p01 = fma(MC.ex[1], r, MC.ex[0]), p23 = fma(MC.ex[3], r, MC.ex[2]), p45 = fma(MC.ex[5], r, MC.ex[4]),
-                     p67 = fma(MC.ex[7], r, MC.ex[6]), p89 = fma(MC.ex[9], r, MC.ex[8]), pab = fma(MC.ex[11], r, MC.ex[10]),
-                     pcd = fma(MC.ex[13], r, MC.ex[12]);
-        const double e0 = fma(fma(pcd, q4, fma(pab, q2, p89)), q8, fma(fma(p67, q2, p45), q4, fma(p23, q2, p01)));
+        const DevBeam* bp = q == 0 ? &br : &bb;
+        const double bcs = bp->cs, bsn = bp->sn, biz0 = bp->inv_z0, biw = bp->inv_w0sq, bhO = bp->hO;
+        double re[NB], im[NB];
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const double phi = q == 0 ? phr[n] : phb[n];
+            const double xr = rp[n] * bcs - z[n] * bsn, zr = rp[n] * bsn + z[n] * bcs;
+            const double s = zr * biz0;
+            const double iq = rcp_d(fma(s, s, 1.0));
+            const double g = xr * xr * biw * iq;
+            // exp(-g), g >= 0 (clamped instead of branching)
+            const double xx = fmax(-g, -700.0);
+            const double t = fma(xx, MC.log2e, MC.magic);
+            const double nn = t - MC.magic;
+            double r = fma(-nn, MC.ln2_hi, xx);
+            r = fma(-nn, MC.ln2_lo, r);
+            const double q2 = r * r, q4 = q2 * q2, q8 = q4 * q4;
+            const double p01 = fma(MC.ex[1], r, MC.ex[0]), p23 = fma(MC.ex[3], r, MC.ex[2]), p45 = fma(MC.ex[5], r, MC.ex[4]),
+                         p67 = fma(MC.ex[7], r, MC.ex[6]), p89 = fma(MC.ex[9], r, MC.ex[8]), pab = fma(MC.ex[11], r, MC.ex[10]),
+                         pcd = fma(MC.ex[13], r, MC.ex[12]);
+            const double e0 = fma(fma(pcd, q4, fma(pab, q2, p89)), q8, fma(fma(p67, q2, p45), q4, fma(p23, q2, p01)));
 #if defined(__CUDA_ARCH__)
-        const double e = b.hO * iq * e0 * __hiloint2double((__double2loint(t) + 1023) << 20, 0);
+            const double e = bhO * iq * e0 * __hiloint2double((__double2loint(t) + 1023) << 20, 0);
 #else
-        const double e = b.hO * iq * ldexp(e0, (int)n);
+            const double e = bhO * iq * ldexp(e0, (int)nn);
 #endif
-        // sincos(phi - s g)
-        const double a = fma(-s, g, phi);
-        const double t2 = fma(a, MC.two_over_pi, MC.magic);
-        const double m2 = t2 - MC.magic;
-        double w = fma(-m2, MC.pio2_hi, a);
-        w = fma(-m2, MC.pio2_mid, w);
-        w = fma(-m2, MC.pio2_lo, w);
-        const double zz = w * w;
-        double ps = fma(MC.sn[5], zz, MC.sn[4]), pc = fma(MC.cs[5], zz, MC.cs[4]);
-        ps = fma(ps, zz, MC.sn[3]); pc = fma(pc, zz, MC.cs[3]);
-        ps = fma(ps, zz, MC.sn[2]); pc = fma(pc, zz, MC.cs[2]);
-        ps = fma(ps, zz, MC.sn[1]); pc = fma(pc, zz, MC.cs[1]);
-        ps = fma(ps, zz, MC.sn[0]); pc = fma(pc, zz, MC.cs[0]);
-        const double sv = fma(ps * zz, w, w);
-        const double cv = fma(pc * zz, zz, fma(-0.5, zz, 1.0));
+            // sincos(phi - s g)
+            const double a = fma(-s, g, phi);
+            const double t2 = fma(a, MC.two_over_pi, MC.magic);
+            const double m2 = t2 - MC.magic;
+            double w = fma(-m2, MC.pio2_hi, a);
+            w = fma(-m2, MC.pio2_mid, w);
+            w = fma(-m2, MC.pio2_lo, w);
+            const double zz = w * w;
+            double ps = fma(MC.sn[5], zz, MC.sn[4]), pc = fma(MC.cs[5], zz, MC.cs[4]);
+            ps = fma(ps, zz, MC.sn[3]); pc = fma(pc, zz, MC.cs[3]);
+            ps = fma(ps, zz, MC.sn[2]); pc = fma(pc, zz, MC.cs[2]);
+            ps = fma(ps, zz, MC.sn[1]); pc = fma(pc, zz, MC.cs[1]);
+            ps = fma(ps, zz, MC.sn[0]); pc = fma(pc, zz, MC.cs[0]);
+            const double sv = fma(ps * zz, w, w);
+            const double cv = fma(pc * zz, zz, fma(-0.5, zz, 1.0));
 #if defined(__CUDA_ARCH__)
-        const int qd = __double2loint(t2);
+            const int qd = __double2loint(t2);
 #else
-        const int qd = (int)(long long)m2;
+            const int qd = (int)(long long)m2;
 #endif
-        const double ss = (qd & 1) ? cv : sv, cc = (qd & 1) ? sv : cv;
-        const double sn = (qd & 2) ? -ss : ss, cs = ((qd + 1) & 2) ? -cc : cc;
-        re[q] = e * (cs - s * sn);
-        im[q] = e * (sn + s * cs);
+            const double ss = (qd & 1) ? cv : sv, cc = (qd & 1) ? sv : cv;
+            const double sn = (qd & 2) ? -ss : ss, cs = ((qd + 1) & 2) ? -cc : cc;
+            re[n] = e * (cs - s * sn);
+            im[n] = e * (sn + s * cs);
+        }
+        if (q == 0) {
+#pragma unroll
+            for (int n = 0; n < NB; ++n) { o[n][0] = re[n]; o[n][1] = im[n]; }
+        } else {
+#pragma unroll
+            for (int n = 0; n < NB; ++n) { o[n][2] = re[n]; o[n][3] = im[n]; }
+        }
     }
-    o[0] = re[0]; o[1] = im[0]; o[2] = re[1]; o[3] = im[1];
 }
 
 // IEEE operations without FMA contraction: the sampler's rejection test and the recapture indicator are
@@ -427,11 +442,13 @@ CA_HD int sample_atom_literal(const SamplerConsts& sc, uint64_t seed, uint64_t i
 // out[j*stride] = Σ_k a_k cos(2π f_k j dtn + φ_k), j = 0..n_nodes-1, φ_k ~ U[0,2π) from Philox (two per call) or
 // host-supplied.  Nodes are produced CH at a time with the Reinsch-stabilised cosine recurrence
 // (c += d; d += σ c; σ = -4 sin²(δ/2)): 3 flop per (node, frequency) plus one sincos per (chunk, frequency).
+// Per-frequency constants of the node recurrence, computed once per call on the host (NoiseK[nf]).
+struct NoiseK { double om, amp, sh, ch, sig; };  // ω = 2π f, a, sin(ω dtn/2), cos(ω dtn/2), -4 sin²(ω dtn/2)
+
 template <int CH>
-CA_HD void gen_noise_trace(const double* __restrict__ f, const double* __restrict__ amp, int nf, int n_nodes, double dtn,
-                           const double* __restrict__ phases, uint64_t seed, uint64_t gi, uint32_t stream, double* __restrict__ out,
-                           int stride) {
-    constexpr int KB = 4;  // frequencies advanced together: 4 independent c/d chains hide the FP64 latency
+CA_HD void gen_noise_trace(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, const double* __restrict__ phases, uint64_t seed,
+                           uint64_t gi, uint32_t stream, double* __restrict__ out, int stride) {
+    constexpr int KB = 8;  // frequencies advanced together: 8 independent c/d chains hide the FP64 latency
     for (int c0 = 0; c0 < n_nodes; c0 += CH) {
         double acc[CH];
 #pragma unroll
@@ -442,34 +459,42 @@ CA_HD void gen_noise_trace(const double* __restrict__ f, const double* __restric
 #pragma unroll
             for (int q = 0; q < KB; q += 2) {
                 // phases of frequencies k0+q, k0+q+1 come from one Philox call (k0 and KB are even)
-                double ph0, ph1;
-                if (phases) { ph0 = k0 + q < nf ? phases[k0 + q] : 0.0; ph1 = k0 + q + 1 < nf ? phases[k0 + q + 1] : 0.0; }
-                else { U4 w = philox(seed, gi, (uint32_t)((k0 + q) >> 1), stream); ph0 = kTwoPi * u53(w.x, w.y); ph1 = kTwoPi * u53(w.z, w.w); }
+                double ph[2];
+                if (phases) { ph[0] = k0 + q < nf ? phases[k0 + q] : 0.0; ph[1] = k0 + q + 1 < nf ? phases[k0 + q + 1] : 0.0; }
+                else { U4 w = philox(seed, gi, (uint32_t)((k0 + q) >> 1), stream); ph[0] = kTwoPi * u53(w.x, w.y); ph[1] = kTwoPi * u53(w.z, w.w); }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int k = k0 + q + e;
-                    const bool live = k < nf;
-                    const double om = kTwoPi * (live ? f[k] : 0.0);
-                    const double a = live ? amp[k] : 0.0;
-                    double s0, c0v, sh, ch;
-                    sincos_fast(om * t0 + (e ? ph1 : ph0), &s0, &c0v);
-                    sincos_fast(0.5 * om * dtn, &sh, &ch);
-                    sig[q + e] = -4.0 * sh * sh;
+                    const int k = k0 + q + e < nf ? k0 + q + e : nf - 1;
+                    const NoiseK kk = nk[k];
+                    const double a = k0 + q + e < nf ? kk.amp : 0.0;
+                    double s0, c0v;
+                    sincos_fast(fma(kk.om, t0, ph[e]), &s0, &c0v);
+                    sig[q + e] = kk.sig;
                     c[q + e] = a * c0v;
-                    d[q + e] = -2.0 * a * (s0 * ch + c0v * sh) * sh;  // c_1 - c_0 = -2 a sin(θ0 + δ/2) sin(δ/2)
+                    d[q + e] = -2.0 * a * (s0 * kk.ch + c0v * kk.sh) * kk.sh;  // c_1 - c_0 = -2 a sin(θ0 + δ/2) sin(δ/2)
                 }
             }
-            acc[0] += (c[0] + c[1]) + (c[2] + c[3]);
+            acc[0] += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
 #pragma unroll
             for (int j = 1; j < CH; ++j) {
 #pragma unroll
                 for (int q = 0; q < KB; ++q) { c[q] += d[q]; d[q] = fma(sig[q], c[q], d[q]); }
-                acc[j] += (c[0] + c[1]) + (c[2] + c[3]);
+                acc[j] += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
             }
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j)
             if (c0 + j < n_nodes) out[(size_t)(c0 + j) * stride] = acc[j];
+    }
+}
+
+// host helper: fills NoiseK[nf]
+inline void fill_noise_k(const double* f, const double* amp, int nf, double dtn, NoiseK* out) {
+    for (int k = 0; k < nf; ++k) {
+        const double om = kTwoPi * f[k];
+        out[k].om = om; out[k].amp = amp[k];
+        out[k].sh = sin(0.5 * om * dtn); out[k].ch = cos(0.5 * om * dtn);
+        out[k].sig = -4.0 * out[k].sh * out[k].sh;
     }
 }
 
@@ -557,7 +582,8 @@ struct Lane1 {
     // noise cache
     const double* tab;                    // table base for this lane: tab[(trace*n_nodes + node)*stride]
     int stride, jc;
-    double pr0, prs, pb0, pbs, tj;
+    double nr0, nr1, nr2, nb0, nb1, nb2;  // node values j, j+1 and the PREFETCHED j+2 of the red / blue trace
+    double tj, tnx;                       // time of node jc and of node jc+1 (+inf in the last interval)
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
@@ -589,30 +615,64 @@ struct Lane1 {
             if (m.doppler_z_legacy) { double Vzt = vz * cz - z0 * m.wz * sz; Dd = m.aDz * Vzt; dd = m.bDz * Vzt; }
             c.dp = m.Delta0 - m.dsign * Dd; c.dr = m.delta0 - m.dsign * dd;
         }
-        double pr = 0.0, pb = 0.0;
-        if (tab) {
-            int j = (int)(tt * m.inv_dtn);
-            j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
-            if (j != jc) {
-                jc = j;
-                tj = j * m.dtn;
-                const double* q0 = tab + (size_t)j * stride;
-                double a0 = q0[0], a1 = q0[stride];
-                const double* q1 = q0 + (size_t)m.n_nodes * stride;
-                double b0 = q1[0], b1 = q1[stride];
-                pr0 = a0; prs = (a1 - a0) * m.inv_dtn; pb0 = b0; pbs = (b1 - b0) * m.inv_dtn;
-            }
-            double w = tt - tj;
-            pr = pr0 + w * prs; pb = pb0 + w * pbs;
-        }
-        if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
+        double pr, pb;
+        noise_at(m, tt, pr, pb);
         if (m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS) {
-            double o[4];
-            gauss_pair(m.red, m.blue, X, Y, Z, pr, pb, o);
-            c.Ar = o[0]; c.Ai = o[1]; c.Br = o[2]; c.Bi = o[3];
+            double o[1][4];
+            gauss_batch<1>(m.red, m.blue, &X, &Y, &Z, &pr, &pb, o);
+            c.Ar = o[0][0]; c.Ai = o[0][1]; c.Br = o[0][2]; c.Bi = o[0][3];
         } else {
             beam_half_omega(m.red, X, Y, Z, pr, &c.Ar, &c.Ai);
             beam_half_omega(m.blue, X, Y, Z, pb, &c.Br, &c.Bi);
+        }
+    }
+
+    // phase-noise values of both traces at time tt: Gridded(Linear) on the node table (rydberg_model.jl:166-167).
+    // The lane keeps nodes j, j+1 and a PREFETCHED j+2: crossing into the next interval (every ~14 steps at the default
+    // config, at a different step for every lane) shifts registers and issues the load of j+3 whose latency is hidden
+    // until the following crossing; only a jump of more than one interval (or a rejected step) reloads synchronously.
+    CA_HD void noise_at(const DevModel& m, double tt, double& pr, double& pb) {
+        pr = 0.0; pb = 0.0;
+        if (tab) {
+            // fast path: still inside [tj, tnx) -- two FP64 compares, no FP64<->int conversions (those issue at 1/8 rate)
+            if (!(tt < tnx) || tt < tj) {
+                int j = (int)(tt * m.inv_dtn);
+                j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+                if (j != jc) {
+                    const double* q0 = tab + (size_t)j * stride;
+                    const double* q1 = q0 + (size_t)m.n_nodes * stride;
+                    if (j == jc + 1) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
+                    else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
+                    const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
+                    nr2 = q0[o2]; nb2 = q1[o2];
+                    jc = j;
+                }
+                tj = j * m.dtn;
+                tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
+            }
+            const double w = (tt - tj) * m.inv_dtn;
+            pr = fma(w, nr1 - nr0, nr0); pb = fma(w, nb1 - nb0, nb0);
+        }
+        if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
+    }
+
+    // Coefficients of the five distinct stage times of one step (c2..c5 and t+h; stage 7 and the next stage 1 share the
+    // last).  Free motion + Gaussian beams: one straight-line batch of 10 beam evaluations; otherwise one by one.
+    CA_HD void coefficients5(const DevModel& m, double tt0, double hh, double tn, Coef* cs) {
+        if (m.free_motion && m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS) {
+            double X[5], Y[5], Z[5], pr[5], pb[5], o[5][4];
+#pragma unroll
+            for (int n = 0; n < 5; ++n) {
+                const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
+                X[n] = fma(vx, tt, x0); Y[n] = fma(vy, tt, y0); Z[n] = fma(vz, tt, z0);
+                noise_at(m, tt, pr[n], pb[n]);
+            }
+            gauss_batch<5>(m.red, m.blue, X, Y, Z, pr, pb, o);
+#pragma unroll
+            for (int n = 0; n < 5; ++n) { cs[n].Ar = o[n][0]; cs[n].Ai = o[n][1]; cs[n].Br = o[n][2]; cs[n].Bi = o[n][3]; cs[n].dp = dpc; cs[n].dr = drc; }
+        } else {
+#pragma unroll
+            for (int n = 0; n < 5; ++n) coefficients(m, n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0), cs[n]);
         }
     }
 
@@ -639,7 +699,7 @@ struct Lane1 {
             if (m.doppler_z_legacy) { Dd = m.aDz * vz; dd = m.bDz * vz; }
             dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
         }
-        tab = table; stride = tstride; jc = -1; pr0 = prs = pb0 = pbs = tj = 0.0;
+        tab = table; stride = tstride; jc = -5; nr0 = nr1 = nr2 = nb0 = nb1 = nb2 = 0.0; tj = 1e300; tnx = -1e300;
         // initial state
         y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
         y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
@@ -734,28 +794,25 @@ struct Lane1 {
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
         const double tn = clipped ? tstop : t + hh;
         double us[NS], ko[NS];
-        Coef cf;
+        Coef cfs[5];
+        coefficients5(m, t, hh, tn, cfs);
         // population quadratures: ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr, accumulated with the b/e/d weights
         double SB0 = MC.rb[1] * g1[0], SB1 = MC.rb[1] * g1[1], SE0 = MC.re[1] * g1[0], SE1 = MC.re[1] * g1[1], SD0 = MC.rd[1] * g1[0],
                SD1 = MC.rd[1] * g1[1];
-#pragma unroll 1
-        for (int s = 2; s <= 6; ++s) {
+#pragma unroll
+        for (int s = 2; s <= 6; ++s) {   // fully unrolled: tableau weights become constant-bank operands, slots immediates
 #pragma unroll
             for (int i = 0; i < NS; ++i) us[i] = 0.0;
-#pragma unroll 1
+#pragma unroll
             for (int j = 1; j < s; ++j) {
                 const double w = MC.ra[s][j];
                 const double* kp = kptr(j);
-                double kv[NS];  // all loads first, then the FMAs (otherwise each FMA waits for its own LDS)
 #pragma unroll
-                for (int i = 0; i < NS; ++i) kv[i] = kp[i * kstride];
-#pragma unroll
-                for (int i = 0; i < NS; ++i) us[i] = fma(w, kv[i], us[i]);
+                for (int i = 0; i < NS; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
             }
 #pragma unroll
             for (int i = 0; i < NS; ++i) us[i] = fma(hh, us[i], y[i]);
-            coefficients(m, s == 6 ? tn : fma(MC.rc[s], hh, t), cf);
-            lindblad_rhs<NS>(cf, g, us, ko);
+            lindblad_rhs<NS>(cfs[s - 2], g, us, ko);
             {
                 const double gg0 = g.G0 * us[2], gg1 = g.Gl * us[2] + g.Gr * us[1];
                 const double wb = MC.rb[s], we = MC.re[s], wd = MC.rd[s];
@@ -766,11 +823,12 @@ struct Lane1 {
 #pragma unroll
             for (int i = 0; i < NS; ++i) ks[i * kstride] = ko[i];
         }
+        const Coef& cf = cfs[4];
         // y_new and the error combination share one pass over k1,k3..k6 (ko still holds k6)
         double er[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) { un[i] = MC.rb[6] * ko[i]; er[i] = MC.re[6] * ko[i]; }
-#pragma unroll 1
+#pragma unroll
         for (int j = 1; j <= 5; ++j) {
             if (j == 2) continue;
             const double wb = MC.rb[j], we = MC.re[j];

@@ -45,11 +45,8 @@ struct R1Params {
     const double* samples;     // NULL or [n_points*n_per_point][6]
     const double* phases_red;  // NULL or [.][nf]
     const double* phases_blue;
-    const double* f;           // [nf]
-    const double* amp_red;
-    const double* amp_blue;
-    const double* nz_ch;       // cos(π f dtn) per frequency (single-point) -- unused for sweeps
-    const double* nz_sh;
+    const NoiseK* nk_red;      // [n_points][nf] per-frequency recurrence constants (dtn depends on the point's t_end)
+    const NoiseK* nk_blue;
     double* scratch;           // per-warp phase-noise tables: [warps][2][n_nodes][32]
     double* accum;             // [n_points][nt][kNV]
     unsigned long long* counters;  // n_rhs, n_accept, n_reject, n_attempts, status(max |err|)
@@ -60,7 +57,7 @@ struct R1Params {
 };
 
 template <int NS>
-constexpr int blocks_per_sm() { return NS == 9 ? 3 : (NS == 15 ? 2 : 1); }
+constexpr int blocks_per_sm() { return NS == 9 ? 2 : (NS == 15 ? 2 : 1); }
 
 template <int NS, bool SWEEP>
 __global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
@@ -71,6 +68,7 @@ __global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(co
     const long long wg = (long long)blockIdx.x * (kThreads1 / 32) + warp;
     const long long W = (long long)gridDim.x * (kThreads1 / 32);
     long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0;
+    long long cyc_noise = 0, cyc_all = -clock64();
     int worst = 0;
     for (long long g = wg; g < P.n_groups; g += W) {
         const int pt = (int)(g / P.groups_per_point);
@@ -110,14 +108,16 @@ __global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(co
         // ---- K2: phase-noise tables for this warp's 32 trajectories
         double* tab = nullptr;
         if (m.laser_noise && P.nf > 0) {
+            cyc_noise -= clock64();
             tab = P.scratch + (size_t)wg * 2 * P.n_nodes_max * 32 + lane;
             if (valid) {
-                gen_noise_trace<kNoiseChunk>(P.f, P.amp_red, P.nf, m.n_nodes, m.dtn, P.phases_red ? P.phases_red + li * P.nf : nullptr,
-                                             P.seed, gi, 2u, tab, 32);
-                gen_noise_trace<kNoiseChunk>(P.f, P.amp_blue, P.nf, m.n_nodes, m.dtn, P.phases_blue ? P.phases_blue + li * P.nf : nullptr,
-                                             P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32);
+                gen_noise_trace<kNoiseChunk>(P.nk_red + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn,
+                                             P.phases_red ? P.phases_red + li * P.nf : nullptr, P.seed, gi, 2u, tab, 32);
+                gen_noise_trace<kNoiseChunk>(P.nk_blue + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn,
+                                             P.phases_blue ? P.phases_blue + li * P.nf : nullptr, P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32);
             }
             __syncwarp();
+            cyc_noise += clock64();
         }
         // ---- K3: integrate
         Lane1<NS> L;
@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(co
         atomicAdd(P.counters + 2, (unsigned long long)tot_rej);
         atomicAdd(P.counters + 3, (unsigned long long)tot_att);
         if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
+        atomicAdd(P.counters + 5, (unsigned long long)cyc_noise);               // warp-cycles in phase-noise generation
+        atomicAdd(P.counters + 6, (unsigned long long)(cyc_all + clock64()));   // warp-cycles in the whole kernel
     }
 }
 
@@ -232,12 +234,12 @@ __global__ void k_sample_atoms(SamplerConsts sc, long long n, long long traj_off
 }
 
 // ϕ tables: one thread per trajectory, output phi[i][node] (lasernoise_sampler.jl:31-37 on a uniform grid)
-__global__ void __launch_bounds__(128) k_phase_noise(const double* __restrict__ f, const double* __restrict__ amp, int nf, int n_nodes, double dtn,
+__global__ void __launch_bounds__(128) k_phase_noise(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn,
                                                      const double* __restrict__ phases, long long n, long long traj_offset,
                                                      unsigned long long seed, unsigned stream, double* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    gen_noise_trace<kNoiseChunk>(f, amp, nf, n_nodes, dtn, phases ? phases + i * nf : nullptr, seed, (uint64_t)(traj_offset + i), stream,
+    gen_noise_trace<kNoiseChunk>(nk, nf, n_nodes, dtn, phases ? phases + i * nf : nullptr, seed, (uint64_t)(traj_offset + i), stream,
                                  out + (size_t)i * n_nodes, 1);
 }
 
@@ -395,23 +397,24 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     const long long n_all = n_per_point * n_points;
     if (samples) { if ((rc = upload(c, c->in_samples, samples, sizeof(double) * 6 * (size_t)n_all))) return rc; P.samples = (const double*)c->in_samples.p; }
     if (any_noise) {
-        std::vector<double> fa((size_t)3 * nf);
-        std::memcpy(fa.data(), f, sizeof(double) * nf);
-        std::memcpy(fa.data() + nf, amp_red, sizeof(double) * nf);
-        std::memcpy(fa.data() + 2 * (size_t)nf, amp_blue, sizeof(double) * nf);
-        if ((rc = ensure_pinned(c, sizeof(double) * 3 * (size_t)nf))) return rc;
-        std::memcpy(c->pinned, fa.data(), sizeof(double) * 3 * (size_t)nf);
-        if ((rc = c->in_f.ensure(sizeof(double) * 3 * (size_t)nf))) return rc;
-        CA_CUDA(cudaMemcpyAsync(c->in_f.p, c->pinned, sizeof(double) * 3 * (size_t)nf, cudaMemcpyHostToDevice, c->stream));
+        const size_t nkb = sizeof(NoiseK) * 2 * (size_t)nf * n_points;
+        if ((rc = ensure_pinned(c, nkb))) return rc;
+        NoiseK* hk = (NoiseK*)c->pinned;
+        for (int p = 0; p < n_points; ++p) {
+            fill_noise_k(f, amp_red, nf, dm[p].dtn, hk + (size_t)p * nf);
+            fill_noise_k(f, amp_blue, nf, dm[p].dtn, hk + (size_t)(n_points + p) * nf);
+        }
+        if ((rc = c->in_f.ensure(nkb))) return rc;
+        CA_CUDA(cudaMemcpyAsync(c->in_f.p, c->pinned, nkb, cudaMemcpyHostToDevice, c->stream));
         CA_CUDA(cudaStreamSynchronize(c->stream));  // pinned staging buffer is reused below
-        P.f = (const double*)c->in_f.p; P.amp_red = P.f + nf; P.amp_blue = P.f + 2 * (size_t)nf;
+        P.nk_red = (const NoiseK*)c->in_f.p; P.nk_blue = P.nk_red + (size_t)n_points * nf;
         if (phases_red) { if ((rc = upload(c, c->in_ph[0], phases_red, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_red = (const double*)c->in_ph[0].p; }
         if (phases_blue) { if ((rc = upload(c, c->in_ph[1], phases_blue, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_blue = (const double*)c->in_ph[1].p; }
     }
     // grid: persistent warps, 3 (NS=9) / 2 / 1 CTAs of 128 threads per SM
     const int wpb = kThreads1 / 32;
     const int ns_sel = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
-    const int bps = ns_sel == 9 ? 3 : (ns_sel == 15 ? 2 : 1);
+    const int bps = ns_sel == 9 ? 2 : (ns_sel == 15 ? 2 : 1);
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
     int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
     if (any_noise) {
@@ -490,6 +493,7 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
         stats->n_sample_attempts = (int64_t)hc[3]; stats->n_launches = launches; stats->status = status;
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); stats->kernel_ms = ms;
+        stats->noise_ms = hc[6] ? ms * (double)hc[5] / (double)hc[6] : 0.0;  // share of warp-cycles spent generating noise tables
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); stats->total_ms = ms;
     }
     if (status == CA_ERR_MAXITERS) { set_error("a trajectory hit maxiters"); return status; }
@@ -698,16 +702,15 @@ int ca_phase_noise(ca_ctx* c, const double* tnodes, int32_t n_nodes, const doubl
         if (std::fabs(tnodes[j] - j * dtn) > 1e-9 * std::fabs(tnodes[n_nodes - 1])) { set_error("tnodes must be uniformly spaced"); return CA_ERR_UNSUPPORTED; }
     if (n == 0) return CA_OK;
     int rc;
-    std::vector<double> fa((size_t)2 * nf);
-    std::memcpy(fa.data(), f, sizeof(double) * nf);
-    std::memcpy(fa.data() + nf, amp, sizeof(double) * nf);
-    if ((rc = upload(c, c->in_f, fa.data(), sizeof(double) * 2 * (size_t)nf))) return rc;
+    std::vector<NoiseK> hk((size_t)nf);
+    fill_noise_k(f, amp, nf, dtn, hk.data());
+    if ((rc = upload(c, c->in_f, hk.data(), sizeof(NoiseK) * (size_t)nf))) return rc;
     CA_CUDA(cudaStreamSynchronize(c->stream));
     const double* d_ph = nullptr;
     if (phases) { if ((rc = upload(c, c->in_ph[0], phases, sizeof(double) * (size_t)nf * n))) return rc; d_ph = (const double*)c->in_ph[0].p; }
     if ((rc = c->out.ensure(sizeof(double) * (size_t)n * n_nodes))) return rc;
-    k_phase_noise<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const double*)c->in_f.p, (const double*)c->in_f.p + nf, nf, n_nodes, dtn, d_ph, n,
-                                                                     traj_offset, seed, (unsigned)stream_id, (double*)c->out.p);
+    k_phase_noise<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const NoiseK*)c->in_f.p, nf, n_nodes, dtn, d_ph, n, traj_offset, seed,
+                                                                     (unsigned)stream_id, (double*)c->out.p);
     CA_CUDA(cudaGetLastError());
     CA_CUDA(cudaMemcpyAsync(phi_out, c->out.p, sizeof(double) * (size_t)n * n_nodes, cudaMemcpyDeviceToHost, c->stream));
     CA_CUDA(cudaStreamSynchronize(c->stream));

@@ -48,8 +48,11 @@ int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const d
     const double* tp = nullptr;
     if (m.laser_noise && nf > 0) {
         tab.resize((size_t)2 * m.n_nodes);
-        gen_noise_trace<64>(f, amp_red, nf, m.n_nodes, m.dtn, phases_red, seed, gi, 2u, tab.data(), 1);
-        gen_noise_trace<64>(f, amp_blue, nf, m.n_nodes, m.dtn, phases_blue, seed, gi, 3u, tab.data() + m.n_nodes, 1);
+        std::vector<NoiseK> kr(nf), kb(nf);
+        fill_noise_k(f, amp_red, nf, m.dtn, kr.data());
+        fill_noise_k(f, amp_blue, nf, m.dtn, kb.data());
+        gen_noise_trace<64>(kr.data(), nf, m.n_nodes, m.dtn, phases_red, seed, gi, 2u, tab.data(), 1);
+        gen_noise_trace<64>(kb.data(), nf, m.n_nodes, m.dtn, phases_blue, seed, gi, 3u, tab.data() + m.n_nodes, 1);
         tp = tab.data();
     }
     double smp[6] = {0, 0, 0, 0, 0, 0};
@@ -68,7 +71,9 @@ int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const d
 
 int he_noise_trace(const double* f, const double* amp, int nf, int n_nodes, double dtn, const double* phases, unsigned long long seed,
                    unsigned long long gi, unsigned stream, double* out) {
-    gen_noise_trace<64>(f, amp, nf, n_nodes, dtn, phases, seed, gi, stream, out, 1);
+    std::vector<NoiseK> kk(nf);
+    fill_noise_k(f, amp, nf, dtn, kk.data());
+    gen_noise_trace<64>(kk.data(), nf, n_nodes, dtn, phases, seed, gi, stream, out, 1);
     return 0;
 }
 
