@@ -390,6 +390,51 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
     }
 }
 
+// ---- anchor / increment evaluation of a Gaussian beam (hot path of the adaptive integrator) ----------------------
+// A DP5 step needs the coefficient Ω e^{iφ}/2 at five times inside [t, t+h].  Only the end point is evaluated with the
+// full exp + sincos (it is also the next step's start: FSAL).  Interior stage times use the EXACT geometry
+// (s, q, g) but obtain e^{-g} and cis(φ - s g) from the values at the step start ("anchor") through short Taylor
+// series of the tiny increments Δg, Δa (|Δg| < 1e-3 -> truncation < 1e-17, |Δa| < 1e-2 -> < 1e-20); a lane whose
+// increments exceed the guards (phase jump ξ, tight beams, huge steps) re-evaluates exactly.  Anchors are refreshed by
+// an exact evaluation every step, so nothing accumulates.
+struct BeamGeom { double s, iq, g; };
+CA_HD BeamGeom beam_geom(const DevBeam& b, double rp, double z) {
+    const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
+    BeamGeom o;
+    o.s = zr * b.inv_z0;
+    o.iq = rcp_d(fma(o.s, o.s, 1.0));
+    o.g = xr * xr * b.inv_w0sq * o.iq;
+    return o;
+}
+// exact: returns Ω e^{iφ}/2 and the anchor {e^{-g}, g, cos a, sin a, a} with a = φ - s g
+CA_HD void gauss_exact(const DevBeam& b, double rp, double z, double phi, double* re, double* im, double* anc) {
+    const BeamGeom q = beam_geom(b, rp, z);
+    const double eg = exp_d(fmax(-q.g, -700.0));
+    const double a = fma(-q.s, q.g, phi);
+    double sn, cs;
+    sincos_fast(a, &sn, &cs);
+    const double e = b.hO * q.iq * eg;
+    *re = e * (cs - q.s * sn);
+    *im = e * (sn + q.s * cs);
+    anc[0] = eg; anc[1] = q.g; anc[2] = cs; anc[3] = sn; anc[4] = a;
+}
+// incremental: same value to ~1e-16 from the anchor; returns false if the increments are outside the guards
+CA_HD bool gauss_incr(const DevBeam& b, double rp, double z, double phi, double a_eg, double a_g, double a_c, double a_s, double a_a,
+                      double* re, double* im) {
+    const BeamGeom q = beam_geom(b, rp, z);
+    const double dg = q.g - a_g;
+    const double da = fma(-q.s, q.g, phi) - a_a;
+    const double em = fma(dg, fma(dg, fma(dg, fma(dg, 1.0 / 24.0, -1.0 / 6.0), 0.5), -1.0), 1.0);       // e^{-dg}
+    const double c2 = da * da;
+    const double dc = fma(c2, fma(c2, fma(c2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);                     // cos da
+    const double ds = da * fma(c2, fma(c2, fma(c2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);        // sin da
+    const double cs = a_c * dc - a_s * ds, sn = a_s * dc + a_c * ds;
+    const double e = b.hO * q.iq * a_eg * em;
+    *re = e * (cs - q.s * sn);
+    *im = e * (sn + q.s * cs);
+    return fabs(dg) < 1e-3 && fabs(da) < 1e-2;
+}
+
 // IEEE operations without FMA contraction: the sampler's rejection test and the recapture indicator are
 // evaluated in the reference's operation order so that they round exactly like the oracle (-ffp-contract=off).
 #if defined(__CUDA_ARCH__)
@@ -586,7 +631,10 @@ struct Lane1 {
     double tj, tnx;                       // time of node jc and of node jc+1 (+inf in the last interval)
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
+    double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
+    double* ab;                           // beam anchors ab[((set*2 + beam)*5 + f)*kstride] (fast path only, may be null)
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
+    int pa;                               // anchor set valid at time t (the other set receives the values at t+h)
     double t, h, dt, lnq_old, tcommit;
     double y[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
@@ -627,52 +675,127 @@ struct Lane1 {
         }
     }
 
-    // phase-noise values of both traces at time tt: Gridded(Linear) on the node table (rydberg_model.jl:166-167).
-    // The lane keeps nodes j, j+1 and a PREFETCHED j+2: crossing into the next interval (every ~14 steps at the default
-    // config, at a different step for every lane) shifts registers and issues the load of j+3 whose latency is hidden
-    // until the following crossing; only a jump of more than one interval (or a rejected step) reloads synchronously.
-    CA_HD void noise_at(const DevModel& m, double tt, double& pr, double& pb) {
+    // ---- phase noise: Gridded(Linear) on the node table (rydberg_model.jl:166-167) --------------------------------
+    // The lane caches THREE consecutive nodes (j, j+1 and the prefetched j+2), i.e. two intervals: a step shorter than
+    // the node spacing never leaves the window, so the window is advanced at most once per step (not per stage) and
+    // the per-stage lookup is branch-free and free of FP64<->int conversions (those issue at 1/8 rate).
+    CA_HD void window_at(const DevModel& m, double tt) {   // make tj <= tt < tnx
+        int j = (int)(tt * m.inv_dtn);
+        j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+        if (j != jc) {
+            const double* q0 = tab + (size_t)j * stride;
+            const double* q1 = q0 + (size_t)m.n_nodes * stride;
+            if (j == jc + 1) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
+            else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
+            const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
+            nr2 = q0[o2]; nb2 = q1[o2];   // prefetch: first used at the next advance
+            jc = j;
+        }
+        tj = j * m.dtn;
+        tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
+    }
+    CA_HD void phases_win(const DevModel& m, double tt, double& pr, double& pb) const {  // needs tj <= tt < tj + 2 dtn
         pr = 0.0; pb = 0.0;
         if (tab) {
-            // fast path: still inside [tj, tnx) -- two FP64 compares, no FP64<->int conversions (those issue at 1/8 rate)
-            if (!(tt < tnx) || tt < tj) {
-                int j = (int)(tt * m.inv_dtn);
-                j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
-                if (j != jc) {
-                    const double* q0 = tab + (size_t)j * stride;
-                    const double* q1 = q0 + (size_t)m.n_nodes * stride;
-                    if (j == jc + 1) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
-                    else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
-                    const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
-                    nr2 = q0[o2]; nb2 = q1[o2];
-                    jc = j;
-                }
-                tj = j * m.dtn;
-                tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
-            }
             const double w = (tt - tj) * m.inv_dtn;
-            pr = fma(w, nr1 - nr0, nr0); pb = fma(w, nb1 - nb0, nb0);
+            const bool hi = !(tt < tnx);
+            const double w2 = hi ? w - 1.0 : w;
+            const double ra = hi ? nr1 : nr0, rb = hi ? nr2 : nr1, ba = hi ? nb1 : nb0, bb = hi ? nb2 : nb1;
+            pr = fma(w2, rb - ra, ra); pb = fma(w2, bb - ba, ba);
+        }
+        if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
+    }
+    CA_HD void noise_at(const DevModel& m, double tt, double& pr, double& pb) const {   // stateless generic lookup
+        pr = 0.0; pb = 0.0;
+        if (tab) {
+            int j = (int)(tt * m.inv_dtn);
+            j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+            const double* q0 = tab + (size_t)j * stride;
+            const double* q1 = q0 + (size_t)m.n_nodes * stride;
+            const double w = (tt - j * m.dtn) * m.inv_dtn;
+            const double a0 = q0[0], a1 = q0[stride], b0 = q1[0], b1 = q1[stride];
+            pr = fma(w, a1 - a0, a0); pb = fma(w, b1 - b0, b0);
         }
         if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
     }
 
+    CA_HD bool fast_model(const DevModel& m) const {
+        return NS == 9 && ab != nullptr && m.free_motion && m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS;
+    }
+    CA_HD double stage_time(int n, double tt0, double hh, double tn) const { return n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0); }
+
+    // exact anchors of both beams at time tt into anchor set `set`
+    CA_HD void set_anchors(const DevModel& m, double tt, int set) {
+        double pr, pb, re, im, anc[5];
+        noise_at(m, tt, pr, pb);
+        const double X = fma(vx, tt, x0), Y = fma(vy, tt, y0), Z = fma(vz, tt, z0);
+        const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            gauss_exact(q == 0 ? m.red : m.blue, rp, Z, q == 0 ? pr : pb, &re, &im, anc);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) ab[((set * 2 + q) * 5 + f) * kstride] = anc[f];
+        }
+    }
+
     // Coefficients of the five distinct stage times of one step (c2..c5 and t+h; stage 7 and the next stage 1 share the
-    // last).  Free motion + Gaussian beams: one straight-line batch of 10 beam evaluations; otherwise one by one.
-    CA_HD void coefficients5(const DevModel& m, double tt0, double hh, double tn, Coef* cs) {
-        if (m.free_motion && m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS) {
-            double X[5], Y[5], Z[5], pr[5], pb[5], o[5][4];
-#pragma unroll
-            for (int n = 0; n < 5; ++n) {
-                const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
-                X[n] = fma(vx, tt, x0); Y[n] = fma(vy, tt, y0); Z[n] = fma(vz, tt, z0);
-                noise_at(m, tt, pr[n], pb[n]);
+    // last) into the shared-memory buffer cb.
+    CA_HD void stage_coefficients(const DevModel& m, double tt0, double hh, double tn) {
+        bool done = false;
+        if (fast_model(m)) {
+            bool ok = true;
+            if (tab) {
+                if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
+                ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
             }
-            gauss_batch<5>(m.red, m.blue, X, Y, Z, pr, pb, o);
+            if (ok) {
+                // end point: exact; its anchors go to the other set (they become the anchors of the next step)
+                {
+                    double pr, pb, re, im, anc[5];
+                    phases_win(m, tn, pr, pb);
+                    const double X = fma(vx, tn, x0), Y = fma(vy, tn, y0), Z = fma(vz, tn, z0);
+                    const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
 #pragma unroll
-            for (int n = 0; n < 5; ++n) { cs[n].Ar = o[n][0]; cs[n].Ai = o[n][1]; cs[n].Br = o[n][2]; cs[n].Bi = o[n][3]; cs[n].dp = dpc; cs[n].dr = drc; }
-        } else {
+                    for (int q = 0; q < 2; ++q) {
+                        gauss_exact(q == 0 ? m.red : m.blue, rp, Z, q == 0 ? pr : pb, &re, &im, anc);
+                        cb[(4 * 6 + 2 * q) * kstride] = re; cb[(4 * 6 + 2 * q + 1) * kstride] = im;
 #pragma unroll
-            for (int n = 0; n < 5; ++n) coefficients(m, n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0), cs[n]);
+                        for (int f = 0; f < 5; ++f) ab[(((1 - pa) * 2 + q) * 5 + f) * kstride] = anc[f];
+                    }
+                }
+                // interior stage times: increments from the anchors at tt0
+                double an[2][5];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int f = 0; f < 5; ++f) an[q][f] = ab[((pa * 2 + q) * 5 + f) * kstride];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const double tt = fma(MC.rc[n + 2], hh, tt0);
+                    double pr, pb, re, im;
+                    phases_win(m, tt, pr, pb);
+                    const double X = fma(vx, tt, x0), Y = fma(vy, tt, y0), Z = fma(vz, tt, z0);
+                    const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        ok &= gauss_incr(q == 0 ? m.red : m.blue, rp, Z, q == 0 ? pr : pb, an[q][0], an[q][1], an[q][2], an[q][3], an[q][4], &re, &im);
+                        cb[(n * 6 + 2 * q) * kstride] = re; cb[(n * 6 + 2 * q + 1) * kstride] = im;
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
+                done = ok;
+            }
+        }
+        if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
+#pragma unroll 1
+            for (int n = 0; n < 5; ++n) {
+                Coef c;
+                coefficients(m, stage_time(n, tt0, hh, tn), c);
+                double* o = cb + (size_t)n * 6 * kstride;
+                o[0] = c.Ar; o[kstride] = c.Ai; o[2 * kstride] = c.Br; o[3 * kstride] = c.Bi; o[4 * kstride] = c.dp; o[5 * kstride] = c.dr;
+            }
+            if (fast_model(m)) set_anchors(m, tn, 1 - pa);
         }
     }
 
@@ -689,8 +812,8 @@ struct Lane1 {
     }
 
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
-                    double t0, double* kbase, int kstr) {
-        kb = kbase; kstride = kstr; p = 0;
+                    double t0, double* kbase, int kstr, double* cbase, double* abase) {
+        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; pa = 0;
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
         vzq = m.vz_from_vy ? vy : vz;
@@ -700,6 +823,7 @@ struct Lane1 {
             dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
         }
         tab = table; stride = tstride; jc = -5; nr0 = nr1 = nr2 = nb0 = nb1 = nb2 = 0.0; tj = 1e300; tnx = -1e300;
+        if (fast_model(m)) set_anchors(m, t0, 0);
         // initial state
         y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
         y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
@@ -786,7 +910,7 @@ struct Lane1 {
             P[0] = Pn[0]; P[1] = Pn[1]; g1[0] = g7[0]; g1[1] = g7[1];
             t = tcommit;
             h = 0.0;
-            p ^= 1;
+            p ^= 1; pa ^= 1;
         }
         if (++iters > oo.maxiters) { status = CA_ERR_MAXITERS; return; }
         double hh = fmin(dt, oo.dtmax);
@@ -794,8 +918,8 @@ struct Lane1 {
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
         const double tn = clipped ? tstop : t + hh;
         double us[NS], ko[NS];
-        Coef cfs[5];
-        coefficients5(m, t, hh, tn, cfs);
+        stage_coefficients(m, t, hh, tn);
+        Coef cf;
         // population quadratures: ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr, accumulated with the b/e/d weights
         double SB0 = MC.rb[1] * g1[0], SB1 = MC.rb[1] * g1[1], SE0 = MC.re[1] * g1[0], SE1 = MC.re[1] * g1[1], SD0 = MC.rd[1] * g1[0],
                SD1 = MC.rd[1] * g1[1];
@@ -812,7 +936,11 @@ struct Lane1 {
             }
 #pragma unroll
             for (int i = 0; i < NS; ++i) us[i] = fma(hh, us[i], y[i]);
-            lindblad_rhs<NS>(cfs[s - 2], g, us, ko);
+            {
+                const double* o = cb + (size_t)(s - 2) * 6 * kstride;
+                cf.Ar = o[0]; cf.Ai = o[kstride]; cf.Br = o[2 * kstride]; cf.Bi = o[3 * kstride]; cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride];
+            }
+            lindblad_rhs<NS>(cf, g, us, ko);
             {
                 const double gg0 = g.G0 * us[2], gg1 = g.Gl * us[2] + g.Gr * us[1];
                 const double wb = MC.rb[s], we = MC.re[s], wd = MC.rd[s];
@@ -823,7 +951,6 @@ struct Lane1 {
 #pragma unroll
             for (int i = 0; i < NS; ++i) ks[i * kstride] = ko[i];
         }
-        const Coef& cf = cfs[4];
         // y_new and the error combination share one pass over k1,k3..k6 (ko still holds k6)
         double er[NS];
 #pragma unroll

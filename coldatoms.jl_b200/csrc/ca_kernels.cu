@@ -35,7 +35,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ----------------------------------------------------------------------------------------------------
 // K1+K2+K3: fused one-atom ensemble kernel
 // ----------------------------------------------------------------------------------------------------
-constexpr int kThreads1 = 128;
+template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 15 ? 96 : 128; }
+template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS == 9 ? 20 : 0); }   // k slots + stage coefficients + anchors
 constexpr int kNoiseChunk = 64;
 
 struct R1Params {
@@ -57,16 +58,19 @@ struct R1Params {
 };
 
 template <int NS>
-constexpr int blocks_per_sm() { return NS == 9 ? 2 : (NS == 15 ? 2 : 1); }
+__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 2 : (NS == 15 ? 2 : 1); }
 
 template <int NS, bool SWEEP>
-__global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
+__global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
+    constexpr int T = threads_for<NS>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sk = reinterpret_cast<double*>(smem_raw);                                   // [6][NS][kThreads1]
-    DevModel* sm_models = reinterpret_cast<DevModel*>(sk + 6 * NS * kThreads1);         // [warps] (sweeps only)
+    double* sk = reinterpret_cast<double*>(smem_raw);                                   // [6][NS][T] stage derivatives
+    double* scb = sk + 6 * NS * T;                                                      // [5][6][T] stage coefficients
+    double* sab = scb + 30 * T;                                                         // [2][2][5][T] beam anchors (NS = 9)
+    DevModel* sm_models = reinterpret_cast<DevModel*>(sk + smem_doubles_per_thread<NS>() * T);  // [warps] (sweeps only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wg = (long long)blockIdx.x * (kThreads1 / 32) + warp;
-    const long long W = (long long)gridDim.x * (kThreads1 / 32);
+    const long long wg = (long long)blockIdx.x * (T / 32) + warp;
+    const long long W = (long long)gridDim.x * (T / 32);
     long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0;
     long long cyc_noise = 0, cyc_all = -clock64();
     int worst = 0;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kThreads1, blocks_per_sm<NS>()) k_lindblad1(co
         }
         // ---- K3: integrate
         Lane1<NS> L;
-        L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, kThreads1);
+        L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS == 9 ? sab + threadIdx.x : nullptr);
         const double tend = tsp[P.nt - 1];
         double* acc_pt = P.accum + (size_t)pt * P.nt * kNV;
         for (int j = 0; j < P.nt; ++j) {
@@ -336,9 +340,10 @@ void* ctx_buf(ca_ctx* c, int which, size_t bytes) {
 
 template <int NS, bool SWEEP>
 static int launch_lindblad1(ca_ctx* c, const R1Params& P, int grid) {
-    const size_t smem = sizeof(double) * 6 * NS * kThreads1 + (SWEEP ? sizeof(DevModel) * (kThreads1 / 32) : 0);
+    constexpr int T = threads_for<NS>();
+    const size_t smem = sizeof(double) * smem_doubles_per_thread<NS>() * T + (SWEEP ? sizeof(DevModel) * (T / 32) : 0);
     CA_CUDA(cudaFuncSetAttribute(k_lindblad1<NS, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_lindblad1<NS, SWEEP><<<grid, kThreads1, smem, c->stream>>>(P);
+    k_lindblad1<NS, SWEEP><<<grid, T, smem, c->stream>>>(P);
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
@@ -412,8 +417,8 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
         if (phases_blue) { if ((rc = upload(c, c->in_ph[1], phases_blue, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_blue = (const double*)c->in_ph[1].p; }
     }
     // grid: persistent warps, 3 (NS=9) / 2 / 1 CTAs of 128 threads per SM
-    const int wpb = kThreads1 / 32;
     const int ns_sel = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
+    const int wpb = (ns_sel == 15 ? 96 : 128) / 32;
     const int bps = ns_sel == 9 ? 2 : (ns_sel == 15 ? 2 : 1);
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
     int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
