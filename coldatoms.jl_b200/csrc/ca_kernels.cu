@@ -35,7 +35,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ----------------------------------------------------------------------------------------------------
 // K1+K2+K3: fused one-atom ensemble kernel
 // ----------------------------------------------------------------------------------------------------
-template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 15 ? 96 : 128; }
+template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? 96 : 128); }
 template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS == 9 ? 20 : 0); }   // k slots + stage coefficients + anchors
 constexpr int kNoiseChunk = 64;
 
@@ -58,7 +58,7 @@ struct R1Params {
 };
 
 template <int NS>
-__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 2 : (NS == 15 ? 2 : 1); }
+__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 1 : (NS == 15 ? 2 : 1); }
 
 template <int NS, bool SWEEP>
 __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
@@ -74,7 +74,14 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
     long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0;
     long long cyc_noise = 0, cyc_all = -clock64();
     int worst = 0;
-    for (long long g = wg; g < P.n_groups; g += W) {
+    // All warps of a CTA walk the group list in lock-step (one barrier per 32-trajectory group): measured, the warps
+    // otherwise drift apart over a long ensemble and the instruction cache (the step is ~36 KB of code) thrashes:
+    // 85.8 -> 96.8 ms per wave between 3 and 27 waves.
+    const long long n_iter = (P.n_groups + W - 1) / W;
+    for (long long it = 0; it < n_iter; ++it) {
+        const long long g = wg + it * W;
+        __syncthreads();
+        if (g >= P.n_groups) continue;
         const int pt = (int)(g / P.groups_per_point);
         const long long il = (g - (long long)pt * P.groups_per_point) * 32 + lane;
         const bool valid = il < P.n_per_point;
@@ -418,8 +425,8 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     }
     // grid: persistent warps, 3 (NS=9) / 2 / 1 CTAs of 128 threads per SM
     const int ns_sel = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
-    const int wpb = (ns_sel == 15 ? 96 : 128) / 32;
-    const int bps = ns_sel == 9 ? 2 : (ns_sel == 15 ? 2 : 1);
+    const int wpb = (ns_sel == 9 ? 256 : (ns_sel == 15 ? 96 : 128)) / 32;
+    const int bps = ns_sel == 9 ? 1 : (ns_sel == 15 ? 2 : 1);
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
     int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
     if (any_noise) {
