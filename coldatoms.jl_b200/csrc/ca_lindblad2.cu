@@ -35,6 +35,12 @@ constexpr int kWarps2 = 8;         // warps (trajectories) per CTA
 constexpr int kMaxFull = 320;      // stage vector entries per warp (289 used for |++>)
 constexpr int kNCoef = 24;         // per-stage coefficient table: 16 dynamic (∓i c_k) + 4 rates + zero
 constexpr int kStages = 5;         // distinct stage times c2,c3,c4,c5,c6(=c7)
+// Gather terms per slot position after dealing the elements by decreasing term count.  These are the order statistics
+// of the full 16x16+4x4+4x4+1 support with all decay channels on; any sub-support / fewer channels has smaller ones.
+// The gather loops are unrolled to these counts and the per-lane descriptors live in registers.
+__host__ __device__ constexpr int slot_terms(int s) { return s == 0 ? 8 : (s == 1 ? 5 : (s == 2 ? 5 : (s == 3 ? 4 : 3))); }
+__host__ __device__ constexpr int slot_offset(int s) { return s == 0 ? 0 : (s == 1 ? 8 : (s == 2 ? 13 : (s == 3 ? 18 : 22))); }
+constexpr int kTermRegs = 25;
 
 // Static structure shared by all trajectories (device copy lives in global memory, staged into smem).
 struct Struct2 {
@@ -221,7 +227,7 @@ __device__ void eval_coefficients(const DevModel& m, Smem2& sm, int w, int lane,
                 vel[a][0] = s[3]; vel[a][1] = m.vz_from_vy ? s[4] : s[5];
             } else {  // R, V: atom_sampler.jl:125-143 (oscillation about the origin although centres are shifted, App. B6)
                 double sr, cr, sz, cz;
-                sincos(m.wr * tt, &sr, &cr); sincos(m.wz * tt, &sz, &cz);
+                sincos_fast(m.wr * tt, &sr, &cr); sincos_fast(m.wz * tt, &sz, &cz);
                 pos[a][0] = s[0] * cr + s[3] / m.wr * sr; pos[a][1] = s[1] * cr + s[4] / m.wr * sr; pos[a][2] = s[2] * cz + s[5] / m.wz * sz;
                 vel[a][0] = s[3] * cr - s[0] * m.wr * sr;
                 vel[a][1] = (m.vz_from_vy ? s[4] : s[5]) * cz - s[2] * m.wz * sz;
@@ -239,7 +245,12 @@ __device__ void eval_coefficients(const DevModel& m, Smem2& sm, int w, int lane,
             }
             if (!(q & 1) && tt >= m.tau) ph += m.xi;  // ϕr(t) = t < τ ? 0 : ξ on both red beams (cz_model.jl:136-137,48)
             double re, im;
-            beam_half_omega((q & 1) ? m.blue : m.red, pos[a][0], pos[a][1], pos[a][2], ph, &re, &im);
+            const DevBeam& bm = (q & 1) ? m.blue : m.red;
+            if (bm.kind == CA_BEAM_GAUSS) {
+                double anc[5];
+                const double rp = sqrt_d(fmax(pos[a][0] * pos[a][0] + pos[a][1] * pos[a][1], 1e-300));
+                gauss_exact(bm, rp, pos[a][2], ph, &re, &im, anc);
+            } else beam_half_omega(bm, pos[a][0], pos[a][1], pos[a][2], ph, &re, &im);
             // operators of atom a: k = 4a + {σ1p: Ωr/2, σp1: conj, σpr: Ωb/2, σrp: conj}; left coefficient -i c, right +i c
             double (*ct)[2] = sm.ctab[w][si];
             const int k0 = 4 * a + ((q & 1) ? 2 : 0);
@@ -257,7 +268,7 @@ __device__ void eval_coefficients(const DevModel& m, Smem2& sm, int w, int lane,
             }
             const double dx = pos[0][0] - pos[1][0], dy = pos[0][1] - pos[1][1], dz = pos[0][2] - pos[1][2];
             const double r2 = dx * dx + dy * dy + dz * dz;
-            dt_[4] = m.c6 / (1e-18 + r2 * r2 * r2);        // get_V: cz_model.jl:12-17
+            dt_[4] = m.c6 * rcp_d(1e-18 + r2 * r2 * r2);   // get_V: cz_model.jl:12-17
         }
     }
     __syncwarp();
@@ -289,6 +300,14 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         decay[s] = st.decay[s][lane]; wgt[s] = st.weight[s][lane];
         ndp[s] = (st.nd[s][lane][0] & 0xff) | ((st.nd[s][lane][1] & 0xff) << 8) | ((st.nd[s][lane][2] & 0xff) << 16) | ((st.nd[s][lane][3] & 0xff) << 24);
     }
+    unsigned dreg[kTermRegs];
+    signed char ndv[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+        ndv[s] = st.nd[s][lane][4];
+#pragma unroll
+        for (int t = 0; t < slot_terms(s); ++t) dreg[slot_offset(s) + t] = st.terms[s][t][lane];
+    }
     double (*us)[2] = sm.us[w];
     for (int i = lane; i < kMaxFull; i += 32) { us[i][0] = 0.0; us[i][1] = 0.0; }
     for (int si = 0; si < kStages; ++si)
@@ -304,7 +323,8 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
     double* tab_w = (m.laser_noise && P.nf > 0) ? P.scratch + (size_t)wg * 4 * m.n_nodes : nullptr;
     const double rtol = P.ode.rtol, atol = P.ode.atol;
 
-    // RHS of this lane's elements at stage table `si`, stage vector in smem, own values in `u`
+    // RHS of this lane's elements at stage table `si`, stage vector in smem, own values in `u`.  All loads of a slot are
+    // independent (descriptors are registers, the loops are unrolled), so their latencies overlap.
     auto rhs = [&](int si, const double (&u)[kSlots][2], double (&du)[kSlots][2]) {
         const double (*ct)[2] = sm.ctab[w][si];
         const double* dtb = sm.dtab[w][si];
@@ -314,18 +334,19 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
             // self term: (-i (E_I - E_J) - (γ_I+γ_J)/2) ρ_IJ with E = -dp, -dr on the p, r levels and +V on |rr>
             const double dE = -((double)(signed char)(ndp[s] & 0xff) * d0 + (double)(signed char)((ndp[s] >> 8) & 0xff) * d1 +
                                 (double)(signed char)((ndp[s] >> 16) & 0xff) * d2 + (double)(signed char)((ndp[s] >> 24) & 0xff) * d3) +
-                              (double)st.nd[s][lane][4] * V;
+                              (double)ndv[s] * V;
             double ar = -decay[s] * u[s][0] + dE * u[s][1];
             double ai = -decay[s] * u[s][1] - dE * u[s][0];
-            const int nt_ = st.n_terms[s];
-            for (int t = 0; t < nt_; ++t) {
-                const unsigned dsc = st.terms[s][t][lane];
+            double br = 0.0, bi = 0.0;
+#pragma unroll
+            for (int t = 0; t < slot_terms(s); ++t) {
+                const unsigned dsc = dreg[slot_offset(s) + t];
                 const double2 c = *reinterpret_cast<const double2*>(ct[dsc & 63u]);
                 const double2 r = *reinterpret_cast<const double2*>(us[dsc >> 6]);
-                ar += c.x * r.x - c.y * r.y;
-                ai += c.x * r.y + c.y * r.x;
+                if (t & 1) { br = fma(c.x, r.x, br); br = fma(-c.y, r.y, br); bi = fma(c.x, r.y, bi); bi = fma(c.y, r.x, bi); }
+                else { ar = fma(c.x, r.x, ar); ar = fma(-c.y, r.y, ar); ai = fma(c.x, r.y, ai); ai = fma(c.y, r.x, ai); }
             }
-            du[s][0] = ar; du[s][1] = wgt[s] == 1.0 ? 0.0 : ai;  // diagonal elements are real
+            du[s][0] = ar + br; du[s][1] = wgt[s] == 1.0 ? 0.0 : ai + bi;  // diagonal elements are real
         }
     };
     auto publish = [&](const double (&u)[kSlots][2]) {  // owners write (I,J) and (J,I) = conj
@@ -490,22 +511,22 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
                     for (int s = 0; s < kSlots; ++s) {
                         const double er = hh * (dp::e1 * k1[s][0] + dp::e3 * k3[s][0] + dp::e4 * k4[s][0] + dp::e5 * k5[s][0] + dp::e6 * k6[s][0] + dp::e7 * k7[s][0]);
                         const double ei = hh * (dp::e1 * k1[s][1] + dp::e3 * k3[s][1] + dp::e4 * k4[s][1] + dp::e5 * k5[s][1] + dp::e6 * k6[s][1] + dp::e7 * k7[s][1]);
-                        const double sc = atol + rtol * sqrt(fmax(y[s][0] * y[s][0] + y[s][1] * y[s][1], un[s][0] * un[s][0] + un[s][1] * un[s][1]));
-                        sacc += wgt[s] * (er * er + ei * ei) / (sc * sc);
+                        const double isc = rcp_d(atol + rtol * sqrt_d(fmax(y[s][0] * y[s][0] + y[s][1] * y[s][1], un[s][0] * un[s][0] + un[s][1] * un[s][1])));
+                        sacc += wgt[s] * (er * er + ei * ei) * (isc * isc);
                     }
                     const double EEst2 = warp_sum2(sacc) * (1.0 / 625.0);
                     if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; break; }
                     const double beta1 = 0.17, beta2 = 0.04, gam = 0.9, qmin = 0.2, qmax = 10.0, ln_qoldinit = -9.210340371976182;
                     double q, lnE = 0.0;
                     if (EEst2 == 0.0) q = 1.0 / qmax;
-                    else { lnE = 0.5 * log(EEst2); q = exp(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
+                    else { lnE = 0.5 * log(EEst2); q = exp_d(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
                     if (EEst2 <= 1.0) {
                         lnq_old = (EEst2 == 0.0) ? ln_qoldinit : fmax(lnE, ln_qoldinit);
-                        const double prop = hh / q;
+                        const double prop = hh * rcp_d(q);
                         dt = clipped ? fmax(dt, prop) : prop;
                     } else {
                         accept = false;
-                        dt = hh / fmin(1.0 / qmin, exp(beta1 * lnE) / gam);
+                        dt = hh * rcp_d(fmin(1.0 / qmin, exp_d(beta1 * lnE) * (1.0 / gam)));
                         n_rej++;
                         if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; break; }
                     }
@@ -621,6 +642,8 @@ extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* t
     if (!P.ode.adaptive && !(P.ode.dt0 > 0)) { set_error("adaptive=false needs dt > 0"); return CA_ERR_ARG; }
     static thread_local Struct2 hs;
     if ((rc = build_struct2(psi0, P.model, &hs))) return rc;
+    for (int sl = 0; sl < kSlots; ++sl)
+        if (hs.n_terms[sl] > slot_terms(sl)) { set_error("two-atom kernel: gather table exceeds the compiled per-slot term counts"); return CA_ERR_UNSUPPORTED; }
     cudaEvent_t e0 = ctx_event(c, 0), e1 = ctx_event(c, 1), e2 = ctx_event(c, 2), e3 = ctx_event(c, 3);
     CA_CUDA2(cudaEventRecord(e0, s));
     // device buffers (ids 20..): struct, tspan, samples x2, phases x4, f/amps, scratch, accum, counters, out
