@@ -662,7 +662,7 @@ int ca_release_recapture(ca_ctx* c, const double* trap, const double* atom, cons
     CA_CUDA(cudaEventRecord(c->ev[3], c->stream));
     CA_CUDA(cudaStreamSynchronize(c->stream));
     const unsigned long long* hc = (const unsigned long long*)c->pinned;
-    const double div = (out_flags & CA_OUT_SUMS) ? 1.0 : (double)(n_total > 0 ? n_total : std::max<long long>(1, n));
+    const double div = (out_flags & CA_OUT_SUMS) ? 1.0 : (double)(n_total > 0 ? n_total : n);  // N = 0 gives 0/0 = NaN like `recapture ./ N` (basic_experiments.jl:80)
     for (int j = 0; j < nt; ++j) probs[j] = (double)hc[j] / div;
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
