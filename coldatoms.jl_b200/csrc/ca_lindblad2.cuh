@@ -1,0 +1,576 @@
+// ca_lindblad2.cuh -- per-lane code of the two-atom CZ kernel K4 (simulation_czlp, src/cz_model.jl:107-171).
+//
+// One trajectory per WARP, written as a template over a "warp" type W that supplies the lane id, the warp's
+// shared-memory areas, sync() and warp sums: the sm_100a kernel (ca_lindblad2.cu) instantiates it with
+// __syncwarp / shuffles, tests/hostemu instantiates the SAME source with 32 host threads and a barrier.
+//
+// State: for ψ0 without |l> components ρ is 16x16 (levels 0,1,r,p of both atoms) ⊕ 4x4 (atom 1
+// lost, L1) ⊕ 4x4 (atom 2 lost, L2) ⊕ ρ_ll,ll.  Every Hermitian block is stored as a REAL matrix M of the same shape,
+//     M[A][B] = Re ρ_AB + Im ρ_AB      (so  2 ρ_AB = (M[A][B] + M[B][A]) + i (M[A][B] - M[B][A])  for every A, B:
+//                                       no case distinction between the triangles and the diagonal),
+// i.e. 256 + 16 + 16 = 288 reals = 9 per lane; ρ_ll,ll follows from the conserved trace.  Lane (B, h) owns rows
+// A = 8h .. 8h+7 of column B = (b1, b2) of the 16x16 block (A = a1 + 4 a2) and one element of L1 (lanes 0-15) or L2.
+//
+// RHS: with G = Hρ (column B of G only needs column B of ρ because H acts on the row index),
+//     dρ = -i (G - G†) + dissipator,      H = H1 ⊗ 1 + 1 ⊗ H2 + V |rr><rr|   (cz_model.jl:31-65).
+// A lane rebuilds the complex entries of its half column from its own reals and the transposed reals (one exchange
+// through shared memory, conflict-free: rows are padded to 18 doubles), multiplies by H with the SAME register-resident
+// coefficients in every lane (H1 couples rows inside a group of four, H2 couples the two groups and the sibling lane),
+// then needs exactly one real of G_BA from the transposed owner (second exchange):
+//     dM[A][B] = (Im G_AB - Re G_AB) + (Im G_BA + Re G_BA) - (γ_A + γ_B)/2 M[A][B] + feeding.   No gather tables, no per-lane
+// coefficient loads; the only irregular accesses are the few population-feeding terms of the jump operators
+// (JumpOperatorsTwo, cz_model.jl:2-9).
+#pragma once
+#include "ca_device.cuh"
+
+namespace ca {
+
+constexpr int kS2 = 9;             // reals per lane
+constexpr int kRS = 18;            // row stride of the 16x16 exchange matrices (144 B: 8 lanes x LDS.128 hit 8 bank groups)
+constexpr int kXL = 16 * kRS;      // offset of the 32 l-block reals in an exchange buffer
+constexpr int kXN = kXL + 32;      // doubles per exchange buffer
+enum { KB_3 = 0, KB_4 = 1, KB_5 = 2, KB_6 = 3, KB_YT = 4, kKB = 5 };   // per-lane buffers in shared memory
+constexpr int kStages2 = 5;        // distinct stage times c2,c3,c4,c5,c6(=c7)
+constexpr int kAccSlots = 10;      // accumulator slots per lane: 9 + ρ_ll,ll (lane 0)
+constexpr int kWarpDoubles2 = 2 * kXN + kKB * kS2 * 32 + kStages2 * 16 + 12;
+
+// Hamiltonian coefficients at one stage time: Ωr/2 (σ1p), Ωb/2 (σpr) of both atoms (with phase noise and the phase jump),
+// detunings (H_pp = -dp, H_rr = -dr) and the blockade shift V -- all stored HALVED (rhs2 multiplies them with 2ρ).
+struct Coef2 { double ar1, ai1, br1, bi1, ar2, ai2, br2, bi2, dp1, dr1, dp2, dr2, V, pad0, pad1, pad2; };
+
+CA_HD int idx5(int A) { return (A & 3) + 5 * (A >> 2); }   // 16-block index a1 + 4 a2 -> reference index a1 + 5 a2
+
+// (lane, slot) holds M[I][J] = Re ρ_IJ + Im ρ_IJ of the 25x25 matrix; returns the composite indices (reference order a1 + 5 a2)
+// and the (lane, slot) of the transposed entry.
+CA_HD void slot_entry(int lane, int slot, int* I, int* J, int* tlane, int* tslot) {
+    if (slot < 8) {
+        const int B = lane >> 1, A = 8 * (lane & 1) + slot;
+        *I = idx5(A); *J = idx5(B);
+        *tlane = (A << 1) | (B >> 3); *tslot = B & 7;
+    } else {
+        const int blk = lane >> 4, a = (lane & 15) >> 2, b = lane & 3;
+        *I = blk == 0 ? 4 + 5 * a : a + 20;
+        *J = blk == 0 ? 4 + 5 * b : b + 20;
+        *tlane = blk * 16 + 4 * b + a; *tslot = 8;
+    }
+}
+
+// host: ρ0 = |ψ0><ψ0| in the per-lane real layout [32][kS2]; false if ψ0 has |l> components (outside the block structure)
+inline bool rho0_lanes(const double* psi0, double* rho0m, double* tr0) {
+    for (int i = 0; i < 25; ++i)
+        if ((i % 5 == 4 || i / 5 == 4) && (psi0[2 * i] != 0.0 || psi0[2 * i + 1] != 0.0)) return false;
+    double tr = 0.0;
+    for (int i = 0; i < 25; ++i) tr += psi0[2 * i] * psi0[2 * i] + psi0[2 * i + 1] * psi0[2 * i + 1];
+    *tr0 = tr;
+    for (int l = 0; l < 32; ++l)
+        for (int s = 0; s < kS2; ++s) {
+            int I, J, tl, ts;
+            slot_entry(l, s, &I, &J, &tl, &ts);
+            const double ar = psi0[2 * I], ai = psi0[2 * I + 1], br = psi0[2 * J], bi = psi0[2 * J + 1];   // ρ_IJ = ψ_I conj(ψ_J)
+            rho0m[l * kS2 + s] = (ar * br + ai * bi) + (ai * br - ar * bi);
+        }
+    return true;
+}
+
+// full complex entry from the sums of a slot and of its transposed slot: out[I + 25 J] (column-major 25x25)
+CA_HD void scatter_entry(int lane, int slot, double v, double vt, double* out) {
+    if (slot == 9) { if (lane == 0) out[2 * (24 + 25 * 24)] = v; return; }
+    int I, J, tl, ts;
+    slot_entry(lane, slot, &I, &J, &tl, &ts);
+    out[2 * (I + 25 * J)] = 0.5 * (v + vt);
+    out[2 * (I + 25 * J) + 1] = I == J ? 0.0 : 0.5 * (v - vt);
+}
+
+// Per-lane static data.
+struct Lane2 {
+    int lane, h;
+    unsigned dg;                // bit j (0..8): own element j is a diagonal entry
+    int a8, blk;
+    int o_pub, o_row, o_sib, o_sibrow, o_f1lo, o_f1hi, o_f2;
+    int o8_t, o8_n1, o8_n1t, o8_n2, o8_n2t, o8_fp, o8_fr, o8_pp;
+    double dlo, dhi, dec8;      // (γ_A + γ_B)/2 without the a1 part
+    double w0, w1, u0, u1, w8;  // population-feeding weights
+
+    CA_HD void init(int ln, const DevModel& m) {
+        lane = ln; h = ln & 1;
+        const int B = ln >> 1, b1 = B & 3, b2 = B >> 2;
+        const double Gp = m.G0 + m.G1 + m.Gl;
+        const double gam[4] = {0.0, 0.0, m.Gr, Gp};
+        dg = 0;
+        for (int j = 0; j < 8; ++j) if (8 * h + j == B) dg |= 1u << j;
+        o_pub = 8 * h * kRS + B;
+        o_row = B * kRS + 8 * h;
+        o_sib = (8 * (1 - h) + 4) * kRS + B;
+        o_sibrow = B * kRS + 8 * (1 - h) + 4;
+        // jumps of atom 1 (σ0p, σ1p): rows with a1 = b1 in {0,1} are fed from M[(p,a2)][(p,b2)]
+        o_f1lo = (3 + 4 * (2 * h)) * kRS + 3 + 4 * b2;
+        o_f1hi = (3 + 4 * (2 * h + 1)) * kRS + 3 + 4 * b2;
+        w0 = b1 == 0 ? m.G0 : 0.0; w1 = b1 == 1 ? m.G1 : 0.0;
+        // jumps of atom 2: rows with a2 = b2 in {0,1} (only the h = 0 half has them) are fed from M[(a1,p)][(b1,p)]
+        o_f2 = 12 * kRS + b1 + 12;
+        u0 = (h == 0 && b2 == 0) ? m.G0 : 0.0; u1 = (h == 0 && b2 == 1) ? m.G1 : 0.0;
+        dlo = 0.5 * (gam[b1] + gam[b2] + gam[2 * h]);
+        dhi = 0.5 * (gam[b1] + gam[b2] + gam[2 * h + 1]);
+        // l-blocks: lane = blk*16 + 4 a + b holds element (a, b) of L1 (atom 1 lost; indices of atom 2) or L2
+        blk = ln >> 4; a8 = (ln & 15) >> 2;
+        const int b8 = ln & 3, base = kXL + blk * 16;
+        if (a8 == b8) dg |= 1u << 8;
+        o8_t = base + 4 * b8 + a8;
+        const int n1 = a8 == 3 ? 1 : 3, n2 = 2;
+        o8_n1 = base + 4 * n1 + b8; o8_n1t = base + 4 * b8 + n1;
+        o8_n2 = base + 4 * n2 + b8; o8_n2t = base + 4 * b8 + n2;
+        if (blk == 0) { o8_fp = (3 + 4 * a8) * kRS + 3 + 4 * b8; o8_fr = (2 + 4 * a8) * kRS + 2 + 4 * b8; }
+        else { o8_fp = (a8 + 12) * kRS + b8 + 12; o8_fr = (a8 + 8) * kRS + b8 + 8; }
+        o8_pp = base + 15;
+        w8 = (a8 == b8 && a8 == 0) ? m.G0 : ((a8 == b8 && a8 == 1) ? m.G1 : 0.0);
+        dec8 = 0.5 * (gam[a8] + gam[b8]);
+    }
+    CA_HD bool is_eq(int j) const { return (dg >> j) & 1u; }
+};
+
+CA_HD void ld2(const double* p, double& a, double& b) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+
+// G += c x (complex)
+#define CA_CMAC(gr, gi, cr, ci, xr_, xi_)        \
+    do {                                         \
+        gr = fma((cr), (xr_), gr);               \
+        gr = fma(-(ci), (xi_), gr);              \
+        gi = fma((cr), (xi_), gi);               \
+        gi = fma((ci), (xr_), gi);               \
+    } while (0)
+
+// TWICE the complex entry of a row from its own real `mo` and the transposed real `mt`
+CA_HD void cplx2(double mo, double mt, double& re, double& im) { re = mo + mt; im = mo - mt; }
+
+// dM/dt of this lane's nine reals; `cf` holds HALF the Hamiltonian entries (the lane works with x = 2ρ).
+// tp[j] returns the transposed partner value: |ρ_AB|² = (u² + tp²)/2 (also on the diagonal, where tp = u).
+template <class W>
+CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const double (&u)[kS2], double (&du)[kS2], double (&tp)[kS2]) {
+    double* xm = w.xm;
+    double* xp = w.xp;
+    // ---- A: publish M
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xm[L.o_pub + j * kRS] = u[j];
+    xm[kXL + L.lane] = u[8];
+    w.sync();
+    // ---- B: x = 2ρ on this half column, G = (H/2) x
+    double xr[8], xi[8], sr[4], si[4];
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ld2(xm + L.o_row + 2 * q, tp[2 * q], tp[2 * q + 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cplx2(u[j], tp[j], xr[j], xi[j]);
+        double st[4];
+        ld2(xm + L.o_sibrow, st[0], st[1]);
+        ld2(xm + L.o_sibrow + 2, st[2], st[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cplx2(xm[L.o_sib + i * kRS], st[i], sr[i], si[i]);
+    }
+    double Gr[8], Gi[8];
+    {
+        const double e2lo = L.h ? -cf.dr2 : 0.0, e2hi = L.h ? -cf.dp2 : 0.0, vrr = L.h ? cf.V : 0.0;
+        const double e1[4] = {0.0, 0.0, -cf.dr1, -cf.dp1};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double e = e1[j & 3] + (j < 4 ? e2lo : e2hi);
+            if (j == 2) e += vrr;   // |rr><rr| (get_V, cz_model.jl:12-17,63)
+            Gr[j] = e * xr[j]; Gi[j] = e * xi[j];
+        }
+        // H1 ⊗ 1: rows (1, r, p) of each group of four
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int j0 = 4 * g;
+            CA_CMAC(Gr[j0 + 1], Gi[j0 + 1], cf.ar1, cf.ai1, xr[j0 + 3], xi[j0 + 3]);     // H[1,p] = Ωr/2
+            CA_CMAC(Gr[j0 + 2], Gi[j0 + 2], cf.br1, -cf.bi1, xr[j0 + 3], xi[j0 + 3]);    // H[r,p] = (Ωb/2)*
+            CA_CMAC(Gr[j0 + 3], Gi[j0 + 3], cf.ar1, -cf.ai1, xr[j0 + 1], xi[j0 + 1]);    // H[p,1] = (Ωr/2)*
+            CA_CMAC(Gr[j0 + 3], Gi[j0 + 3], cf.br1, cf.bi1, xr[j0 + 2], xi[j0 + 2]);     // H[p,r] = Ωb/2
+        }
+        // 1 ⊗ H2: h = 0 holds a2 = (0, 1), h = 1 holds a2 = (r, p); the 1 <-> p coupling crosses to the sibling lane
+        const double k01r = L.h ? cf.br2 : 0.0, k01i = L.h ? -cf.bi2 : 0.0;   // row r <- (Ωb/2)* p
+        const double k10r = L.h ? cf.br2 : 0.0, k10i = L.h ? cf.bi2 : 0.0;    // row p <- Ωb/2 r
+        const double ksr = cf.ar2, ksi = L.h ? -cf.ai2 : cf.ai2;              // row p <- (Ωr/2)* 1 ; row 1 <- Ωr/2 p
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            CA_CMAC(Gr[a], Gi[a], k01r, k01i, xr[4 + a], xi[4 + a]);
+            CA_CMAC(Gr[4 + a], Gi[4 + a], ksr, ksi, sr[a], si[a]);
+            CA_CMAC(Gr[4 + a], Gi[4 + a], k10r, k10i, xr[a], xi[a]);
+        }
+    }
+    // l-block element (a8, b): G = H_s L with H_s the Hamiltonian of the surviving atom
+    double G8r, G8i;
+    {
+        double x8r, x8i, n1r, n1i, n2r, n2i;
+        tp[8] = xm[L.o8_t];
+        cplx2(u[8], tp[8], x8r, x8i);
+        cplx2(xm[L.o8_n1], xm[L.o8_n1t], n1r, n1i);
+        cplx2(xm[L.o8_n2], xm[L.o8_n2t], n2r, n2i);
+        const double alr = L.blk ? cf.ar1 : cf.ar2, ali = L.blk ? cf.ai1 : cf.ai2, ber = L.blk ? cf.br1 : cf.br2, bei = L.blk ? cf.bi1 : cf.bi2;
+        const double dpx = L.blk ? cf.dp1 : cf.dp2, drx = L.blk ? cf.dr1 : cf.dr2;
+        // a = 1: Ωr/2 L_p ; a = r: (Ωb/2)* L_p - dr L_r ; a = p: (Ωr/2)* L_1 + Ωb/2 L_r - dp L_p
+        const double c1r = L.a8 == 0 ? 0.0 : (L.a8 == 2 ? ber : alr);
+        const double c1i = L.a8 == 0 ? 0.0 : (L.a8 == 1 ? ali : (L.a8 == 2 ? -bei : -ali));
+        const double c2r = L.a8 == 3 ? ber : 0.0, c2i = L.a8 == 3 ? bei : 0.0;
+        const double e = L.a8 == 2 ? -drx : (L.a8 == 3 ? -dpx : 0.0);
+        G8r = e * x8r; G8i = e * x8i;
+        CA_CMAC(G8r, G8i, c1r, c1i, n1r, n1i);
+        CA_CMAC(G8r, G8i, c2r, c2i, n2r, n2i);
+    }
+    // publish Im G + Re G for the transposed owner, keep Im G - Re G; decay and population feeding
+    {
+        const double ga[4] = {0.0, 0.0, 0.5 * m.Gr, 0.5 * (m.G0 + m.G1 + m.Gl)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            xp[L.o_pub + j * kRS] = Gi[j] + Gr[j];
+            du[j] = fma(-((j < 4 ? L.dlo : L.dhi) + ga[j & 3]), u[j], Gi[j] - Gr[j]);
+        }
+        xp[kXL + L.lane] = G8i + G8r;
+        const double vlo = xm[L.o_f1lo], vhi = xm[L.o_f1hi];
+        du[0] = fma(L.w0, vlo, du[0]); du[1] = fma(L.w1, vlo, du[1]);
+        du[4] = fma(L.w0, vhi, du[4]); du[5] = fma(L.w1, vhi, du[5]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double v = xm[L.o_f2 + a * kRS];
+            du[a] = fma(L.u0, v, du[a]); du[4 + a] = fma(L.u1, v, du[4 + a]);
+        }
+        double d8 = fma(-L.dec8, u[8], G8i - G8r);
+        d8 = fma(m.Gl, xm[L.o8_fp], d8);
+        d8 = fma(m.Gr, xm[L.o8_fr], d8);
+        du[8] = fma(L.w8, xm[L.o8_pp], d8);
+    }
+    w.sync();
+    // ---- C: add the transposed owner's half of -i (G - G†)
+    {
+        double q[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ld2(xp + L.o_row + 2 * k, q[2 * k], q[2 * k + 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) du[j] += q[j];
+        du[8] += xp[L.o8_t];
+    }
+}
+
+// Coefficients of the five distinct stage times of one step, one (quantity, stage) pair per lane:
+// q = 0..3 -> Ω/2 of red1, blue1, red2, blue2 (own phase-noise traces, phase jump ξ on the red beams: cz_model.jl:37-65,
+// 136-137), q = 4 -> detunings and V(t) = c6 / (1e-18 + R^6) (cz_model.jl:12-17).
+template <class W>
+CA_HD void eval_coefficients2(W& w, const DevModel& m, const double* tab, double t0, double hh, double tn) {
+    const int q = w.lane % 5, si = w.lane / 5;
+    if (si < kStages2) {
+        const double tt = si == kStages2 - 1 ? tn : t0 + MC.rc[si + 2] * hh;
+        double pos[2][3], vel[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const double* s = w.smp + 6 * a;
+            if (m.free_motion) {
+                pos[a][0] = s[0] + s[3] * tt; pos[a][1] = s[1] + s[4] * tt; pos[a][2] = s[2] + s[5] * tt;
+                vel[a][0] = s[3]; vel[a][1] = m.vz_from_vy ? s[4] : s[5];
+            } else {  // R, V: atom_sampler.jl:125-143 (oscillation about the origin although centres are shifted, App. B6)
+                double sr, cr, sz, cz;
+                sincos_fast(m.wr * tt, &sr, &cr); sincos_fast(m.wz * tt, &sz, &cz);
+                pos[a][0] = s[0] * cr + s[3] / m.wr * sr; pos[a][1] = s[1] * cr + s[4] / m.wr * sr; pos[a][2] = s[2] * cz + s[5] / m.wz * sz;
+                vel[a][0] = s[3] * cr - s[0] * m.wr * sr;
+                vel[a][1] = (m.vz_from_vy ? s[4] : s[5]) * cz - s[2] * m.wz * sz;
+            }
+        }
+        double* o = reinterpret_cast<double*>(w.coef + si);
+        if (q < 4) {
+            const int a = q >> 1;
+            double ph = 0.0;
+            if (tab) {
+                int j = (int)(tt * m.inv_dtn);
+                j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+                const double* p = tab + (size_t)q * m.n_nodes + j;
+                const double wgt = (tt - j * m.dtn) * m.inv_dtn;
+                ph = p[0] + wgt * (p[1] - p[0]);
+            }
+            if (!(q & 1) && tt >= m.tau) ph += m.xi;  // ϕr(t) = t < τ ? 0 : ξ on both red beams (cz_model.jl:136-137,48)
+            double re, im;
+            const DevBeam& bm = (q & 1) ? m.blue : m.red;
+            if (bm.kind == CA_BEAM_GAUSS) {
+                double anc[5];
+                const double rp = sqrt_d(fmax(pos[a][0] * pos[a][0] + pos[a][1] * pos[a][1], 1e-300));
+                gauss_exact(bm, rp, pos[a][2], ph, &re, &im, anc);
+            } else beam_half_omega(bm, pos[a][0], pos[a][1], pos[a][2], ph, &re, &im);
+            o[2 * q] = 0.5 * re; o[2 * q + 1] = 0.5 * im;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const double Dd = m.aDx * vel[a][0] + m.aDz * vel[a][1], dd = m.bDx * vel[a][0] + m.bDz * vel[a][1];
+                o[8 + 2 * a] = 0.5 * (m.Delta0 - m.dsign * Dd);      // dp/2: H_pp = -dp
+                o[9 + 2 * a] = 0.5 * (m.delta0 - m.dsign * dd);      // dr/2: H_rr = -dr
+            }
+            const double dx = pos[0][0] - pos[1][0], dy = pos[0][1] - pos[1][1], dz = pos[0][2] - pos[1][2];
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            o[12] = 0.5 * m.c6 * rcp_d(1e-18 + r2 * r2 * r2);      // V/2, get_V: cz_model.jl:12-17
+        }
+    }
+    w.sync();
+}
+
+// Later uses of k3 / k5 read the shared-memory copy (they are stored there for the dense output anyway) instead of
+// pinning 18 registers each across three / two RHS evaluations.
+#ifndef CA_K3_SMEM
+#define CA_K3_SMEM 1
+#endif
+#ifndef CA_K5_SMEM
+#define CA_K5_SMEM 0
+#endif
+#if CA_K3_SMEM
+#define CA_K3L(s) kb[(KB_3 * kS2 + (s)) * 32]
+#else
+#define CA_K3L(s) k3[s]
+#endif
+#if CA_K5_SMEM
+#define CA_K5L(s) kb[(KB_5 * kS2 + (s)) * 32]
+#else
+#define CA_K5L(s) k5[s]
+#endif
+
+#ifdef CA_TIMERS
+#define CA_TICK(w, i) (w).tick(i)
+#else
+#define CA_TICK(w, i)
+#endif
+
+struct Stats2 { long long n_rhs, n_acc, n_rej; int status; };
+
+// One trajectory: DP5 (OrdinaryDiffEq semantics, see oracle) over tspan; ρ and ρ·ρ at every tspan point are ADDED to
+// acc[((j*2 + which)*kAccSlots + slot)*32] (pointer already offset by the lane).
+template <class W>
+CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo, const double* tspan, int nt, const double* tab,
+                      const double* rho0, double tr0, double* acc, Stats2& st) {
+    const double rtol = oo.rtol, atol = oo.atol;
+    double* kb = w.kb;   // kb[(buf*kS2 + s)*32], lane offset included
+    double y[kS2], un[kS2], k1[kS2], k7[kS2], unt[kS2], ut[kS2];
+#pragma unroll
+    for (int s = 0; s < kS2; ++s) { y[s] = rho0[s]; un[s] = y[s]; }
+    const double t0 = tspan[0], tend = tspan[nt - 1];
+    double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0, lnq_old = log(1e-4);
+    long long iters = 0;
+    int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0;
+    auto diag_sum = [&](const double (&v)[kS2]) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < kS2; ++j) s += L.is_eq(j) ? v[j] : 0.0;
+        return s;
+    };
+    // k1 = f(t0, y)
+    eval_coefficients2(w, m, tab, t0, 0.0, t0);
+    rhs2(w, L, m, w.coef[kStages2 - 1], y, k1, unt);
+#pragma unroll
+    for (int s = 0; s < kS2; ++s) { kb[(KB_YT * kS2 + s) * 32] = unt[s]; k7[s] = k1[s]; }
+    n_rhs = 1;
+    double y_ll = tr0 - w.sum(diag_sum(y)), un_ll = y_ll;
+    if (dt <= 0.0) {  // OrdinaryDiffEq initial step (Hairer), norms over all 625 entries
+        double d0 = 0.0, d1 = 0.0, isk2[kS2];
+#pragma unroll
+        for (int s = 0; s < kS2; ++s) {
+            const double a2 = 0.5 * (y[s] * y[s] + unt[s] * unt[s]);   // |ρ_AB|²
+            const double sk = atol + sqrt(a2) * rtol;
+            isk2[s] = 1.0 / (sk * sk);   // the entries (A,B) and (B,A) of the full matrix share |err|² = (e² + e_t²)/2: weight 1 per real
+            d0 += isk2[s] * y[s] * y[s];
+            d1 += isk2[s] * k1[s] * k1[s];
+        }
+        const double f0_ll = -w.sum(diag_sum(k1));
+        const double sk_ll = atol + fabs(y_ll) * rtol;
+        d0 = sqrt((w.sum(d0) + y_ll * y_ll / (sk_ll * sk_ll)) / 625.0);
+        d1 = sqrt((w.sum(d1) + f0_ll * f0_ll / (sk_ll * sk_ll)) / 625.0);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        dt0 = fmin(dt0, oo.dtmax);
+#pragma unroll
+        for (int s = 0; s < kS2; ++s) ut[s] = y[s] + dt0 * k1[s];
+        eval_coefficients2(w, m, tab, t0, 0.0, t0 + dt0);
+        double k2[kS2], dum[kS2];
+        rhs2(w, L, m, w.coef[kStages2 - 1], ut, k2, dum);
+        n_rhs++;
+        double d2 = 0.0;
+#pragma unroll
+        for (int s = 0; s < kS2; ++s) { const double a = k2[s] - k1[s]; d2 += isk2[s] * a * a; }
+        const double f1_ll = -w.sum(diag_sum(k2));
+        d2 = sqrt((w.sum(d2) + (f1_ll - f0_ll) * (f1_ll - f0_ll) / (sk_ll * sk_ll)) / 625.0) / dt0;
+        const double mx = fmax(d1, d2);
+        const double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / 5.0);
+        dt = fmin(100.0 * dt0, fmin(dt1, oo.dtmax));
+    }
+    for (int j = 0; j < nt; ++j) {
+        const double T = tspan[j];
+        const double tstop = oo.dense ? tend : T;
+        while (status == 0 && tcommit < T) {
+            if (h != 0.0) {  // commit the pending accepted step (FSAL)
+#pragma unroll
+                for (int s = 0; s < kS2; ++s) { y[s] = un[s]; k1[s] = k7[s]; }
+                y_ll = un_ll;
+                t = tcommit; h = 0.0;
+            }
+            if (++iters > oo.maxiters) { status = CA_ERR_MAXITERS; break; }
+            double hh = fmin(dt, oo.dtmax);
+            bool clipped = false;
+            if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
+            const double tn = clipped ? tstop : t + hh;
+            CA_TICK(w, 3);
+            eval_coefficients2(w, m, tab, t, hh, tn);
+            CA_TICK(w, 1);
+            double k2[kS2], k3[kS2], k5[kS2], kk[kS2], er[kS2], dum[kS2];
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) ut[s] = fma(hh * MC.a21, k1[s], y[s]);
+            rhs2(w, L, m, w.coef[0], ut, k2, dum);
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) ut[s] = fma(hh, fma(MC.a32, k2[s], MC.a31 * k1[s]), y[s]);
+            rhs2(w, L, m, w.coef[1], ut, k3, dum);
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) {
+                kb[(KB_3 * kS2 + s) * 32] = k3[s];
+                ut[s] = fma(hh, fma(MC.a43, k3[s], fma(MC.a42, k2[s], MC.a41 * k1[s])), y[s]);
+            }
+            rhs2(w, L, m, w.coef[2], ut, kk, dum);   // k4
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) {
+                kb[(KB_4 * kS2 + s) * 32] = kk[s];
+                ut[s] = fma(hh, fma(MC.a54, kk[s], fma(MC.a53, CA_K3L(s), fma(MC.a52, k2[s], MC.a51 * k1[s]))), y[s]);
+            }
+            rhs2(w, L, m, w.coef[3], ut, k5, dum);
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) {
+                kb[(KB_5 * kS2 + s) * 32] = k5[s];
+                const double k4 = kb[(KB_4 * kS2 + s) * 32];
+                ut[s] = fma(hh, fma(MC.a65, k5[s], fma(MC.a64, k4, fma(MC.a63, CA_K3L(s), fma(MC.a62, k2[s], MC.a61 * k1[s])))), y[s]);
+            }
+            rhs2(w, L, m, w.coef[4], ut, kk, dum);   // k6
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) {
+                kb[(KB_6 * kS2 + s) * 32] = kk[s];
+                const double k4 = kb[(KB_4 * kS2 + s) * 32];
+                const double k3v = CA_K3L(s), k5v = CA_K5L(s);
+                un[s] = fma(hh, fma(MC.b6, kk[s], fma(MC.b5, k5v, fma(MC.b4, k4, fma(MC.b3, k3v, MC.b1 * k1[s])))), y[s]);
+                er[s] = fma(MC.e6, kk[s], fma(MC.e5, k5v, fma(MC.e4, k4, fma(MC.e3, k3v, MC.e1 * k1[s]))));
+            }
+            CA_TICK(w, 3);
+            rhs2(w, L, m, w.coef[4], un, k7, unt);   // stage 7 = next step's stage 1 (c6 = c7 = 1)
+            CA_TICK(w, 2);
+            n_rhs += 6;
+            bool accept = true;
+            double un_ll_new = un_ll;
+            if (oo.adaptive) {
+                double sacc = 0.0, sdu = 0.0, sde = 0.0;
+#pragma unroll
+                for (int s = 0; s < kS2; ++s) {
+                    const double e = hh * fma(MC.e7, k7[s], er[s]);
+                    const double yt = kb[(KB_YT * kS2 + s) * 32];
+                    const double isc = rcp_d(atol + rtol * sqrt_d(0.5 * fmax(y[s] * y[s] + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
+                    const bool eq = L.is_eq(s);
+                    sacc += (e * e) * (isc * isc);
+                    sdu += eq ? un[s] : 0.0; sde += eq ? e : 0.0;
+                }
+                w.sum3(sacc, sdu, sde);
+                un_ll_new = tr0 - sdu;
+                {
+                    const double isc = rcp_d(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
+                    sacc += (sde * sde) * (isc * isc);   // err of ρ_ll,ll = -Σ err of the other diagonal entries
+                }
+                const double EEst2 = sacc * (1.0 / 625.0);
+                if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; break; }
+                const double beta1 = 0.17, beta2 = 0.04, gam = 0.9, qmin = 0.2, qmax = 10.0, ln_qoldinit = -9.210340371976182;
+                double q, lnE = 0.0;
+                if (EEst2 == 0.0) q = 1.0 / qmax;
+                else { lnE = 0.5 * log(EEst2); q = exp_d(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
+                if (EEst2 <= 1.0) {
+                    lnq_old = (EEst2 == 0.0) ? ln_qoldinit : fmax(lnE, ln_qoldinit);
+                    const double prop = hh * rcp_d(q);
+                    dt = clipped ? fmax(dt, prop) : prop;
+                } else {
+                    accept = false;
+                    dt = hh * rcp_d(fmin(1.0 / qmin, exp_d(beta1 * lnE) * (1.0 / gam)));
+                    n_rej++;
+                    if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; break; }
+                }
+            } else {
+                dt = oo.dt0;
+                un_ll_new = tr0 - w.sum(diag_sum(un));
+            }
+            if (accept) {
+                n_acc++; h = hh; tcommit = tn; un_ll = un_ll_new;
+#pragma unroll
+                for (int s = 0; s < kS2; ++s) kb[(KB_YT * kS2 + s) * 32] = unt[s];   // becomes the partner of y at the commit
+            }
+        }
+        // ---- output at T (Hairer contd5 inside the last accepted step)
+        double o[kS2];
+        if (h == 0.0 || T >= tcommit) {
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) o[s] = un[s];
+        } else {
+            const double th = (T - t) / h, th1 = 1.0 - th;
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) {
+                const double k3 = kb[(KB_3 * kS2 + s) * 32], k4 = kb[(KB_4 * kS2 + s) * 32], k5 = kb[(KB_5 * kS2 + s) * 32], k6 = kb[(KB_6 * kS2 + s) * 32];
+                const double r2 = un[s] - y[s], r3 = h * k1[s] - r2, r4 = r2 - h * k7[s] - r3;
+                const double r5 = h * (MC.d1 * k1[s] + MC.d3 * k3 + MC.d4 * k4 + MC.d5 * k5 + MC.d6 * k6 + MC.d7 * k7[s]);
+                o[s] = y[s] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+            }
+        }
+        if (status != 0) {
+#pragma unroll
+            for (int s = 0; s < kS2; ++s) o[s] = 0.0;
+        }
+        // second moment: complex entries through the exchange buffers (xm and xp are contiguous: 16x16 + 2x4x4 complex)
+        double* a0 = acc + (size_t)j * 2 * kAccSlots * 32;
+        {
+            double* xm = w.xm;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) xm[L.o_pub + s * kRS] = o[s];
+            xm[kXL + L.lane] = o[8];
+            w.sync();
+            double xr[kS2], xi[kS2];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) cplx2(o[s], xm[L.o_row + s], xr[s], xi[s]);   // 2ρ
+            cplx2(o[8], xm[L.o8_t], xr[8], xi[8]);
+            w.sync();
+            if (m.rho2_mode == CA_RHO2_MATSQ) {   // (ρ·ρ)_AB = Σ_K ρ_AK ρ_KB, block by block
+                const int B = L.lane >> 1;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) { double* p = xm + ((8 * L.h + s) * 16 + B) * 2; p[0] = xr[s]; p[1] = xi[s]; }
+                { double* p = xm + 512 + L.lane * 2; p[0] = xr[8]; p[1] = xi[8]; }
+                w.sync();
+#pragma unroll 1
+                for (int s = 0; s < 8; ++s) {
+                    double ar = 0.0, ai = 0.0;
+                    const double* row = xm + (8 * L.h + s) * 32;
+                    for (int K = 0; K < 16; ++K) {
+                        const double cr = row[2 * K], ci = row[2 * K + 1], dr = xm[(K * 16 + B) * 2], di = xm[(K * 16 + B) * 2 + 1];
+                        CA_CMAC(ar, ai, cr, ci, dr, di);
+                    }
+                    a0[(kAccSlots + s) * 32] += 0.25 * (ar + ai);
+                }
+                {
+                    double ar = 0.0, ai = 0.0;
+                    const int b8 = L.lane & 3;
+                    const double* blk = xm + 512 + L.blk * 32;
+                    for (int K = 0; K < 4; ++K) {
+                        const double cr = blk[(4 * L.a8 + K) * 2], ci = blk[(4 * L.a8 + K) * 2 + 1], dr = blk[(4 * K + b8) * 2], di = blk[(4 * K + b8) * 2 + 1];
+                        CA_CMAC(ar, ai, cr, ci, dr, di);
+                    }
+                    a0[(kAccSlots + 8) * 32] += 0.25 * (ar + ai);
+                }
+                w.sync();
+            } else {
+#pragma unroll
+                for (int s = 0; s < kS2; ++s) a0[(kAccSlots + s) * 32] += 0.25 * (xr[s] * xr[s] + xi[s] * xi[s]);   // |ρ_AB|² (real: Im part 0)
+            }
+        }
+        double o_ll = tr0 - w.sum(diag_sum(o));
+        if (status != 0) o_ll = 0.0;
+#pragma unroll
+        for (int s = 0; s < kS2; ++s) a0[s * 32] += o[s];
+        if (L.lane == 0) { a0[9 * 32] += o_ll; a0[(kAccSlots + 9) * 32] += o_ll * o_ll; }
+    }
+    st.n_rhs = n_rhs; st.n_acc = n_acc; st.n_rej = n_rej; st.status = status;
+}
+
+}  // namespace ca

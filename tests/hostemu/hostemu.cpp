@@ -5,7 +5,10 @@
 #include <cstring>
 #include <vector>
 
+#include <pthread.h>
+
 #include "../../coldatoms.jl_b200/csrc/ca_device.cuh"
+#include "../../coldatoms.jl_b200/csrc/ca_lindblad2.cuh"
 #include "../../coldatoms.jl_b200/csrc/ca_model.h"
 
 using namespace ca;
@@ -33,7 +36,120 @@ static int run_lane(const DevModel& m, const OdeOpts& oo, const double* tspan, i
     return 0;
 }
 
+// ---- two-atom kernel: the per-lane template of ca_lindblad2.cuh run by 32 host threads in lock-step ----
+struct HostShared {
+    pthread_barrier_t bar;
+    double red[32][3];
+    std::vector<double> mem;
+};
+struct HostWarp {
+    int lane;
+    double *xm, *xp, *kb;
+    Coef2* coef;
+    double* smp;
+    HostShared* sh;
+    void sync() { pthread_barrier_wait(&sh->bar); }
+    double sum(double v) {
+        sh->red[lane][0] = v;
+        sync();
+        double s = 0.0;
+        for (int l = 0; l < 32; ++l) s += sh->red[l][0];
+        sync();
+        return s;
+    }
+    void sum3(double& a, double& b, double& c) {
+        sh->red[lane][0] = a; sh->red[lane][1] = b; sh->red[lane][2] = c;
+        sync();
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int l = 0; l < 32; ++l) { s0 += sh->red[l][0]; s1 += sh->red[l][1]; s2 += sh->red[l][2]; }
+        sync();
+        a = s0; b = s1; c = s2;
+    }
+};
+struct LaneArgs {
+    HostWarp w;
+    const DevModel* m; const OdeOpts* oo; const double* tspan; int nt; const double* tab; const double* rho0; double tr0; double* acc;
+    Stats2 st;
+};
+static void* lane_main(void* p) {
+    LaneArgs* a = static_cast<LaneArgs*>(p);
+    Lane2 L;
+    L.init(a->w.lane, *a->m);
+    integrate2(a->w, L, *a->m, *a->oo, a->tspan, a->nt, a->tab, a->rho0, a->tr0, a->acc, a->st);
+    return nullptr;
+}
+
 extern "C" {
+
+// One two-atom trajectory through the device source: full 25x25 column-major complex ρ(t_j), (ρ·ρ)(t_j).
+int he_rydberg2_traj(const ca_model* model, const double* tspan, int nt, const double* psi0, const double* sample1, const double* sample2,
+                     const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int nf,
+                     const ca_ode_opts* ode, unsigned long long seed, unsigned long long gi, double* rho, double* rho2, long long* stats) {
+    DevModel m;
+    int rc = derive_model(*model, nullptr, 0, tspan[0], tspan[nt - 1], &m);
+    if (rc) return rc;
+    OdeOpts oo;
+    fill_ode(ode, tspan[0], tspan[nt - 1], &oo);
+    std::vector<double> tab;
+    const double* tp = nullptr;
+    if (m.laser_noise && nf > 0) {
+        tab.resize((size_t)4 * m.n_nodes);
+        std::vector<NoiseK> kr(nf), kb(nf);
+        fill_noise_k(f, amp_red, nf, m.dtn, kr.data());
+        fill_noise_k(f, amp_blue, nf, m.dtn, kb.data());
+        for (int q = 0; q < 4; ++q)
+            gen_noise_trace<64>((q & 1) ? kb.data() : kr.data(), nf, m.n_nodes, m.dtn, phases4 ? phases4[q] : nullptr, seed, gi, 2u + q,
+                                tab.data() + (size_t)q * m.n_nodes, 1);
+        tp = tab.data();
+    }
+    double rho0m[32 * kS2], tr0;
+    if (!rho0_lanes(psi0, rho0m, &tr0)) return CA_ERR_UNSUPPORTED;
+    HostShared sh;
+    pthread_barrier_init(&sh.bar, nullptr, 32);
+    sh.mem.assign(kWarpDoubles2 + 2, 0.0);
+    double* base = sh.mem.data();
+    for (int a = 0; a < 2; ++a) {
+        double s6[6] = {0, 0, 0, 0, 0, 0};
+        const double* src = a == 0 ? sample1 : sample2;
+        if (src) std::memcpy(s6, src, sizeof s6);
+        else {
+            SamplerConsts sc;
+            for (int q = 0; q < 6; ++q) sc.sig[q] = m.sig[q];
+            sc.U0 = m.U0; sc.w0 = m.w0; sc.z0 = m.z0; sc.mfac = m.mfac; sc.ecut = m.ecut;
+            sample_atom_literal(sc, seed, gi, (uint32_t)a, s6);
+        }
+        for (int q = 0; q < 3; ++q) s6[q] += m.center[a][q];
+        for (int q = 0; q < 6; ++q) base[2 * kXN + kKB * kS2 * 32 + kStages2 * 16 + 6 * a + q] = m.atom_motion ? s6[q] : 0.0;
+    }
+    std::vector<double> acc((size_t)nt * 2 * kAccSlots * 32, 0.0);
+    std::vector<LaneArgs> la(32);
+    std::vector<pthread_t> th(32);
+    for (int l = 0; l < 32; ++l) {
+        HostWarp& w = la[l].w;
+        w.lane = l; w.xm = base; w.xp = base + kXN; w.kb = base + 2 * kXN + l;
+        w.coef = reinterpret_cast<Coef2*>(base + 2 * kXN + kKB * kS2 * 32);
+        w.smp = base + 2 * kXN + kKB * kS2 * 32 + kStages2 * 16;
+        w.sh = &sh;
+        la[l].m = &m; la[l].oo = &oo; la[l].tspan = tspan; la[l].nt = nt; la[l].tab = tp; la[l].rho0 = rho0m + l * kS2; la[l].tr0 = tr0;
+        la[l].acc = acc.data() + l;
+        pthread_create(&th[l], nullptr, lane_main, &la[l]);
+    }
+    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&sh.bar);
+    std::memset(rho, 0, sizeof(double) * nt * 1250);
+    std::memset(rho2, 0, sizeof(double) * nt * 1250);
+    for (int j = 0; j < nt; ++j)
+        for (int which = 0; which < 2; ++which)
+            for (int s = 0; s < kAccSlots; ++s)
+                for (int l = 0; l < 32; ++l) {
+                    int I, J, tl = 0, ts = 9;
+                    if (s < 9) slot_entry(l, s, &I, &J, &tl, &ts);
+                    const double* a = acc.data() + (size_t)(j * 2 + which) * kAccSlots * 32;
+                    scatter_entry(l, s, a[s * 32 + l], a[ts * 32 + tl], (which ? rho2 : rho) + (size_t)j * 1250);
+                }
+    stats[0] = la[0].st.n_rhs; stats[1] = la[0].st.n_acc; stats[2] = la[0].st.n_rej;
+    return la[0].st.status;
+}
 
 // One trajectory: packed (ρ, ρ²) per time point into out[nt][50].
 int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const double* psi0, const double* sample, const double* phases_red,

@@ -65,17 +65,17 @@ def test_other_initial_states_and_flags(pkg, oracle, ctx, czcfg):
     n = 6
     ode = pkg._abi.ode_opts(dt=6e-5, adaptive=False)
     for psi in (pkg.tensor(pkg.ket_1, pkg.ket_1), pkg.tensor(pkg.ket_0, pkg.ket_1), pkg.tensor((pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2), pkg.ket_r),
-                pkg.tensor((pkg.ket_l + pkg.ket_1) / np.sqrt(2), pkg.ket_1)):
+                pkg.tensor((pkg.ket_p + pkg.ket_1) / np.sqrt(2), (pkg.ket_r - 1j * pkg.ket_0) / np.sqrt(2))):
         model = pkg.model_from_config(cz, two_atom=True, rho2_mode=pkg._abi.CA_RHO2_ABS2)
         kw = dict(seed=4, ode=ode)
         rho, rho2, _ = ctx.rydberg2_run(model, cz.tspan, psi, n, **kw)
         o, o2, _ = oracle.rydberg2_run(model, cz.tspan, psi, n, **kw)
         assert np.abs(rho - o).max() < TOL_FIXED and np.abs(rho2 - o2).max() < TOL_FIXED
-    # a ψ0 whose reachable support exceeds the 160 packed elements the kernel holds is refused loudly, not silently wrong
-    full = (pkg.ket_0 + pkg.ket_1 + pkg.ket_l) / np.sqrt(3)
-    with pytest.raises(pkg._lib.ColdAtomsError) as e:
-        ctx.rydberg2_run(pkg.model_from_config(cz, two_atom=True), cz.tspan, pkg.tensor(full, full), 2)
-    assert e.value.code == pkg._abi.CA_ERR_UNSUPPORTED
+    # a ψ0 with |l> components lies outside the 16x16 + 4x4 + 4x4 + 1 block structure: refused loudly, not silently wrong
+    for bad in (pkg.tensor((pkg.ket_l + pkg.ket_1) / np.sqrt(2), pkg.ket_1), pkg.tensor(pkg.ket_1, pkg.ket_l)):
+        with pytest.raises(pkg._lib.ColdAtomsError) as e:
+            ctx.rydberg2_run(pkg.model_from_config(cz, two_atom=True), cz.tspan, bad, 2)
+        assert e.value.code == pkg._abi.CA_ERR_UNSUPPORTED
     # maxiters is reported (OrdinaryDiffEq default 1e5; close atom pairs need more: V ~ R^-6 sets the step)
     with pytest.raises(pkg._lib.ColdAtomsError) as e:
         ctx.rydberg2_run(pkg.model_from_config(cz, two_atom=True), cz.tspan, cz.ψ0, 2, ode=pkg._abi.ode_opts(maxiters=20))

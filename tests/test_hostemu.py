@@ -132,3 +132,73 @@ def test_device_beam_code(pkg, oracle, he):
         assert he.he_eval_beam(C.byref(b), P(xyz), C.c_longlong(len(xyz)), P(out)) == 0
         o = oracle.eval_beam(b, xyz)
         assert np.abs(out[:, 0] + 1j * out[:, 1] - o).max() < 1e-12 * max(1.0, np.abs(o).max())
+
+
+# ---- two-atom kernel: the per-lane template of ca_lindblad2.cuh executed by 32 host threads in lock-step -------------
+def he_traj2(he, model, tspan, psi0, s1, s2, ph4, f, ar, ab, ode, seed=1, gi=0):
+    tspan = np.ascontiguousarray(tspan, float)
+    nt = len(tspan)
+    rho, rho2 = np.zeros((nt, 25, 25), complex), np.zeros((nt, 25, 25), complex)
+    st = (C.c_longlong * 3)()
+    psi = np.ascontiguousarray(np.asarray(psi0, complex)).view(float)
+    arrs = [None if a is None else np.ascontiguousarray(a, float) for a in (s1, s2, f, ar, ab)]
+    keep = None if ph4 is None else [np.ascontiguousarray(p, float) for p in ph4]
+    ph = None if keep is None else (dp * 4)(*[P(p) for p in keep])
+    nf = 0 if f is None else len(f)
+    rc = he.he_rydberg2_traj(C.byref(model), P(tspan), nt, P(psi), P(arrs[0]), P(arrs[1]), ph, P(arrs[2]), P(arrs[3]), P(arrs[4]), nf,
+                             C.byref(ode), C.c_ulonglong(seed), C.c_ulonglong(gi), rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), st)
+    return rc, rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), list(st)
+
+
+@pytest.fixture(scope="module")
+def czcfg(pkg):
+    _, cz = pkg.get_default_configs()
+    cz.laser_noise = True
+    cz.tspan = np.array([0.0, 0.004, 0.008])
+    cz.ξ = 1.3  # phase jump at tspan[end]/2
+    return cz
+
+
+@pytest.mark.parametrize("free", [True, False])
+def test_warp2_fixed_step_matches_oracle(pkg, oracle, he, czcfg, free):
+    cz = czcfg.copy()
+    cz.free_motion = free
+    rng = np.random.default_rng(3)
+    s1, _ = oracle.sample_atoms(cz.trap_params, cz.atom_params, 1, seed=3, stream=0)
+    s2, _ = oracle.sample_atoms(cz.trap_params, cz.atom_params, 1, seed=3, stream=1)
+    ph = list(rng.uniform(0, 2 * np.pi, (4, 1, len(cz.f))))
+    model = pkg.model_from_config(cz, two_atom=True)
+    ode = pkg._abi.ode_opts(dt=6e-5, adaptive=False)
+    kw = dict(f=cz.f, amp_red=cz.red_laser_phase_amplitudes, amp_blue=cz.blue_laser_phase_amplitudes)
+    rc, r, r2, st = he_traj2(he, model, cz.tspan, cz.ψ0, s1[0], s2[0], [p[0] for p in ph], cz.f, kw["amp_red"], kw["amp_blue"], ode)
+    assert rc == 0
+    o, o2, ost = oracle.rydberg2_run(model, cz.tspan, cz.ψ0, 1, samples1=s1, samples2=s2, phases4=ph, ode=ode, **kw)
+    assert st[0] == ost["n_rhs"]
+    assert np.abs(r - o).max() < 1e-12 and np.abs(r2 - o2).max() < 1e-12
+
+
+def test_warp2_adaptive_states_and_modes(pkg, oracle, he, czcfg):
+    cz = czcfg.copy()
+    kw = dict(f=cz.f, amp_red=cz.red_laser_phase_amplitudes, amp_blue=cz.blue_laser_phase_amplitudes)
+    model = pkg.model_from_config(cz, two_atom=True)
+    # adaptive with on-"device" Philox samples and phases, dense output and tstops mode
+    for ode in (pkg._abi.ode_opts(), pkg._abi.ode_opts(dense=False)):
+        rc, r, r2, st = he_traj2(he, model, cz.tspan, cz.ψ0, None, None, None, cz.f, kw["amp_red"], kw["amp_blue"], ode, seed=17, gi=5)
+        assert rc == 0
+        o, o2, ost = oracle.rydberg2_run(model, cz.tspan, cz.ψ0, 1, seed=17, traj_offset=5, ode=ode, **kw)
+        assert st == [ost["n_rhs"], ost["n_accept"], ost["n_reject"]]
+        assert np.abs(r - o).max() < 1e-10 and np.abs(r2 - o2).max() < 1e-10
+    # other initial states, |ρ_ij|² second moment, a decay channel switched off, no noise
+    cz.laser_noise = False
+    cz.spontaneous_decay_rydberg = False
+    ode = pkg._abi.ode_opts(dt=6e-5, adaptive=False)
+    model = pkg.model_from_config(cz, two_atom=True, rho2_mode=pkg._abi.CA_RHO2_ABS2)
+    for psi in (pkg.tensor(pkg.ket_1, pkg.ket_1), pkg.tensor(pkg.ket_0, pkg.ket_1), pkg.tensor((pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2), pkg.ket_r),
+                pkg.tensor((pkg.ket_p + pkg.ket_1) / np.sqrt(2), (pkg.ket_r - 1j * pkg.ket_0) / np.sqrt(2))):
+        rc, r, r2, _ = he_traj2(he, model, cz.tspan, psi, None, None, None, None, None, None, ode, seed=4, gi=0)
+        assert rc == 0
+        o, o2, _ = oracle.rydberg2_run(model, cz.tspan, psi, 1, seed=4, ode=ode)
+        assert np.abs(r - o).max() < 1e-12 and np.abs(r2 - o2).max() < 1e-12
+    # ψ0 with |l> components lies outside the block structure: refused, not silently wrong
+    rc, *_ = he_traj2(he, model, cz.tspan, pkg.tensor((pkg.ket_l + pkg.ket_1) / np.sqrt(2), pkg.ket_1), None, None, None, None, None, None, ode)
+    assert rc == pkg._abi.CA_ERR_UNSUPPORTED
