@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the Monte-Carlo master-equation hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload r1|r1b|z1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload r1|r1b|z1] [--trajectories N] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one ensemble of synthetic trajectories.  Default workload `r1` is
 BASELINE.json configs[1]: single-atom two-photon Rydberg Rabi oscillation with Doppler/position noise, laser phase
@@ -90,6 +90,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference(pkg, oracle, cfg, natoms, budget_s, threads):
     """Reference CPU path (oracle port, OpenMP over trajectories) on a bounded sample of the same workload."""
     model = pkg.model_from_config(cfg, two_atom=(natoms == 2))
@@ -116,7 +123,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="r1", choices=["r1", "r1b", "z1"])
-    ap.add_argument("--n", type=int, default=0, help="trajectories per GPU per step (default: BASELINE size)")
+    ap.add_argument("--trajectories", type=int, default=0, help="trajectories per GPU per step (default: BASELINE size)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -124,7 +131,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     pkg = graft.load_package()
-    n_per = args.n or {"r1": 1_000_000, "r1b": 1_000_000, "z1": 100_000}[args.workload]
+    n_per = args.trajectories or {"r1": 1_000_000, "r1b": 1_000_000, "z1": 100_000}[args.workload]
     cfg, natoms, desc = workload(pkg, args.workload, n_per)
     metric = "master-eq trajectories/sec"
     unit = "trajectories/s"
@@ -134,7 +141,7 @@ def main():
             return
         oracle = graft.load_oracle()
         oracle.build()
-        threads = oracle.num_threads()
+        threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every core the process may run on
         vals = []
         for i in range(args.warmup + args.steps):
             v, n_s, _ = cpu_reference(pkg, oracle, cfg, natoms, max(2.0, args.cpu_seconds / 2), threads)
@@ -246,7 +253,7 @@ def main():
         if not args.no_cpu:
             oracle = graft.load_oracle()
             oracle.build()
-            threads = oracle.num_threads()
+            threads = host_threads()
             v, n_s, _ = cpu_reference(pkg, oracle, cfg, natoms, args.cpu_seconds, threads)
             cpu = {"value": v, "unit": unit, "cores": threads, "kind": "port",
                    "sample": f"{n_s} trajectories of the same workload (C oracle, OpenMP over trajectories, DP5 rtol 1e-6/atol 1e-8)"}

@@ -21,7 +21,10 @@ int ctx_device(ca_ctx* c);
 void* ctx_buf(ca_ctx* c, int which, size_t bytes);  // grow-only device buffers owned by the context
 cudaEvent_t ctx_event(ca_ctx* c, int i);
 
-constexpr int kWarps2 = 8;   // warps (trajectories) per CTA, one CTA per SM
+#ifndef CA_WARPS2
+#define CA_WARPS2 8
+#endif
+constexpr int kWarps2 = CA_WARPS2;   // warps (trajectories) per CTA, one CTA per SM
 
 struct R2Params {
     DevModel model;
