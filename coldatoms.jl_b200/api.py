@@ -23,7 +23,7 @@ from .physics import Ω_twophoton, δ_twophoton
 __all__ = [
     "simulation", "simulation_czlp", "simulation_blue_intens", "release_recapture", "samples_generate", "ϕ", "phi",
     "calibrate_two_photon", "get_blockade_stark_shift_factor", "get_rydberg_probs", "get_two_qubit_probs", "seed_b200",
-    "Ω", "simple_flattopHG_field", "simple_flattopLG_field", "HG_coeff", "LG_coeff", "last_stats",
+    "Ω", "simple_flattopHG_field", "simple_flattopLG_field", "HG_coeff", "LG_coeff", "last_stats", "blue_intens_model",
 ]
 # Python NFKC-normalises identifiers (ϕ U+03D5 -> φ U+03C6): normalise the export list the same way
 __all__ = [__import__("unicodedata").normalize("NFKC", _n) for _n in __all__]
@@ -220,13 +220,12 @@ def simulation(cfg: RydbergConfig, temperature_calibrate=False, seed=None, devic
     return ρ, ρ2
 
 
-def simulation_blue_intens(tspan, ψ0, atom_params, trap_params, samples, red_laser_params, blue_laser_params, detuning_params,
-                           decay_params, atom_motion=True, free_motion=True, spontaneous_decay=True, parallel=False, device=None,
-                           **ode_kwargs):
-    """`simulation_blue_intens` (src/rydberg_model_arb_bms.jl:15-86): uniform red, flat-top HG/LG blue, Doppler from vz
-    only, two decay channels, no phase noise, host-supplied samples.  The reference file uses symbols that do not
-    exist in the snapshot; the semantics implemented are the ones inferred in SURVEY App. B7 (Δ=k_r vz,
-    δ=(k_r ± k_b) vz, jumps sqrt(Γg)|1><p| and sqrt(Γgt)|0><p|)."""
+def blue_intens_model(atom_params, trap_params, red_laser_params, blue_laser_params, detuning_params, decay_params,
+                      atom_motion=True, free_motion=True, spontaneous_decay=True, parallel=False):
+    """The ca_model behind `simulation_blue_intens` (src/rydberg_model_arb_bms.jl:15-86): uniform red, flat-top HG/LG blue,
+    Doppler from vz only, two decay channels, no phase noise.  The reference file uses symbols that do not exist in the
+    snapshot; the semantics implemented are the ones inferred in SURVEY App. B7 (Δ=k_r vz, δ=(k_r ± k_b) vz, jumps
+    sqrt(Γg)|1><p| and sqrt(Γgt)|0><p|)."""
     m = _abi.ca_model()
     m.atom_m, m.atom_T = map(float, atom_params)
     m.trap_U0, m.trap_w0, m.trap_z0 = map(float, trap_params)
@@ -239,6 +238,15 @@ def simulation_blue_intens(tspan, ψ0, atom_params, trap_params, samples, red_la
     m.decay_intermediate, m.decay_rydberg = 1, 0
     m.doppler_kind, m.parallel = _abi.CA_DOPPLER_Z, int(parallel)
     m.detuning_sign, m.compat, m.rho2_mode, m.n_noise_nodes = _abi.CA_SIGN_RYDBERG1, 0, _abi.CA_RHO2_MATSQ, 1001
+    return m
+
+
+def simulation_blue_intens(tspan, ψ0, atom_params, trap_params, samples, red_laser_params, blue_laser_params, detuning_params,
+                           decay_params, atom_motion=True, free_motion=True, spontaneous_decay=True, parallel=False, device=None,
+                           **ode_kwargs):
+    """`simulation_blue_intens` (src/rydberg_model_arb_bms.jl:15-86) -> (ρ_mean, ρ2_mean) over the host-supplied samples."""
+    m = blue_intens_model(atom_params, trap_params, red_laser_params, blue_laser_params, detuning_params, decay_params,
+                          atom_motion, free_motion, spontaneous_decay, parallel)
     samples = np.asarray(samples, dtype=float).reshape(-1, 6)
     ctx = _lib.default_context(device)
     ρ, ρ2, st = ctx.rydberg1_run(m, tspan, ψ0, len(samples), samples=samples, ode=_ode(ode_kwargs))

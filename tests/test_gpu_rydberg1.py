@@ -147,3 +147,44 @@ def test_simulation_api_and_sweep(pkg, oracle, ctx, r1cfg):
         o, o2, _ = oracle.rydberg1_run(models[k], [0.0, tends[k]], psis[k], n_pp, traj_offset=k * n_pp, **kw)
         assert np.abs(srho[k] - o[-1]).max() < TOL_ADAPTIVE
         assert np.abs(srho2[k] - o2[-1]).max() < TOL_ADAPTIVE
+
+
+def _r2_args(pkg, kind):
+    """R2 workload: params/default.jl:19-54 geometry, uniform red, flat-top HG (n=m=4) or LG (l=6) blue scaled
+    as in notebooks/modeling.ipynb cells 7-8 (wb -> wb/sqrt(s), zb -> zb/s)."""
+    Γ = 2 * np.pi * 6.0
+    Δ0, Ω = 2 * np.pi * 1500.0, 2 * np.pi * 96.0
+    wb, zb = 2.0, pkg.w0_to_z0(2.0, 0.475)
+    T0 = pkg.T_twophoton(Ω, Ω, Δ0)
+    tspan = (T0 / 50) * np.arange(0, 61, 6)
+    if kind == "HG":
+        s = 4 // 2 + 1
+        blue = [Ω, wb / np.sqrt(s), zb / s, "simp_flattop_HG", 4, 4, 1.0]
+    else:
+        s = 6 // 2 + 1
+        blue = [Ω, wb / np.sqrt(s), zb / s, "simp_flattop_LG", 6, 0]
+    return dict(tspan=tspan, ψ0=pkg.ket_1, atom_params=[86.9091835, 70.0], trap_params=[1000.0, 1.1, pkg.w0_to_z0(1.1, 0.852, 1.3)],
+                red_laser_params=[Ω, 100.0, pkg.w0_to_z0(100.0, 0.795)], blue_laser_params=blue,
+                detuning_params=[Δ0, pkg.δ_twophoton(Ω, Ω, Δ0)], decay_params=[Γ / 4, 3 * Γ / 4])
+
+
+@pytest.mark.parametrize("kind", ["HG", "LG"])
+@pytest.mark.parametrize("parallel", [False, True])
+def test_arbitrary_beams_blue_intens(pkg, oracle, ctx, kind, parallel):
+    """simulation_blue_intens (src/rydberg_model_arb_bms.jl:15-86) through the public entry vs the oracle on the same samples."""
+    a = _r2_args(pkg, kind)
+    n = 40
+    samples, _ = oracle.sample_atoms(a["trap_params"], a["atom_params"], n, seed=11)
+    rho, rho2 = pkg.simulation_blue_intens(a["tspan"], a["ψ0"], a["atom_params"], a["trap_params"], samples, a["red_laser_params"],
+                                           a["blue_laser_params"], a["detuning_params"], a["decay_params"], parallel=parallel)
+    m = pkg.blue_intens_model(a["atom_params"], a["trap_params"], a["red_laser_params"], a["blue_laser_params"], a["detuning_params"],
+                              a["decay_params"], parallel=parallel)
+    o, o2, ost = oracle.rydberg1_run(m, a["tspan"], a["ψ0"], n, samples=samples)
+    assert rho.shape == (len(a["tspan"]), 5, 5)
+    assert np.abs(rho - o).max() < TOL_ADAPTIVE and np.abs(rho2 - o2).max() < TOL_ADAPTIVE
+    assert abs(pkg.last_stats()["n_rhs"] - ost["n_rhs"]) <= 0.01 * ost["n_rhs"]
+    # fixed step: no accept/reject decisions, roundoff-level agreement
+    ode = pkg._abi.ode_opts(dt=1e-4, adaptive=False)
+    r, r2, _ = ctx.rydberg1_run(m, a["tspan"][:3], a["ψ0"], n, samples=samples, ode=ode)
+    o, o2, _ = oracle.rydberg1_run(m, a["tspan"][:3], a["ψ0"], n, samples=samples, ode=ode)
+    assert np.abs(r - o).max() < 1e-10 and np.abs(r2 - o2).max() < 1e-10
