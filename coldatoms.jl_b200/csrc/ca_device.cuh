@@ -224,6 +224,7 @@ struct DevModel {
     int atom_motion, free_motion, laser_noise;
     int vz_from_vy, doppler_z_legacy, rho2_mode;
     int rows;                   // bit0: ψ0 has a |0> component, bit1: |l> component
+    int noise_coarse;           // phase-noise tables: every noise_coarse-th node is summed exactly (see gen_noise_trace_c)
     double rho0[25];            // Hermitian-packed initial state (see pack order below)
 };
 
@@ -390,13 +391,16 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
     }
 }
 
-// ---- anchor / increment evaluation of a Gaussian beam (hot path of the adaptive integrator) ----------------------
-// A DP5 step needs the coefficient Ω e^{iφ}/2 at five times inside [t, t+h].  Only the end point is evaluated with the
-// full exp + sincos (it is also the next step's start: FSAL).  Interior stage times use the EXACT geometry
-// (s, q, g) but obtain e^{-g} and cis(φ - s g) from the values at the step start ("anchor") through short Taylor
-// series of the tiny increments Δg, Δa (|Δg| < 1e-3 -> truncation < 1e-17, |Δa| < 1e-2 -> < 1e-20); a lane whose
-// increments exceed the guards (phase jump ξ, tight beams, huge steps) re-evaluates exactly.  Anchors are refreshed by
-// an exact evaluation every step, so nothing accumulates.
+// ---- node-anchored evaluation of a Gaussian beam (hot path of the adaptive integrator) ------------------------------
+// A DP5 step needs the coefficient c(t) = (Ω/2) B(r(t)) e^{iφ(t)} at five times inside [t, t+h] for both beams.  φ(t) is
+// piecewise linear on the phase-noise nodes (rydberg_model.jl:166-167) and ln B along the ballistic trajectory is smooth
+// on the scale w0/v >> node spacing, so on the two node intervals around the middle node jm of the lane's window
+//     ln c(t) = ln c(t_jm) + u (m1 + u m2) + i u Δφ_{left|right},   u = (t - t_jm)/dtn in [-1, 1],
+// with m1, m2 the central first / second differences of ln B over the three window nodes (exact up to the third
+// difference, ~1e-14 for µm-scale beams; a guard on |m2| falls back to the exact evaluation).  Per window advance
+// (every ~13 steps) the lane evaluates one exact exp + sincos and one log1p + atan per beam; per stage time only a
+// degree-4 Taylor exponential of the tiny exponent (|δ| < 2e-3, truncation < 3e-16, guarded).  Nothing accumulates:
+// every value is anchored at an exactly evaluated node.
 struct BeamGeom { double s, iq, g; };
 CA_HD BeamGeom beam_geom(const DevBeam& b, double rp, double z) {
     const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
@@ -406,7 +410,7 @@ CA_HD BeamGeom beam_geom(const DevBeam& b, double rp, double z) {
     o.g = xr * xr * b.inv_w0sq * o.iq;
     return o;
 }
-// exact: returns Ω e^{iφ}/2 and the anchor {e^{-g}, g, cos a, sin a, a} with a = φ - s g
+// exact: returns Ω e^{iφ}/2 (and {e^{-g}, g, cos a, sin a, a} with a = φ - s g)
 CA_HD void gauss_exact(const DevBeam& b, double rp, double z, double phi, double* re, double* im, double* anc) {
     const BeamGeom q = beam_geom(b, rp, z);
     const double eg = exp_d(fmax(-q.g, -700.0));
@@ -418,21 +422,11 @@ CA_HD void gauss_exact(const DevBeam& b, double rp, double z, double phi, double
     *im = e * (sn + q.s * cs);
     anc[0] = eg; anc[1] = q.g; anc[2] = cs; anc[3] = sn; anc[4] = a;
 }
-// incremental: same value to ~1e-16 from the anchor; returns false if the increments are outside the guards
-CA_HD bool gauss_incr(const DevBeam& b, double rp, double z, double phi, double a_eg, double a_g, double a_c, double a_s, double a_a,
-                      double* re, double* im) {
+// log of the noise-free Gaussian beam factor up to the constant ln(Ω0/2):  ln[ iq e^{-g} (1 + i s) e^{-i s g} ]
+CA_HD void gauss_log(const DevBeam& b, double rp, double z, double* lre, double* lim) {
     const BeamGeom q = beam_geom(b, rp, z);
-    const double dg = q.g - a_g;
-    const double da = fma(-q.s, q.g, phi) - a_a;
-    const double em = fma(dg, fma(dg, fma(dg, fma(dg, 1.0 / 24.0, -1.0 / 6.0), 0.5), -1.0), 1.0);       // e^{-dg}
-    const double c2 = da * da;
-    const double dc = fma(c2, fma(c2, fma(c2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);                     // cos da
-    const double ds = da * fma(c2, fma(c2, fma(c2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);        // sin da
-    const double cs = a_c * dc - a_s * ds, sn = a_s * dc + a_c * ds;
-    const double e = b.hO * q.iq * a_eg * em;
-    *re = e * (cs - q.s * sn);
-    *im = e * (sn + q.s * cs);
-    return fabs(dg) < 1e-3 && fabs(da) < 1e-2;
+    *lre = -0.5 * log1p(q.s * q.s) - q.g;
+    *lim = atan(q.s) - q.s * q.g;
 }
 
 // IEEE operations without FMA contraction: the sampler's rejection test and the recapture indicator are
@@ -491,14 +485,14 @@ CA_HD int sample_atom_literal(const SamplerConsts& sc, uint64_t seed, uint64_t i
 struct NoiseK { double om, amp, sh, ch, sig; };  // ω = 2π f, a, sin(ω dtn/2), cos(ω dtn/2), -4 sin²(ω dtn/2)
 
 template <int CH>
-CA_HD void gen_noise_trace(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, const double* __restrict__ phases, uint64_t seed,
-                           uint64_t gi, uint32_t stream, double* __restrict__ out, int stride) {
+CA_HD void gen_noise_trace(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, double t_first, const double* __restrict__ phases,
+                           uint64_t seed, uint64_t gi, uint32_t stream, double* __restrict__ out, int stride) {
     constexpr int KB = 8;  // frequencies advanced together: 8 independent c/d chains hide the FP64 latency
     for (int c0 = 0; c0 < n_nodes; c0 += CH) {
         double acc[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) acc[j] = 0.0;
-        const double t0 = c0 * dtn;
+        const double t0 = fma((double)c0, dtn, t_first);
         for (int k0 = 0; k0 < nf; k0 += KB) {
             double c[KB], d[KB], sig[KB];
 #pragma unroll
@@ -540,6 +534,81 @@ inline void fill_noise_k(const double* f, const double* amp, int nf, double dtn,
         out[k].om = om; out[k].amp = amp[k];
         out[k].sh = sin(0.5 * om * dtn); out[k].ch = cos(0.5 * om * dtn);
         out[k].sig = -4.0 * out[k].sh * out[k].sh;
+    }
+}
+
+// ---- band-limited shortcut -----------------------------------------------------------------------------------------
+// The trace is a sum of cosines with f <= f_max, and the node grid (rydberg_model.jl:216) oversamples it hundreds of
+// times.  Only every c-th node (c = 8, 4 or 2) is summed exactly; the nodes in between follow from 8-point (degree 7)
+// Lagrange interpolation of the exact ones, whose error Σ_k a_k (ω_k c dtn)^8 · 43.07/8! is kept below 1e-14 rad by the
+// choice of c (observed: 6e-16 for the R1 workload at c = 4) -- the table equals the directly summed one to rounding
+// while the O(nodes x frequencies) work drops by c.
+struct LagrangeW { double w[11][8]; };   // rows: c=2 (r=1), c=4 (r=1..3), c=8 (r=1..7); columns: nodes at offsets -3..4
+#define CA_LAGRANGE_INIT {{ \
+    {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
+    {-495.0 / 262144.0, 5005.0 / 262144.0, -27027.0 / 262144.0, 225225.0 / 262144.0, 75075.0 / 262144.0, -19305.0 / 262144.0, 4095.0 / 262144.0, -429.0 / 262144.0}, \
+    {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
+    {-429.0 / 262144.0, 4095.0 / 262144.0, -19305.0 / 262144.0, 75075.0 / 262144.0, 225225.0 / 262144.0, -27027.0 / 262144.0, 5005.0 / 262144.0, -495.0 / 262144.0}, \
+    {-36363.0 / 33554432.0, 374325.0 / 33554432.0, -2121175.0 / 33554432.0, 31817625.0 / 33554432.0, 4545375.0 / 33554432.0, -1272705.0 / 33554432.0, 276675.0 / 33554432.0, -29325.0 / 33554432.0}, \
+    {-495.0 / 262144.0, 5005.0 / 262144.0, -27027.0 / 262144.0, 225225.0 / 262144.0, 75075.0 / 262144.0, -19305.0 / 262144.0, 4095.0 / 262144.0, -429.0 / 262144.0}, \
+    {-78793.0 / 33554432.0, 783783.0 / 33554432.0, -4061421.0 / 33554432.0, 24819795.0 / 33554432.0, 14891877.0 / 33554432.0, -3436587.0 / 33554432.0, 709137.0 / 33554432.0, -73359.0 / 33554432.0}, \
+    {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
+    {-73359.0 / 33554432.0, 709137.0 / 33554432.0, -3436587.0 / 33554432.0, 14891877.0 / 33554432.0, 24819795.0 / 33554432.0, -4061421.0 / 33554432.0, 783783.0 / 33554432.0, -78793.0 / 33554432.0}, \
+    {-429.0 / 262144.0, 4095.0 / 262144.0, -19305.0 / 262144.0, 75075.0 / 262144.0, 225225.0 / 262144.0, -27027.0 / 262144.0, 5005.0 / 262144.0, -495.0 / 262144.0}, \
+    {-29325.0 / 33554432.0, 276675.0 / 33554432.0, -1272705.0 / 33554432.0, 4545375.0 / 33554432.0, 31817625.0 / 33554432.0, -2121175.0 / 33554432.0, 374325.0 / 33554432.0, -36363.0 / 33554432.0} }}
+#if defined(__CUDACC__)
+static __constant__ LagrangeW c_lw = CA_LAGRANGE_INIT;
+#endif
+static const LagrangeW h_lw = CA_LAGRANGE_INIT;
+#if defined(__CUDA_ARCH__)
+#define LW c_lw
+#else
+#define LW h_lw
+#endif
+
+CA_HD int noise_coarse_count(int n_nodes, int c) { return (n_nodes - 1 + c - 1) / c + 8; }   // coarse nodes m = -3 .. ceil((n-1)/c) + 4
+
+// host: largest coarsening factor whose interpolation error bound stays below 1e-14 rad (1 = sum every node)
+inline int choose_noise_coarse(const double* f, const double* amp_a, const double* amp_b, int nf, double dtn, int n_nodes) {
+    if (n_nodes < 64) return 1;
+    for (int c = 8; c >= 2; c >>= 1) {
+        double ba = 0.0, bb = 0.0;
+        for (int k = 0; k < nf; ++k) {
+            const double x = kTwoPi * fabs(f[k]) * c * dtn, x2 = x * x, x8 = (x2 * x2) * (x2 * x2);
+            ba += fabs(amp_a[k]) * x8; bb += fabs(amp_b ? amp_b[k] : 0.0) * x8;
+        }
+        if (fmax(ba, bb) * (43.07 / 40320.0) <= 1e-14) return c;
+    }
+    return 1;
+}
+
+// nk must hold the recurrence constants of spacing c*dtn (fill_noise_k(f, amp, nf, c*dtn)); tmp: noise_coarse_count(n_nodes, c) slots.
+template <int CH>
+CA_HD void gen_noise_trace_c(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, int c, const double* __restrict__ phases, uint64_t seed,
+                             uint64_t gi, uint32_t stream, double* __restrict__ out, int stride, double* __restrict__ tmp, int tstride) {
+    if (c <= 1) { gen_noise_trace<CH>(nk, nf, n_nodes, dtn, 0.0, phases, seed, gi, stream, out, stride); return; }
+    const int n_c = noise_coarse_count(n_nodes, c);
+    gen_noise_trace<CH>(nk, nf, n_c, c * dtn, -3.0 * c * dtn, phases, seed, gi, stream, tmp, tstride);
+    const int row0 = c == 2 ? 0 : (c == 4 ? 1 : 4);
+    double win[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) win[i] = tmp[(size_t)i * tstride];
+    for (int mc = 0; mc * c < n_nodes; ++mc) {
+        if (mc > 0) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) win[i] = win[i + 1];
+            win[7] = tmp[(size_t)(mc + 7) * tstride];
+        }
+        out[(size_t)(mc * c) * stride] = win[3];
+        for (int r = 1; r < c; ++r) {
+            const int j = mc * c + r;
+            if (j >= n_nodes) break;
+            const double* wv = LW.w[row0 + r - 1];
+            double a = wv[0] * win[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) a = fma(wv[i], win[i], a);
+            out[(size_t)j * stride] = a;
+        }
     }
 }
 
@@ -632,9 +701,9 @@ struct Lane1 {
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
-    double* ab;                           // beam anchors ab[((set*2 + beam)*5 + f)*kstride] (fast path only, may be null)
+    double* ab;                           // per beam q: ab[(q*10 + i)*kstride], i = lnB(jm) re,im | lnB(jm+1) re,im | c(t_jm) re,im | m1 re,im | m2 re,im
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
-    int pa;                               // anchor set valid at time t (the other set receives the values at t+h)
+    bool win_ok;                          // the window's quadratic model of ln B passed its guard
     double t, h, dt, lnq_old, tcommit;
     double y[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
@@ -676,35 +745,8 @@ struct Lane1 {
     }
 
     // ---- phase noise: Gridded(Linear) on the node table (rydberg_model.jl:166-167) --------------------------------
-    // The lane caches THREE consecutive nodes (j, j+1 and the prefetched j+2), i.e. two intervals: a step shorter than
-    // the node spacing never leaves the window, so the window is advanced at most once per step (not per stage) and
-    // the per-stage lookup is branch-free and free of FP64<->int conversions (those issue at 1/8 rate).
-    CA_HD void window_at(const DevModel& m, double tt) {   // make tj <= tt < tnx
-        int j = (int)(tt * m.inv_dtn);
-        j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
-        if (j != jc) {
-            const double* q0 = tab + (size_t)j * stride;
-            const double* q1 = q0 + (size_t)m.n_nodes * stride;
-            if (j == jc + 1) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
-            else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
-            const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
-            nr2 = q0[o2]; nb2 = q1[o2];   // prefetch: first used at the next advance
-            jc = j;
-        }
-        tj = j * m.dtn;
-        tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
-    }
-    CA_HD void phases_win(const DevModel& m, double tt, double& pr, double& pb) const {  // needs tj <= tt < tj + 2 dtn
-        pr = 0.0; pb = 0.0;
-        if (tab) {
-            const double w = (tt - tj) * m.inv_dtn;
-            const bool hi = !(tt < tnx);
-            const double w2 = hi ? w - 1.0 : w;
-            const double ra = hi ? nr1 : nr0, rb = hi ? nr2 : nr1, ba = hi ? nb1 : nb0, bb = hi ? nb2 : nb1;
-            pr = fma(w2, rb - ra, ra); pb = fma(w2, bb - ba, ba);
-        }
-        if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
-    }
+    // The lane caches THREE consecutive nodes (jc, jc+1 and jc+2), i.e. two intervals: a step shorter than the node
+    // spacing never leaves the window, so the window is advanced at most once per step (advance_window below).
     CA_HD void noise_at(const DevModel& m, double tt, double& pr, double& pb) const {   // stateless generic lookup
         pr = 0.0; pb = 0.0;
         if (tab) {
@@ -720,22 +762,58 @@ struct Lane1 {
     }
 
     CA_HD bool fast_model(const DevModel& m) const {
-        return NS == 9 && ab != nullptr && m.free_motion && m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS;
+        return NS == 9 && ab != nullptr && m.free_motion && m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS && m.xi == 0.0 &&
+               m.dtn > 0.0;
     }
     CA_HD double stage_time(int n, double tt0, double hh, double tn) const { return n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0); }
 
-    // exact anchors of both beams at time tt into anchor set `set`
-    CA_HD void set_anchors(const DevModel& m, double tt, int set) {
-        double pr, pb, re, im, anc[5];
-        noise_at(m, tt, pr, pb);
-        const double X = fma(vx, tt, x0), Y = fma(vy, tt, y0), Z = fma(vz, tt, z0);
-        const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
+    // Move the three-node window so that t lies in its first interval (middle node jm = jc + 1) and rebuild the beam anchors.
+    CA_HD void advance_window(const DevModel& m, double tt) {
+        int j = (int)(tt * m.inv_dtn);
+        j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+        const bool shift = (j == jc + 1);
+        if (tab) {
+            const double* q0 = tab + (size_t)j * stride;
+            const double* q1 = q0 + (size_t)m.n_nodes * stride;
+            if (shift) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
+            else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
+            const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
+            nr2 = q0[o2]; nb2 = q1[o2];
+        }
+        win_ok = true;
+        const double tm = (j + 1) * m.dtn;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            gauss_exact(q == 0 ? m.red : m.blue, rp, Z, q == 0 ? pr : pb, &re, &im, anc);
+            const DevBeam& bm = q == 0 ? m.red : m.blue;
+            double* a = ab + (size_t)q * 10 * kstride;
+            double L[3][2];
+            if (shift) { L[0][0] = a[0]; L[0][1] = a[kstride]; L[1][0] = a[2 * kstride]; L[1][1] = a[3 * kstride]; }
 #pragma unroll
-            for (int f = 0; f < 5; ++f) ab[((set * 2 + q) * 5 + f) * kstride] = anc[f];
+            for (int i = 0; i < 3; ++i) {
+                if (shift && i < 2) continue;
+                const double tn_ = (j + i) * m.dtn;
+                const double X = fma(vx, tn_, x0), Y = fma(vy, tn_, y0), Z = fma(vz, tn_, z0);
+                gauss_log(bm, sqrt_d(fmax(X * X + Y * Y, 1e-300)), Z, &L[i][0], &L[i][1]);
+            }
+            a[0] = L[1][0]; a[kstride] = L[1][1]; a[2 * kstride] = L[2][0]; a[3 * kstride] = L[2][1];
+            {   // exact coefficient at the middle node, with its noise phase
+                const double X = fma(vx, tm, x0), Y = fma(vy, tm, y0), Z = fma(vz, tm, z0);
+                double re, im, anc[5];
+                gauss_exact(bm, sqrt_d(fmax(X * X + Y * Y, 1e-300)), Z, q == 0 ? nr1 : nb1, &re, &im, anc);
+                a[4 * kstride] = re; a[5 * kstride] = im;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const double dm = L[1][c] - L[0][c], dpl = L[2][c] - L[1][c];
+                a[(6 + c) * kstride] = 0.5 * (dpl + dm);
+                a[(8 + c) * kstride] = 0.5 * (dpl - dm);
+            }
+            const double m2r = 0.5 * ((L[2][0] - L[1][0]) - (L[1][0] - L[0][0])), m2i = 0.5 * ((L[2][1] - L[1][1]) - (L[1][1] - L[0][1]));
+            win_ok = win_ok && (m2r * m2r + m2i * m2i < 1e-12);
         }
+        jc = j;
+        tj = j * m.dtn;
+        tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
     }
 
     // Coefficients of the five distinct stage times of one step (c2..c5 and t+h; stage 7 and the next stage 1 share the
@@ -743,48 +821,44 @@ struct Lane1 {
     CA_HD void stage_coefficients(const DevModel& m, double tt0, double hh, double tn) {
         bool done = false;
         if (fast_model(m)) {
-            bool ok = true;
-            if (tab) {
-                if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
-                ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
-            }
+            if (!(tt0 < tnx) || tt0 < tj) advance_window(m, tt0);
+            bool ok = win_ok && !(tt0 < tj) && tn <= tj + 2.0 * m.dtn;
             if (ok) {
-                // end point: exact; its anchors go to the other set (they become the anchors of the next step)
-                {
-                    double pr, pb, re, im, anc[5];
-                    phases_win(m, tn, pr, pb);
-                    const double X = fma(vx, tn, x0), Y = fma(vy, tn, y0), Z = fma(vz, tn, z0);
-                    const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
+                double ca[2][2], m1[2][2], m2[2][2], sl[2], sr[2];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        gauss_exact(q == 0 ? m.red : m.blue, rp, Z, q == 0 ? pr : pb, &re, &im, anc);
-                        cb[(4 * 6 + 2 * q) * kstride] = re; cb[(4 * 6 + 2 * q + 1) * kstride] = im;
-#pragma unroll
-                        for (int f = 0; f < 5; ++f) ab[(((1 - pa) * 2 + q) * 5 + f) * kstride] = anc[f];
-                    }
+                for (int q = 0; q < 2; ++q) {
+                    const double* a = ab + (size_t)q * 10 * kstride;
+                    ca[q][0] = a[4 * kstride]; ca[q][1] = a[5 * kstride];
+                    m1[q][0] = a[6 * kstride]; m1[q][1] = a[7 * kstride]; m2[q][0] = a[8 * kstride]; m2[q][1] = a[9 * kstride];
                 }
-                // interior stage times: increments from the anchors at tt0
-                double an[2][5];
+                sl[0] = nr1 - nr0; sr[0] = nr2 - nr1; sl[1] = nb1 - nb0; sr[1] = nb2 - nb1;
+                if (!tab) { sl[0] = sr[0] = sl[1] = sr[1] = 0.0; }
+                double worst = 0.0;
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int f = 0; f < 5; ++f) an[q][f] = ab[((pa * 2 + q) * 5 + f) * kstride];
-#pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                    const double tt = fma(MC.rc[n + 2], hh, tt0);
-                    double pr, pb, re, im;
-                    phases_win(m, tt, pr, pb);
-                    const double X = fma(vx, tt, x0), Y = fma(vy, tt, y0), Z = fma(vz, tt, z0);
-                    const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
+                for (int n = 0; n < 5; ++n) {
+                    const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
+                    const double u = fma(tt - tj, m.inv_dtn, -1.0);
+                    const bool hi = !(u < 0.0);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        ok &= gauss_incr(q == 0 ? m.red : m.blue, rp, Z, q == 0 ? pr : pb, an[q][0], an[q][1], an[q][2], an[q][3], an[q][4], &re, &im);
-                        cb[(n * 6 + 2 * q) * kstride] = re; cb[(n * 6 + 2 * q + 1) * kstride] = im;
+                        // δ = u (m1 + u m2) + i u Δφ ;  e^δ = 1 + δ (1 + δ/2 (1 + δ/3 (1 + δ/4)))
+                        const double dr = u * fma(u, m2[q][0], m1[q][0]);
+                        const double di = u * (fma(u, m2[q][1], m1[q][1]) + (hi ? sr[q] : sl[q]));
+                        worst = fmax(worst, fma(dr, dr, di * di));
+                        double er = fma(0.25, dr, 1.0), ei = 0.25 * di;
+                        double t_r = dr * er - di * ei, t_i = dr * ei + di * er;
+                        er = fma(1.0 / 3.0, t_r, 1.0); ei = (1.0 / 3.0) * t_i;
+                        t_r = dr * er - di * ei; t_i = dr * ei + di * er;
+                        er = fma(0.5, t_r, 1.0); ei = 0.5 * t_i;
+                        t_r = dr * er - di * ei; t_i = dr * ei + di * er;
+                        er = 1.0 + t_r; ei = t_i;
+                        cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
+                        cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
                     }
                 }
 #pragma unroll
                 for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
-                done = ok;
+                done = worst < 4e-6;   // |δ| < 2e-3: the degree-4 series is exact to 3e-16
             }
         }
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
@@ -795,7 +869,6 @@ struct Lane1 {
                 double* o = cb + (size_t)n * 6 * kstride;
                 o[0] = c.Ar; o[kstride] = c.Ai; o[2 * kstride] = c.Br; o[3 * kstride] = c.Bi; o[4 * kstride] = c.dp; o[5 * kstride] = c.dr;
             }
-            if (fast_model(m)) set_anchors(m, tn, 1 - pa);
         }
     }
 
@@ -813,7 +886,7 @@ struct Lane1 {
 
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
                     double t0, double* kbase, int kstr, double* cbase, double* abase) {
-        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; pa = 0;
+        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false;
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
         vzq = m.vz_from_vy ? vy : vz;
@@ -823,7 +896,6 @@ struct Lane1 {
             dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
         }
         tab = table; stride = tstride; jc = -5; nr0 = nr1 = nr2 = nb0 = nb1 = nb2 = 0.0; tj = 1e300; tnx = -1e300;
-        if (fast_model(m)) set_anchors(m, t0, 0);
         // initial state
         y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
         y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
@@ -910,7 +982,7 @@ struct Lane1 {
             P[0] = Pn[0]; P[1] = Pn[1]; g1[0] = g7[0]; g1[1] = g7[1];
             t = tcommit;
             h = 0.0;
-            p ^= 1; pa ^= 1;
+            p ^= 1;
         }
         if (++iters > oo.maxiters) { status = CA_ERR_MAXITERS; return; }
         double hh = fmin(dt, oo.dtmax);

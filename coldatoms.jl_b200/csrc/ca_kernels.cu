@@ -48,13 +48,13 @@ struct R1Params {
     const double* phases_blue;
     const NoiseK* nk_red;      // [n_points][nf] per-frequency recurrence constants (dtn depends on the point's t_end)
     const NoiseK* nk_blue;
-    double* scratch;           // per-warp phase-noise tables: [warps][2][n_nodes][32]
+    double* scratch;           // per-warp phase-noise tables [2][n_nodes_max][32] + coarse staging [n_coarse_max][32]
     double* accum;             // [n_points][nt][kNV]
     unsigned long long* counters;  // n_rhs, n_accept, n_reject, n_attempts, status(max |err|)
     OdeOpts ode;
     long long n_per_point, traj_offset, groups_per_point, n_groups;
     unsigned long long seed;
-    int n_points, nt, nf, n_nodes_max;
+    int n_points, nt, nf, n_nodes_max, n_coarse_max;
 };
 
 template <int NS>
@@ -120,12 +120,13 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
         double* tab = nullptr;
         if (m.laser_noise && P.nf > 0) {
             cyc_noise -= clock64();
-            tab = P.scratch + (size_t)wg * 2 * P.n_nodes_max * 32 + lane;
+            tab = P.scratch + (size_t)wg * (2 * P.n_nodes_max + P.n_coarse_max) * 32 + lane;
             if (valid) {
-                gen_noise_trace<kNoiseChunk>(P.nk_red + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn,
-                                             P.phases_red ? P.phases_red + li * P.nf : nullptr, P.seed, gi, 2u, tab, 32);
-                gen_noise_trace<kNoiseChunk>(P.nk_blue + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn,
-                                             P.phases_blue ? P.phases_blue + li * P.nf : nullptr, P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32);
+                double* tmp = tab + (size_t)2 * P.n_nodes_max * 32;
+                gen_noise_trace_c<kNoiseChunk>(P.nk_red + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn, m.noise_coarse,
+                                               P.phases_red ? P.phases_red + li * P.nf : nullptr, P.seed, gi, 2u, tab, 32, tmp, 32);
+                gen_noise_trace_c<kNoiseChunk>(P.nk_blue + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn, m.noise_coarse,
+                                               P.phases_blue ? P.phases_blue + li * P.nf : nullptr, P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32, tmp, 32);
             }
             __syncwarp();
             cyc_noise += clock64();
@@ -245,13 +246,13 @@ __global__ void k_sample_atoms(SamplerConsts sc, long long n, long long traj_off
 }
 
 // ϕ tables: one thread per trajectory, output phi[i][node] (lasernoise_sampler.jl:31-37 on a uniform grid)
-__global__ void __launch_bounds__(128) k_phase_noise(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn,
+__global__ void __launch_bounds__(128) k_phase_noise(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, int coarse,
                                                      const double* __restrict__ phases, long long n, long long traj_offset,
-                                                     unsigned long long seed, unsigned stream, double* __restrict__ out) {
+                                                     unsigned long long seed, unsigned stream, double* __restrict__ out, double* __restrict__ tmp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    gen_noise_trace<kNoiseChunk>(nk, nf, n_nodes, dtn, phases ? phases + i * nf : nullptr, seed, (uint64_t)(traj_offset + i), stream,
-                                 out + (size_t)i * n_nodes, 1);
+    gen_noise_trace_c<kNoiseChunk>(nk, nf, n_nodes, dtn, coarse, phases ? phases + i * nf : nullptr, seed, (uint64_t)(traj_offset + i), stream,
+                                   out + (size_t)i * n_nodes, 1, tmp + (size_t)i * noise_coarse_count(n_nodes, coarse), 1);
 }
 
 __global__ void k_eval_beam(DevBeam b, const double* __restrict__ xyz, long long n, double* __restrict__ out) {
@@ -367,7 +368,7 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     std::vector<DevModel> dm(n_points);
     int rows = 0;
     bool any_noise = false;
-    int n_nodes_max = 2;
+    int n_nodes_max = 2, n_coarse_max = 0;
     for (int p = 0; p < n_points; ++p) {
         const double* ts = tspans + (size_t)p * nt;
         for (int j = 1; j < nt; ++j)
@@ -379,6 +380,8 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
             if (!f || !amp_red || !amp_blue || nf < 1) { set_error("laser_noise=true needs f and amplitudes"); return CA_ERR_ARG; }
             any_noise = true;
             if (ts[0] < 0) { set_error("laser noise is tabulated on [0, tspan[end]]: tspan[0] must be >= 0"); return CA_ERR_ARG; }
+            dm[p].noise_coarse = choose_noise_coarse(f, amp_red, amp_blue, nf, dm[p].dtn, dm[p].n_nodes);
+            n_coarse_max = std::max(n_coarse_max, noise_coarse_count(dm[p].n_nodes, dm[p].noise_coarse));
         }
         n_nodes_max = std::max(n_nodes_max, dm[p].n_nodes);
     }
@@ -395,7 +398,7 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     P.n_per_point = n_per_point; P.traj_offset = traj_offset; P.seed = seed;
     P.groups_per_point = (n_per_point + 31) / 32;
     P.n_groups = P.groups_per_point * n_points;
-    P.n_nodes_max = n_nodes_max;
+    P.n_nodes_max = n_nodes_max; P.n_coarse_max = n_coarse_max;
     const bool sweep = n_points > 1;
 
     int rc;
@@ -413,8 +416,8 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
         if ((rc = ensure_pinned(c, nkb))) return rc;
         NoiseK* hk = (NoiseK*)c->pinned;
         for (int p = 0; p < n_points; ++p) {
-            fill_noise_k(f, amp_red, nf, dm[p].dtn, hk + (size_t)p * nf);
-            fill_noise_k(f, amp_blue, nf, dm[p].dtn, hk + (size_t)(n_points + p) * nf);
+            fill_noise_k(f, amp_red, nf, dm[p].noise_coarse * dm[p].dtn, hk + (size_t)p * nf);
+            fill_noise_k(f, amp_blue, nf, dm[p].noise_coarse * dm[p].dtn, hk + (size_t)(n_points + p) * nf);
         }
         if ((rc = c->in_f.ensure(nkb))) return rc;
         CA_CUDA(cudaMemcpyAsync(c->in_f.p, c->pinned, nkb, cudaMemcpyHostToDevice, c->stream));
@@ -430,7 +433,7 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
     int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
     if (any_noise) {
-        if ((rc = c->scratch.ensure(sizeof(double) * (size_t)grid * wpb * 2 * n_nodes_max * 32))) return rc;
+        if ((rc = c->scratch.ensure(sizeof(double) * (size_t)grid * wpb * (2 * n_nodes_max + n_coarse_max) * 32))) return rc;
         P.scratch = (double*)c->scratch.p;
     }
     const size_t n_mats = (size_t)n_points * nt;
@@ -715,14 +718,16 @@ int ca_phase_noise(ca_ctx* c, const double* tnodes, int32_t n_nodes, const doubl
     if (n == 0) return CA_OK;
     int rc;
     std::vector<NoiseK> hk((size_t)nf);
-    fill_noise_k(f, amp, nf, dtn, hk.data());
+    const int coarse = choose_noise_coarse(f, amp, nullptr, nf, dtn, n_nodes);
+    fill_noise_k(f, amp, nf, coarse * dtn, hk.data());
     if ((rc = upload(c, c->in_f, hk.data(), sizeof(NoiseK) * (size_t)nf))) return rc;
     CA_CUDA(cudaStreamSynchronize(c->stream));
     const double* d_ph = nullptr;
     if (phases) { if ((rc = upload(c, c->in_ph[0], phases, sizeof(double) * (size_t)nf * n))) return rc; d_ph = (const double*)c->in_ph[0].p; }
     if ((rc = c->out.ensure(sizeof(double) * (size_t)n * n_nodes))) return rc;
-    k_phase_noise<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const NoiseK*)c->in_f.p, nf, n_nodes, dtn, d_ph, n, traj_offset, seed,
-                                                                     (unsigned)stream_id, (double*)c->out.p);
+    if ((rc = c->scratch.ensure(sizeof(double) * (size_t)n * noise_coarse_count(n_nodes, coarse)))) return rc;
+    k_phase_noise<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const NoiseK*)c->in_f.p, nf, n_nodes, dtn, coarse, d_ph, n, traj_offset, seed,
+                                                                     (unsigned)stream_id, (double*)c->out.p, (double*)c->scratch.p);
     CA_CUDA(cudaGetLastError());
     CA_CUDA(cudaMemcpyAsync(phi_out, c->out.p, sizeof(double) * (size_t)n * n_nodes, cudaMemcpyDeviceToHost, c->stream));
     CA_CUDA(cudaStreamSynchronize(c->stream));

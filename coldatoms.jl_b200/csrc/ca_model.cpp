@@ -100,6 +100,7 @@ int derive_model(const ca_model& m, const double* psi0, int npsi, double t0, dou
     d->atom_motion = m.atom_motion; d->free_motion = m.free_motion; d->laser_noise = m.laser_noise;
     d->vz_from_vy = (m.compat & CA_COMPAT_VZ_FROM_VY) ? 1 : 0;
     d->rho2_mode = m.rho2_mode;
+    d->noise_coarse = 1;
     (void)t0;
     if (psi0 && npsi == 5) {
         double re[5], im[5];

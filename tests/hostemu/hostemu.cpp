@@ -98,7 +98,7 @@ int he_rydberg2_traj(const ca_model* model, const double* tspan, int nt, const d
         fill_noise_k(f, amp_red, nf, m.dtn, kr.data());
         fill_noise_k(f, amp_blue, nf, m.dtn, kb.data());
         for (int q = 0; q < 4; ++q)
-            gen_noise_trace<64>((q & 1) ? kb.data() : kr.data(), nf, m.n_nodes, m.dtn, phases4 ? phases4[q] : nullptr, seed, gi, 2u + q,
+            gen_noise_trace<64>((q & 1) ? kb.data() : kr.data(), nf, m.n_nodes, m.dtn, 0.0, phases4 ? phases4[q] : nullptr, seed, gi, 2u + q,
                                 tab.data() + (size_t)q * m.n_nodes, 1);
         tp = tab.data();
     }
@@ -165,10 +165,12 @@ int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const d
     if (m.laser_noise && nf > 0) {
         tab.resize((size_t)2 * m.n_nodes);
         std::vector<NoiseK> kr(nf), kb(nf);
-        fill_noise_k(f, amp_red, nf, m.dtn, kr.data());
-        fill_noise_k(f, amp_blue, nf, m.dtn, kb.data());
-        gen_noise_trace<64>(kr.data(), nf, m.n_nodes, m.dtn, phases_red, seed, gi, 2u, tab.data(), 1);
-        gen_noise_trace<64>(kb.data(), nf, m.n_nodes, m.dtn, phases_blue, seed, gi, 3u, tab.data() + m.n_nodes, 1);
+        const int cz = choose_noise_coarse(f, amp_red, amp_blue, nf, m.dtn, m.n_nodes);   // same plan as run_r1
+        std::vector<double> tmp(noise_coarse_count(m.n_nodes, cz));
+        fill_noise_k(f, amp_red, nf, cz * m.dtn, kr.data());
+        fill_noise_k(f, amp_blue, nf, cz * m.dtn, kb.data());
+        gen_noise_trace_c<64>(kr.data(), nf, m.n_nodes, m.dtn, cz, phases_red, seed, gi, 2u, tab.data(), 1, tmp.data(), 1);
+        gen_noise_trace_c<64>(kb.data(), nf, m.n_nodes, m.dtn, cz, phases_blue, seed, gi, 3u, tab.data() + m.n_nodes, 1, tmp.data(), 1);
         tp = tab.data();
     }
     double smp[6] = {0, 0, 0, 0, 0, 0};
@@ -188,8 +190,10 @@ int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const d
 int he_noise_trace(const double* f, const double* amp, int nf, int n_nodes, double dtn, const double* phases, unsigned long long seed,
                    unsigned long long gi, unsigned stream, double* out) {
     std::vector<NoiseK> kk(nf);
-    fill_noise_k(f, amp, nf, dtn, kk.data());
-    gen_noise_trace<64>(kk.data(), nf, n_nodes, dtn, phases, seed, gi, stream, out, 1);
+    const int cz = choose_noise_coarse(f, amp, nullptr, nf, dtn, n_nodes);
+    std::vector<double> tmp(noise_coarse_count(n_nodes, cz));
+    fill_noise_k(f, amp, nf, cz * dtn, kk.data());
+    gen_noise_trace_c<64>(kk.data(), nf, n_nodes, dtn, cz, phases, seed, gi, stream, out, 1, tmp.data(), 1);
     return 0;
 }
 
