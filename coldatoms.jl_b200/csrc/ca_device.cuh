@@ -391,16 +391,16 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
     }
 }
 
-// ---- node-anchored evaluation of a Gaussian beam (hot path of the adaptive integrator) ------------------------------
+// ---- anchored evaluation of a Gaussian beam (hot path of the adaptive integrator) -----------------------------------
 // A DP5 step needs the coefficient c(t) = (Ω/2) B(r(t)) e^{iφ(t)} at five times inside [t, t+h] for both beams.  φ(t) is
-// piecewise linear on the phase-noise nodes (rydberg_model.jl:166-167) and ln B along the ballistic trajectory is smooth
-// on the scale w0/v >> node spacing, so on the two node intervals around the middle node jm of the lane's window
-//     ln c(t) = ln c(t_jm) + u (m1 + u m2) + i u Δφ_{left|right},   u = (t - t_jm)/dtn in [-1, 1],
-// with m1, m2 the central first / second differences of ln B over the three window nodes (exact up to the third
-// difference, ~1e-14 for µm-scale beams; a guard on |m2| falls back to the exact evaluation).  Per window advance
-// (every ~13 steps) the lane evaluates one exact exp + sincos and one log1p + atan per beam; per stage time only a
-// degree-4 Taylor exponential of the tiny exponent (|δ| < 2e-3, truncation < 3e-16, guarded).  Nothing accumulates:
-// every value is anchored at an exactly evaluated node.
+// piecewise linear on the phase-noise nodes (rydberg_model.jl:166-167; the lane keeps a three-node window) and ln B along
+// the ballistic trajectory is smooth on the scale w0/v >> h.  Every 16 attempts ALL lanes of a warp re-anchor together
+// (no divergence): one exact exp + sincos at the current time t_a and a quadratic model of ln B from its values at
+// t_a, t_a + H, t_a + 2H (H = 9 h; exact up to the third difference, ~1e-14 for µm-scale beams, guarded through |b2|).
+// In between
+//     c(t) = c(t_a) exp(δ),  δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)),  τ = t - t_a,
+// costs a degree-4 Taylor exponential per stage time (|δ| < 2e-3 guarded: truncation < 3e-16).  Nothing accumulates:
+// every value hangs off an exactly evaluated anchor; a lane whose step leaves [t_a, t_a + 2H] re-anchors on the spot.
 struct BeamGeom { double s, iq, g; };
 CA_HD BeamGeom beam_geom(const DevBeam& b, double rp, double z) {
     const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
@@ -425,8 +425,14 @@ CA_HD void gauss_exact(const DevBeam& b, double rp, double z, double phi, double
 // log of the noise-free Gaussian beam factor up to the constant ln(Ω0/2):  ln[ iq e^{-g} (1 + i s) e^{-i s g} ]
 CA_HD void gauss_log(const DevBeam& b, double rp, double z, double* lre, double* lim) {
     const BeamGeom q = beam_geom(b, rp, z);
-    *lre = -0.5 * log1p(q.s * q.s) - q.g;
-    *lim = atan(q.s) - q.s * q.g;
+    const double s2 = q.s * q.s;
+    double l1p, at;
+    if (s2 < 2.5e-3) {   // |s| = |z'|/z0 is tiny for every realistic beam: alternating series, truncation < 1e-19
+        l1p = s2 * fma(-s2, fma(-s2, fma(-s2, fma(-s2, fma(-s2, 1.0 / 6.0, 1.0 / 5.0), 1.0 / 4.0), 1.0 / 3.0), 0.5), 1.0);
+        at = q.s * fma(-s2, fma(-s2, fma(-s2, fma(-s2, fma(-s2, fma(-s2, 1.0 / 13.0, 1.0 / 11.0), 1.0 / 9.0), 1.0 / 7.0), 1.0 / 5.0), 1.0 / 3.0), 1.0);
+    } else { l1p = log1p(s2); at = atan(q.s); }
+    *lre = -0.5 * l1p - q.g;
+    *lim = at - q.s * q.g;
 }
 
 // IEEE operations without FMA contraction: the sampler's rejection test and the recapture indicator are
@@ -701,9 +707,9 @@ struct Lane1 {
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
-    double* ab;                           // per beam q: ab[(q*10 + i)*kstride], i = lnB(jm) re,im | lnB(jm+1) re,im | c(t_jm) re,im | m1 re,im | m2 re,im
+    double* ab;                           // per beam q: ab[(q*7 + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a); ab[14] = t_a, ab[15] = t_a + 2H
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
-    bool win_ok;                          // the window's quadratic model of ln B passed its guard
+    bool win_ok;                          // the anchor's quadratic model of ln B passed its guard
     double t, h, dt, lnq_old, tcommit;
     double y[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
@@ -747,6 +753,32 @@ struct Lane1 {
     // ---- phase noise: Gridded(Linear) on the node table (rydberg_model.jl:166-167) --------------------------------
     // The lane caches THREE consecutive nodes (jc, jc+1 and jc+2), i.e. two intervals: a step shorter than the node
     // spacing never leaves the window, so the window is advanced at most once per step (advance_window below).
+    CA_HD void window_at(const DevModel& m, double tt) {   // make tj <= tt < tnx
+        int j = (int)(tt * m.inv_dtn);
+        j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+        if (j != jc) {
+            const double* q0 = tab + (size_t)j * stride;
+            const double* q1 = q0 + (size_t)m.n_nodes * stride;
+            if (j == jc + 1) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
+            else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
+            const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
+            nr2 = q0[o2]; nb2 = q1[o2];   // prefetch: first used at the next advance
+            jc = j;
+        }
+        tj = j * m.dtn;
+        tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
+    }
+    CA_HD void phases_win(const DevModel& m, double tt, double& pr, double& pb) const {  // needs tj <= tt < tj + 2 dtn
+        pr = 0.0; pb = 0.0;
+        if (tab) {
+            const double w = (tt - tj) * m.inv_dtn;
+            const bool hi = !(tt < tnx);
+            const double w2 = hi ? w - 1.0 : w;
+            const double ra = hi ? nr1 : nr0, rb = hi ? nr2 : nr1, ba = hi ? nb1 : nb0, bb = hi ? nb2 : nb1;
+            pr = fma(w2, rb - ra, ra); pb = fma(w2, bb - ba, ba);
+        }
+        if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
+    }
     CA_HD void noise_at(const DevModel& m, double tt, double& pr, double& pb) const {   // stateless generic lookup
         pr = 0.0; pb = 0.0;
         if (tab) {
@@ -767,83 +799,79 @@ struct Lane1 {
     }
     CA_HD double stage_time(int n, double tt0, double hh, double tn) const { return n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0); }
 
-    // Move the three-node window so that t lies in its first interval (middle node jm = jc + 1) and rebuild the beam anchors.
-    CA_HD void advance_window(const DevModel& m, double tt) {
-        int j = (int)(tt * m.inv_dtn);
-        j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
-        const bool shift = (j == jc + 1);
+    // Exact anchor at time tt: c(tt) with its noise phase and the quadratic model of ln B on [tt, tt + 2H].
+    CA_HD void refresh_anchor(const DevModel& m, double tt, double H) {
+        double pr = 0.0, pb = 0.0;
         if (tab) {
-            const double* q0 = tab + (size_t)j * stride;
-            const double* q1 = q0 + (size_t)m.n_nodes * stride;
-            if (shift) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
-            else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
-            const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
-            nr2 = q0[o2]; nb2 = q1[o2];
+            if (!(tt < tnx) || tt < tj) window_at(m, tt);
+            phases_win(m, tt, pr, pb);
         }
         win_ok = true;
-        const double tm = (j + 1) * m.dtn;
-#pragma unroll
+        const double iH = rcp_d(H);
+#pragma unroll 1
         for (int q = 0; q < 2; ++q) {
             const DevBeam& bm = q == 0 ? m.red : m.blue;
-            double* a = ab + (size_t)q * 10 * kstride;
+            double* a = ab + (size_t)q * 7 * kstride;
             double L[3][2];
-            if (shift) { L[0][0] = a[0]; L[0][1] = a[kstride]; L[1][0] = a[2 * kstride]; L[1][1] = a[3 * kstride]; }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                if (shift && i < 2) continue;
-                const double tn_ = (j + i) * m.dtn;
+                const double tn_ = fma((double)i, H, tt);
                 const double X = fma(vx, tn_, x0), Y = fma(vy, tn_, y0), Z = fma(vz, tn_, z0);
-                gauss_log(bm, sqrt_d(fmax(X * X + Y * Y, 1e-300)), Z, &L[i][0], &L[i][1]);
-            }
-            a[0] = L[1][0]; a[kstride] = L[1][1]; a[2 * kstride] = L[2][0]; a[3 * kstride] = L[2][1];
-            {   // exact coefficient at the middle node, with its noise phase
-                const double X = fma(vx, tm, x0), Y = fma(vy, tm, y0), Z = fma(vz, tm, z0);
-                double re, im, anc[5];
-                gauss_exact(bm, sqrt_d(fmax(X * X + Y * Y, 1e-300)), Z, q == 0 ? nr1 : nb1, &re, &im, anc);
-                a[4 * kstride] = re; a[5 * kstride] = im;
+                const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
+                gauss_log(bm, rp, Z, &L[i][0], &L[i][1]);
+                if (i == 0) {
+                    double re, im, anc[5];
+                    gauss_exact(bm, rp, Z, q == 0 ? pr : pb, &re, &im, anc);
+                    a[0] = re; a[kstride] = im;
+                }
             }
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const double dm = L[1][c] - L[0][c], dpl = L[2][c] - L[1][c];
-                a[(6 + c) * kstride] = 0.5 * (dpl + dm);
-                a[(8 + c) * kstride] = 0.5 * (dpl - dm);
+            for (int c = 0; c < 2; ++c) {   // ln B(tt + τ) - ln B(tt) = τ (b1 + τ b2)
+                const double d1 = L[1][c] - L[0][c], d2 = L[2][c] - L[1][c];
+                a[(2 + c) * kstride] = (1.5 * d1 - 0.5 * d2) * iH;
+                const double b2 = 0.5 * (d2 - d1) * iH * iH;
+                a[(4 + c) * kstride] = b2;
+                win_ok = win_ok && fabs(d2 - d1) < 1e-6;
             }
-            const double m2r = 0.5 * ((L[2][0] - L[1][0]) - (L[1][0] - L[0][0])), m2i = 0.5 * ((L[2][1] - L[1][1]) - (L[1][1] - L[0][1]));
-            win_ok = win_ok && (m2r * m2r + m2i * m2i < 1e-12);
+            a[6 * kstride] = q == 0 ? pr : pb;
         }
-        jc = j;
-        tj = j * m.dtn;
-        tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
+        ab[14 * kstride] = tt; ab[15 * kstride] = fma(2.0, H, tt);
     }
 
     // Coefficients of the five distinct stage times of one step (c2..c5 and t+h; stage 7 and the next stage 1 share the
-    // last) into the shared-memory buffer cb.
-    CA_HD void stage_coefficients(const DevModel& m, double tt0, double hh, double tn) {
+    // last) into the shared-memory buffer cb.  `refresh`: warp-uniform request to re-anchor now.
+    CA_HD void stage_coefficients(const DevModel& m, double tt0, double hh, double tn, bool refresh) {
         bool done = false;
         if (fast_model(m)) {
-            if (!(tt0 < tnx) || tt0 < tj) advance_window(m, tt0);
-            bool ok = win_ok && !(tt0 < tj) && tn <= tj + 2.0 * m.dtn;
+            bool ok = true;
+            if (tab) {
+                if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
+                ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
+            }
+            if (refresh || !(tn <= ab[15 * kstride]) || tt0 < ab[14 * kstride]) refresh_anchor(m, tt0, 9.0 * hh);   // 18 steps of headroom for the 16-attempt cadence
+            ok = ok && win_ok;
             if (ok) {
-                double ca[2][2], m1[2][2], m2[2][2], sl[2], sr[2];
+                double ca[2][2], b1[2][2], b2[2][2], pa[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const double* a = ab + (size_t)q * 10 * kstride;
-                    ca[q][0] = a[4 * kstride]; ca[q][1] = a[5 * kstride];
-                    m1[q][0] = a[6 * kstride]; m1[q][1] = a[7 * kstride]; m2[q][0] = a[8 * kstride]; m2[q][1] = a[9 * kstride];
+                    const double* a = ab + (size_t)q * 7 * kstride;
+                    ca[q][0] = a[0]; ca[q][1] = a[kstride];
+                    b1[q][0] = a[2 * kstride]; b1[q][1] = a[3 * kstride]; b2[q][0] = a[4 * kstride]; b2[q][1] = a[5 * kstride];
+                    pa[q] = a[6 * kstride];
                 }
-                sl[0] = nr1 - nr0; sr[0] = nr2 - nr1; sl[1] = nb1 - nb0; sr[1] = nb2 - nb1;
-                if (!tab) { sl[0] = sr[0] = sl[1] = sr[1] = 0.0; }
+                const double ta = ab[14 * kstride];
                 double worst = 0.0;
 #pragma unroll
                 for (int n = 0; n < 5; ++n) {
                     const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
-                    const double u = fma(tt - tj, m.inv_dtn, -1.0);
-                    const bool hi = !(u < 0.0);
+                    const double tau = tt - ta;
+                    double ph[2] = {0.0, 0.0};
+                    if (tab) phases_win(m, tt, ph[0], ph[1]);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        // δ = u (m1 + u m2) + i u Δφ ;  e^δ = 1 + δ (1 + δ/2 (1 + δ/3 (1 + δ/4)))
-                        const double dr = u * fma(u, m2[q][0], m1[q][0]);
-                        const double di = u * (fma(u, m2[q][1], m1[q][1]) + (hi ? sr[q] : sl[q]));
+                        // δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)) ;  e^δ = 1 + δ (1 + δ/2 (1 + δ/3 (1 + δ/4)))
+                        const double dr = tau * fma(tau, b2[q][0], b1[q][0]);
+                        const double di = fma(tau, fma(tau, b2[q][1], b1[q][1]), ph[q] - pa[q]);
                         worst = fmax(worst, fma(dr, dr, di * di));
                         double er = fma(0.25, dr, 1.0), ei = 0.25 * di;
                         double t_r = dr * er - di * ei, t_i = dr * ei + di * er;
@@ -887,6 +915,7 @@ struct Lane1 {
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
                     double t0, double* kbase, int kstr, double* cbase, double* abase) {
         kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false;
+        if (ab) { ab[14 * kstride] = 1e300; ab[15 * kstride] = -1e300; }
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
         vzq = m.vz_from_vy ? vy : vz;
@@ -975,7 +1004,7 @@ struct Lane1 {
     }
 
     // Commit the pending accepted step (FSAL) and attempt one new step towards `tstop`.
-    CA_HD void attempt(const DevModel& m, const Rates& g, const OdeOpts& oo, double tstop) {
+    CA_HD void attempt(const DevModel& m, const Rates& g, const OdeOpts& oo, double tstop, bool refresh = false) {
         if (h != 0.0) {  // commit: y <- un, k1 <- k7 (slot toggle), t <- t+h
 #pragma unroll
             for (int i = 0; i < NS; ++i) y[i] = un[i];
@@ -990,7 +1019,7 @@ struct Lane1 {
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
         const double tn = clipped ? tstop : t + hh;
         double us[NS], ko[NS];
-        stage_coefficients(m, t, hh, tn);
+        stage_coefficients(m, t, hh, tn, refresh);
         Coef cf;
         // population quadratures: ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr, accumulated with the b/e/d weights
         double SB0 = MC.rb[1] * g1[0], SB1 = MC.rb[1] * g1[1], SE0 = MC.re[1] * g1[0], SE1 = MC.re[1] * g1[1], SD0 = MC.rd[1] * g1[0],

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
         Lane1<NS> L;
         L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS == 9 ? sab + threadIdx.x : nullptr);
         const double tend = tsp[P.nt - 1];
+        unsigned n_att = 0;
         double* acc_pt = P.accum + (size_t)pt * P.nt * kNV;
         for (int j = 0; j < P.nt; ++j) {
             const double T = tsp[j];
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             while (true) {
                 const bool need = valid && L.status == 0 && L.tcommit < T;
                 if (!__any_sync(0xffffffffu, need)) break;
-                if (need) L.attempt(m, rt, P.ode, tstop);
+                if (need) L.attempt(m, rt, P.ode, tstop, (n_att & 15) == 0);   // all lanes re-anchor their beam model together
+                ++n_att;
             }
             double v[kNV];
             L.state_at(m, T, v);

@@ -22,10 +22,11 @@ static int run_lane(const DevModel& m, const OdeOpts& oo, const double* tspan, i
     double kstore[6 * NS], cstore[30], astore[20];
     L.init(m, rt, oo, smp, tab, 1, tspan[0], kstore, 1, cstore, NS == 9 ? astore : nullptr);
     const double tend = tspan[nt - 1];
+    unsigned n_att = 0;
     for (int j = 0; j < nt; ++j) {
         const double T = tspan[j];
         const double tstop = oo.dense ? tend : T;
-        while (L.status == 0 && L.tcommit < T) L.attempt(m, rt, oo, tstop);
+        while (L.status == 0 && L.tcommit < T) { L.attempt(m, rt, oo, tstop, (n_att & 15) == 0); ++n_att; }
         if (L.status) return L.status;
         double v[kNV];
         L.state_at(m, T, v);
