@@ -13,3 +13,6 @@ from .physics import Sϕ, ϕ_amplitudes, Ω_twophoton, T_twophoton, δ_twophoton
 from .config import (RydbergConfig, CZLPConfig, get_default_configs, model_from_config, beam_from_params,  # noqa: F401
                      ket_0, ket_1, ket_r, ket_p, ket_l, tensor, nlevelstate)
 from .api import *  # noqa: F401,F403
+from .gates import get_gate, project_on_qubit, Id, Hadamard, X, Y, Z, RX, RY, RZ, op_tensor  # noqa: F401
+from .fidelity import (basis_fidelity_states, get_rydberg_fidelity_configs, get_rydberg_infidelity, get_parity_fidelity,  # noqa: F401
+                       get_parity_fidelity_temp, get_cz_infidelity, parity_scan)

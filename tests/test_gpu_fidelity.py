@@ -1,0 +1,41 @@
+"""GPU tests of the fidelity callers (src/fidelity.jl) built on the batched sweep and the CZ ensemble."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rydberg_infidelity_batched_equals_serial(pkg):
+    cfg, _ = pkg.get_default_configs()
+    T0 = cfg.tspan[20]
+    cfg.tspan = np.array([0.0, T0])   # 2π pulse: returns every qubit state to itself up to the known phase
+    U = pkg.RZ(0.0)
+    a = pkg.get_rydberg_infidelity(cfg, U=U, n_samples=6, seed=5, batched=True)
+    b = pkg.get_rydberg_infidelity(cfg, U=U, n_samples=6, seed=5, batched=False)
+    assert list(a) == list(b) == ["Intermdeiate state decay", "Rydberg state decay", "Laser noise", "Atom motion", "Total"]
+    for k in a:
+        assert abs(a[k] - b[k]) < 1e-9, (k, a[k], b[k])
+        assert -1e-9 < a[k] < 1.0
+    # each error source alone costs less than all of them together (up to sampling noise of 6 trajectories)
+    assert a["Rydberg state decay"] < a["Total"] + 1e-3 and a["Intermdeiate state decay"] < a["Total"] + 1e-3
+
+
+def test_cz_parity_pipeline(pkg, oracle):
+    _, cz = pkg.get_default_configs()
+    c = cz.copy()
+    c.spontaneous_decay_intermediate = c.spontaneous_decay_rydberg = c.laser_noise = False
+    c.atom_params[1] = 1.0
+    c.n_samples = 1
+    ϕs, F, ϕmax = pkg.get_parity_fidelity(c, seed=3)
+    assert len(ϕs) == 62832 and F.shape == ϕs.shape and 0 <= ϕmax < 2 * np.pi
+    c.ψ0 = pkg.tensor((pkg.ket_0 + pkg.ket_1) / np.sqrt(2), (pkg.ket_0 + pkg.ket_1) / np.sqrt(2))
+    ρ = pkg.simulation_czlp(c, seed=3)[0][-1]
+    Fmax, _ = pkg.get_parity_fidelity_temp(ρ, ϕmax)
+    assert abs(Fmax - F.max()) < 1e-12
+    # the same single trajectory (Philox seed 3, index 0) through the CPU oracle gives the same scan
+    o, _, _ = oracle.rydberg2_run(pkg.model_from_config(c, two_atom=True), c.tspan, c.ψ0, 1, seed=3)
+    assert np.abs(pkg.parity_scan(o[-1], ϕs[::97]) - F[::97]).max() < 1e-6
+    inf, cal = pkg.get_cz_infidelity(cz, n_samples=2, seed=3)
+    assert abs(cal - (1.0 - F.max())) < 1e-9   # calibration run = the scan's trajectory at its best phase
+    assert set(inf) == {"Intermdeiate state decay", "Rydberg state decay", "Laser noise", "Atom motion", "Total"}
+    assert all(0 <= v < 0.5 for v in inf.values())
