@@ -22,7 +22,7 @@ _lock = threading.Lock()
 EXPORTS = [
     "ca_version", "ca_last_error", "ca_init", "ca_finalize", "ca_set_stream", "ca_reset_stream", "ca_synchronize",
     "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg1_sweep", "ca_release_recapture",
-    "ca_sample_atoms", "ca_phase_noise", "ca_eval_beam",
+    "ca_sample_atoms", "ca_sample_atoms_metropolis", "ca_phase_noise", "ca_eval_beam",
 ]
 
 
@@ -209,6 +209,15 @@ class Context:
         _check(load().ca_sample_atoms(self._h, _p(trap), _p(atom), C.c_int64(n), C.c_int64(traj_offset), C.c_uint64(seed),
                                       C.c_int32(stream), C.c_double(eps), _p(out), C.byref(att)))
         return out, att.value
+
+    def sample_atoms_metropolis(self, trap, atom, n, freq=10, skip=1000, harmonic=False, eps=1e-2, n_chains=0, seed=_abi.DEFAULT_SEED, stream=0):
+        trap, atom = _arr(trap, (3,)), _arr(atom, (2,))
+        out = np.zeros((n, 6))
+        acc = C.c_double()
+        _check(load().ca_sample_atoms_metropolis(self._h, _p(trap), _p(atom), C.c_int64(n), C.c_int64(freq), C.c_int64(skip),
+                                                 C.c_int32(int(bool(harmonic))), C.c_double(eps), C.c_int64(n_chains), C.c_uint64(seed),
+                                                 C.c_int32(stream), _p(out), C.byref(acc)))
+        return out, acc.value
 
     def phase_noise(self, tnodes, f, amp, n, traj_offset=0, seed=_abi.DEFAULT_SEED, stream=_abi.STREAM_RED1, phases=None):
         tnodes, f, amp = _arr(tnodes), _arr(f), _arr(amp)

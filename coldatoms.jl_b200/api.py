@@ -98,17 +98,17 @@ def _allreduce_mean(ctx, run, nt, d, n_total):
 # ---------------------------------------------------------------------------------------------------------
 # samplers (exported helpers, docs/src/examples.md:139)
 # ---------------------------------------------------------------------------------------------------------
-def samples_generate(trap_params, atom_params, N, freq=10, skip=1000, harmonic=True, eps=1e-2, seed=None, device=None):
+def samples_generate(trap_params, atom_params, N, freq=10, skip=1000, harmonic=True, eps=1e-2, seed=None, device=None, n_chains=0):
     """`samples_generate` (src/atom_sampler.jl:80-120) -> (samples[N,6], acc_rate).
 
-    harmonic=True is the on-device Philox sampler (MvNormal + energy rejection, :84-96).  The Metropolis branch
-    (:97-120) is a sequential Markov chain and is not part of the accelerated path yet.
+    harmonic=True is the on-device Philox sampler (MvNormal + energy rejection, :84-96).  harmonic=False is the Metropolis
+    branch (:97-120) run as `n_chains` independent chains, one per GPU thread (each with its own `skip` burn-in, emitting
+    every `freq`-th state); n_chains=1 is the reference's single sequential chain, the default fills the GPU.
     """
-    if not harmonic:
-        raise _lib.ColdAtomsError(_abi.CA_ERR_UNSUPPORTED,
-                                  "samples_generate(harmonic=false) (Metropolis chain, src/atom_sampler.jl:97-120) is not "
-                                  "implemented on the GPU path; use harmonic=true")
     ctx = _lib.default_context(device)
+    if not harmonic:
+        return ctx.sample_atoms_metropolis(trap_params, atom_params, int(N), freq=freq, skip=skip, harmonic=False, eps=eps,
+                                           n_chains=n_chains, seed=_next_seed(seed))
     out, _ = ctx.sample_atoms(trap_params, atom_params, int(N), seed=_next_seed(seed), eps=eps)
     return out, 1
 
@@ -300,15 +300,20 @@ def get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, 
 # ---------------------------------------------------------------------------------------------------------
 def release_recapture(tspan, trap_params, atom_params, N, freq=10, skip=1000, eps=1e-3, harmonic=True, seed=None, device=None,
                       distributed=False):
-    """`release_recapture` (src/basic_experiments.jl:72-81) -> (probs[nt], acc_rate)."""
-    if not harmonic:
-        raise _lib.ColdAtomsError(_abi.CA_ERR_UNSUPPORTED,
-                                  "release_recapture(harmonic=false) needs the Metropolis sampler (src/atom_sampler.jl:97-120), "
-                                  "which is not on the GPU path yet; use harmonic=true")
+    """`release_recapture` (src/basic_experiments.jl:72-81) -> (probs[nt], acc_rate).  harmonic=False draws the atoms with the
+    multi-chain Metropolis sampler (sampler eps stays 1e-2, :73) and feeds them to the recapture kernel."""
     ctx = _lib.default_context(device)
     n = int(N)
     lo, cnt, world = _shard(n, distributed)
     sd = _next_seed(seed)
+    if not harmonic:
+        if world != 1:
+            raise _lib.ColdAtomsError(_abi.CA_ERR_UNSUPPORTED, "release_recapture(harmonic=false) is single-process")
+        smp, acc = ctx.sample_atoms_metropolis(trap_params, atom_params, n, freq=freq, skip=skip, harmonic=False, seed=sd)
+        probs, _, st = ctx.release_recapture(trap_params, atom_params, tspan, n, eps=eps, seed=sd, samples=smp)
+        _last_stats.clear()
+        _last_stats.update(st)
+        return probs, acc
     if world == 1:
         probs, _, st = ctx.release_recapture(trap_params, atom_params, tspan, cnt, traj_offset=lo, n_total=n, eps=eps, seed=sd)
     else:

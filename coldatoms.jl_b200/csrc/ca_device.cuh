@@ -483,6 +483,67 @@ CA_HD int sample_atom_literal(const SamplerConsts& sc, uint64_t seed, uint64_t i
     return -1;
 }
 
+// Metropolis branch of samples_generate (atom_sampler.jl:97-120) as MANY independent chains: chain c starts at the
+// reference's initial state, burns `skip` transitions in and then emits every freq-th state; its k-th sample is global
+// sample c + k*n_chains.  One chain (n_chains = 1) is exactly the reference algorithm.  RNG: Philox(seed; index =
+// chain<<32 | transition, draw 0..2 -> Box-Muller proposal pairs, draw 3 -> acceptance uniform; stream).
+struct MetroConsts { double sd[6]; double U0, w0, z0, mfac, T, ecut; int harmonic; };
+CA_HD double metro_energy(const MetroConsts& mc, const double* c) {
+    double pot;
+    if (mc.harmonic) {   // Π_Harmonic: atom_sampler.jl:24-30
+        const double r2 = CA_ADD(CA_MUL(c[0], c[0]), CA_MUL(c[1], c[1])), zz = CA_DIV(c[2], mc.z0);
+        pot = CA_MUL(mc.U0, CA_ADD(CA_DIV(CA_MUL(2.0, r2), CA_MUL(mc.w0, mc.w0)), CA_MUL(zz, zz)));
+    } else {
+        const double A = trap_A_literal(c[0], c[1], c[2], mc.w0, mc.z0);
+        pot = CA_MUL(mc.U0, CA_ADD(1.0, -CA_MUL(A, A)));
+    }
+    return CA_ADD(pot, kinetic_literal(mc.mfac, c[3], c[4], c[5]));
+}
+// Runs chain `chain`; writes its samples to out[(chain + k*n_chains)*6 ..]; returns accepted transitions, *steps = transitions made.
+CA_HD long long metropolis_chain(const MetroConsts& mc, uint64_t seed, uint32_t stream, long long chain, long long n_chains, long long N,
+                                 long long freq, long long skip, double* out, long long* steps) {
+    const long long M = chain < N ? (N - chain + n_chains - 1) / n_chains : 0;   // samples of this chain
+    *steps = 0;
+    if (M == 0) return 0;
+    const double v0 = CA_DIV(mc.sd[3], sqrt(3.0));
+    double cur[6] = {0.0, 0.0, 0.0, v0, v0, v0};   // atom_sampler.jl:104
+    double Ec = metro_energy(mc, cur);
+    const long long L = skip + (M - 1) * freq + 1;   // states visited up to the last emitted one
+    long long acc = 0, k = 0;
+    for (long long i = 0;; ++i) {
+        if (i >= skip && (i - skip) % freq == 0) {
+            double* o = out + (size_t)(chain + k * n_chains) * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o[q] = cur[q];
+            if (++k == M) break;
+        }
+        if (i + 1 >= L) break;
+        const uint64_t idx = ((uint64_t)chain << 32) | (uint64_t)(i + 1);
+        double nw[6];
+#pragma unroll
+        for (uint32_t c = 0; c < 3; ++c) {
+            U4 w = philox(seed, idx, c, stream);
+            const double u1 = u53_open(w.x, w.y), u2 = u53(w.z, w.w);
+            const double r = sqrt(CA_MUL(-2.0, log(u1)));
+            double sn, cs;
+            sincos_d(CA_MUL(kTwoPi, u2), &sn, &cs);
+            nw[2 * c] = CA_ADD(cur[2 * c], CA_MUL(mc.sd[2 * c], CA_MUL(r, cs)));
+            nw[2 * c + 1] = CA_ADD(cur[2 * c + 1], CA_MUL(mc.sd[2 * c + 1], CA_MUL(r, sn)));
+        }
+        U4 w = philox(seed, idx, 3u, stream);
+        const double u = u53(w.x, w.y);
+        const double En = metro_energy(mc, nw);
+        const double p_acc = CA_DIV(exp(-CA_DIV(En, mc.T)), exp(-CA_DIV(Ec, mc.T)));   // prob_boltzmann ratio, :108
+        if (p_acc > u && En < mc.ecut) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cur[q] = nw[q];
+            Ec = En; ++acc;
+        }
+        ++*steps;
+    }
+    return acc;
+}
+
 // Phase-noise trace (lasernoise_sampler.jl:31-37 on the uniform node grid of rydberg_model.jl:216):
 // out[j*stride] = Σ_k a_k cos(2π f_k j dtn + φ_k), j = 0..n_nodes-1, φ_k ~ U[0,2π) from Philox (two per call) or
 // host-supplied.  Nodes are produced CH at a time with the Reinsch-stabilised cosine recurrence

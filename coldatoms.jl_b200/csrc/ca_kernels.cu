@@ -11,6 +11,7 @@
 //   k_dfma_peak            FP64 FMA-chain microbenchmark (roofline denominator).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -245,6 +246,17 @@ __global__ void k_sample_atoms(SamplerConsts sc, long long n, long long traj_off
 #pragma unroll
     for (int q = 0; q < 6; ++q) out[i * 6 + q] = c[q];
     if (att > 0) atomicAdd(attempts, (unsigned long long)att);
+}
+
+// Metropolis sampler: one chain per thread (atom_sampler.jl:97-120 run as n_chains independent chains)
+__global__ void __launch_bounds__(128) k_metropolis(MetroConsts mc, unsigned long long seed, unsigned stream, long long n_chains, long long N,
+                                                    long long freq, long long skip, double* __restrict__ out, unsigned long long* __restrict__ counters) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    long long steps = 0;
+    const long long acc = metropolis_chain(mc, seed, stream, c, n_chains, N, freq, skip, out, &steps);
+    atomicAdd(counters, (unsigned long long)acc);
+    atomicAdd(counters + 1, (unsigned long long)steps);
 }
 
 // ϕ tables: one thread per trajectory, output phi[i][node] (lasernoise_sampler.jl:31-37 on a uniform grid)
@@ -705,6 +717,37 @@ int ca_sample_atoms(ca_ctx* c, const double* trap, const double* atom, int64_t n
     CA_CUDA(cudaMemcpyAsync(&att, c->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CA_CUDA(cudaStreamSynchronize(c->stream));
     if (attempts_out) *attempts_out = (int64_t)att;
+    return CA_OK;
+}
+
+int ca_sample_atoms_metropolis(ca_ctx* c, const double* trap, const double* atom, int64_t n, int64_t freq, int64_t skip, int32_t harmonic,
+                               double eps, int64_t n_chains, uint64_t seed, int32_t stream_id, double* samples_out, double* acc_rate_out) {
+    if (!c || !trap || !atom || n < 0 || freq < 1 || skip < 0 || !samples_out) { set_error("bad argument"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    if (n_chains <= 0) n_chains = std::min<int64_t>(n, (int64_t)c->sm_count * 256);
+    n_chains = std::max<int64_t>(1, std::min<int64_t>(n_chains, std::max<int64_t>(1, n)));
+    if (n_chains > 0xffffffffLL || n * freq + skip > 0xffffffffLL) { set_error("chain / step index exceeds 32 bits"); return CA_ERR_ARG; }
+    MetroConsts mc;
+    const double U0 = trap[0], w0 = trap[1], z0 = trap[2], m = atom[0], T = atom[1];
+    const double vc = std::sqrt(1.380649e-23 * 1e-6 / 1.66053906660e-27);   // vconst (atom_sampler.jl:3-10), as in ca_model.cpp
+    const double vstep = vc * std::sqrt(T / m), rstep = std::sqrt(T / U0) / 2.0;   // atom_sampler.jl:99-101
+    mc.sd[0] = mc.sd[1] = w0 * rstep; mc.sd[2] = z0 * std::sqrt(2.0) * rstep; mc.sd[3] = mc.sd[4] = mc.sd[5] = vstep;
+    mc.U0 = U0; mc.w0 = w0; mc.z0 = z0; mc.mfac = m / (vc * vc); mc.T = T; mc.ecut = U0 * (1.0 - eps); mc.harmonic = harmonic ? 1 : 0;
+    if (acc_rate_out) *acc_rate_out = 0.0;
+    if (n == 0) return CA_OK;
+    int rc;
+    if ((rc = c->out.ensure(sizeof(double) * 6 * (size_t)n))) return rc;
+    if ((rc = c->counters.ensure(64))) return rc;
+    CA_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    k_metropolis<<<(unsigned)((n_chains + 127) / 128), 128, 0, c->stream>>>(mc, seed, (unsigned)stream_id, n_chains, n, freq, skip, (double*)c->out.p,
+                                                                            (unsigned long long*)c->counters.p);
+    CA_CUDA(cudaGetLastError());
+    CA_CUDA(cudaMemcpyAsync(samples_out, c->out.p, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long hc[2] = {0, 0};
+    CA_CUDA(cudaMemcpyAsync(hc, c->counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    // acc_rate / (N*freq + skip) with one chain (atom_sampler.jl:119); with K chains: accepted / (transitions + K initial states)
+    if (acc_rate_out) *acc_rate_out = (double)hc[0] / (double)(hc[1] + (unsigned long long)n_chains);
     return CA_OK;
 }
 

@@ -10,6 +10,7 @@
  *   ca_rydberg2_run      <- simulation_czlp           src/cz_model.jl:107-171       (lines 111-170)
  *   ca_release_recapture <- release_recapture         src/basic_experiments.jl:72-81
  *   ca_sample_atoms      <- samples_generate (harmonic=true branch) src/atom_sampler.jl:84-96
+ *   ca_sample_atoms_metropolis <- samples_generate (harmonic=false branch) src/atom_sampler.jl:97-120
  *   ca_phase_noise       <- ϕ                         src/lasernoise_sampler.jl:31-37
  *   ca_rydberg1_sweep    <- the (config, ψ0) loops of src/fidelity.jl:78-88 and BASELINE config 5
  *
@@ -207,6 +208,17 @@ int ca_release_recapture(ca_ctx* ctx, const double* trap, const double* atom, co
 int ca_sample_atoms(ca_ctx* ctx, const double* trap, const double* atom, int64_t n, int64_t traj_offset,
                     uint64_t seed, int32_t stream_id, double eps, double* samples_out /* n x 6 host */,
                     int64_t* attempts_out);
+
+/*
+ * Metropolis branch of samples_generate (src/atom_sampler.jl:97-120) run as n_chains independent chains (one per thread):
+ * every chain starts at the reference's initial state, discards `skip` states and emits every freq-th one; chain c's
+ * k-th sample is samples_out[c + k*n_chains].  n_chains = 1 is the reference's single chain; n_chains <= 0 picks
+ * min(n, 256 per SM).  harmonic != 0 uses Π_Harmonic in the Boltzmann weight (the `harmonic` keyword forwarded by
+ * prob_boltzmann / H).  acc_rate_out: accepted transitions / states visited (= acc_rate/(N*freq+skip) for one chain).
+ */
+int ca_sample_atoms_metropolis(ca_ctx* ctx, const double* trap, const double* atom, int64_t n, int64_t freq,
+                               int64_t skip, int32_t harmonic, double eps, int64_t n_chains, uint64_t seed,
+                               int32_t stream_id, double* samples_out, double* acc_rate_out);
 int ca_phase_noise(ca_ctx* ctx, const double* tnodes, int32_t n_nodes, const double* f,
                    const double* amp, int32_t nf, int64_t n, int64_t traj_offset, uint64_t seed,
                    int32_t stream_id, const double* phases /* NULL or n x nf */,

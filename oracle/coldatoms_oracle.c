@@ -270,6 +270,48 @@ double co_sample_atoms_metropolis(const double* trap, const double* atom, int64_
     return (double)acc / (double)L;
 }
 
+/* The same Metropolis kernel run as n_chains independent chains (chain c emits samples c, c+K, ...): the parallel
+ * decomposition the GPU path uses (ca_sample_atoms_metropolis); n_chains = 1 visits exactly the states of the single
+ * reference chain.  RNG: Philox index = chain<<32 | transition.  Returns accepted / states visited. */
+double co_sample_atoms_metropolis_chains(const double* trap, const double* atom, int64_t N, int64_t freq, int64_t skip,
+                                         int harmonic, double eps, int64_t n_chains, uint64_t seed, int32_t stream, double* out) {
+    double U0 = trap[0], w0 = trap[1], z0 = trap[2], m = atom[0], T = atom[1];
+    double vc = co_vconst();
+    double vstep = vc * sqrt(T / m), rstep = sqrt(T / U0) / 2.0;
+    double sd[6] = {w0 * rstep, w0 * rstep, z0 * sqrt(2.0) * rstep, vstep, vstep, vstep};
+    int64_t acc = 0, visited = 0;
+    for (int64_t c = 0; c < n_chains; ++c) {
+        int64_t M = c < N ? (N - c + n_chains - 1) / n_chains : 0;
+        if (M == 0) continue;
+        double cur[6] = {0, 0, 0, vstep / sqrt(3.0), vstep / sqrt(3.0), vstep / sqrt(3.0)};
+        int64_t L = skip + (M - 1) * freq + 1, k = 0;
+        ++visited;
+        for (int64_t i = 0;; ++i) {
+            if (i >= skip && (i - skip) % freq == 0) { memcpy(out + 6 * (c + k * n_chains), cur, sizeof cur); if (++k == M) break; }
+            if (i + 1 >= L) break;
+            uint64_t idx = ((uint64_t)c << 32) | (uint64_t)(i + 1);
+            double nw[6];
+            for (uint32_t q = 0; q < 3; ++q) {
+                uint32_t w[4];
+                co_philox(seed, idx, q, (uint32_t)stream, w);
+                double u1 = u53_open(w[0], w[1]), u2 = u53(w[2], w[3]);
+                double r = sqrt(-2.0 * log(u1));
+                nw[2 * q] = cur[2 * q] + sd[2 * q] * (r * cos(2.0 * CO_PI * u2));
+                nw[2 * q + 1] = cur[2 * q + 1] + sd[2 * q + 1] * (r * sin(2.0 * CO_PI * u2));
+            }
+            uint32_t w[4];
+            co_philox(seed, idx, 3u, (uint32_t)stream, w);
+            double u = u53(w[0], w[1]);
+            double En = harmonic ? energy_H_harmonic(nw, U0, w0, z0, m) : energy_H(nw, U0, w0, z0, m);
+            double Ec = harmonic ? energy_H_harmonic(cur, U0, w0, z0, m) : energy_H(cur, U0, w0, z0, m);
+            double p_acc = exp(-En / T) / exp(-Ec / T);
+            if (p_acc > u && En < U0 * (1.0 - eps)) { memcpy(cur, nw, sizeof cur); ++acc; }
+            ++visited;
+        }
+    }
+    return visited ? (double)acc / (double)visited : 0.0;
+}
+
 /* trap_frequencies: src/utilities.jl:73-79 */
 void co_trap_frequencies(const double atom[2], const double trap[3], double* wr, double* wz) {
     double om = co_vconst() / trap[1] * sqrt(trap[0] / atom[0]);

@@ -14,6 +14,7 @@ void co_sampler_sigmas(const double trap[3], const double atom[2], double sig[6]
 int64_t co_sample_one(const double trap[3], const double atom[2], uint64_t seed, uint64_t index, uint32_t stream, double eps, double out[6]);
 int64_t co_sample_atoms(const double* trap, const double* atom, int64_t n, int64_t offset, uint64_t seed, int32_t stream, double eps, double* out);
 double co_sample_atoms_metropolis(const double* trap, const double* atom, int64_t N, int64_t freq, int64_t skip, int harmonic, double eps, uint64_t seed, int32_t stream, double* out);
+double co_sample_atoms_metropolis_chains(const double* trap, const double* atom, int64_t N, int64_t freq, int64_t skip, int harmonic, double eps, int64_t n_chains, uint64_t seed, int32_t stream, double* out);
 void co_trap_frequencies(const double atom[2], const double trap[3], double* wr, double* wz);
 void co_phi_amplitudes(const double* f, int nf, double h0, const double* hg, const double* sg, const double* fg, int ng, double* out);
 void co_phase_draw(uint64_t seed, uint64_t index, uint32_t stream, int nf, double* phases);

@@ -49,6 +49,7 @@ def lib():
         L.co_HG_coeff.restype = C.c_double
         L.co_sample_atoms.restype = C.c_int64
         L.co_sample_atoms_metropolis.restype = C.c_double
+        L.co_sample_atoms_metropolis_chains.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -104,6 +105,15 @@ def sample_atoms_metropolis(trap, atom, N, freq=10, skip=1000, harmonic=False, e
     out = np.empty((N, 6))
     acc = lib().co_sample_atoms_metropolis(_p(trap), _p(atom), C.c_int64(N), C.c_int64(freq), C.c_int64(skip),
                                            C.c_int(int(harmonic)), C.c_double(eps), C.c_uint64(seed), C.c_int32(stream), _p(out))
+    return out, float(acc)
+
+
+def sample_atoms_metropolis_chains(trap, atom, N, freq=10, skip=1000, harmonic=False, eps=1e-2, n_chains=1, seed=abi.DEFAULT_SEED, stream=0):
+    """The Metropolis kernel run as n_chains independent chains (the GPU path's decomposition; n_chains=1 = the reference chain)."""
+    trap, atom = _arr(trap), _arr(atom)
+    out = np.empty((N, 6))
+    acc = lib().co_sample_atoms_metropolis_chains(_p(trap), _p(atom), C.c_int64(N), C.c_int64(freq), C.c_int64(skip), C.c_int(int(harmonic)),
+                                                  C.c_double(eps), C.c_int64(n_chains), C.c_uint64(seed), C.c_int32(stream), _p(out))
     return out, float(acc)
 
 

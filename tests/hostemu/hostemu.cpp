@@ -224,5 +224,23 @@ int he_eval_beam(const ca_beam* beam, const double* xyz, long long n, double* ou
     return 0;
 }
 
+// multi-chain Metropolis sampler through the device source (all chains run serially here)
+double he_metropolis(const double* trap, const double* atom, long long N, long long freq, long long skip, int harmonic, double eps,
+                     long long n_chains, unsigned long long seed, unsigned stream, double* out) {
+    MetroConsts mc;
+    const double U0 = trap[0], w0 = trap[1], z0 = trap[2], m = atom[0], T = atom[1];
+    const double vc = std::sqrt(1.380649e-23 * 1e-6 / 1.66053906660e-27);
+    const double vstep = vc * std::sqrt(T / m), rstep = std::sqrt(T / U0) / 2.0;
+    mc.sd[0] = mc.sd[1] = w0 * rstep; mc.sd[2] = z0 * std::sqrt(2.0) * rstep; mc.sd[3] = mc.sd[4] = mc.sd[5] = vstep;
+    mc.U0 = U0; mc.w0 = w0; mc.z0 = z0; mc.mfac = m / (vc * vc); mc.T = T; mc.ecut = U0 * (1.0 - eps); mc.harmonic = harmonic;
+    long long acc = 0, visited = 0;
+    for (long long c = 0; c < n_chains; ++c) {
+        long long steps = 0;
+        acc += metropolis_chain(mc, seed, stream, c, n_chains, N, freq, skip, out, &steps);
+        if (c < N) visited += steps + 1;
+    }
+    return visited ? (double)acc / (double)visited : 0.0;
+}
+
 const char* he_last_error() { return get_error(); }
 }

@@ -94,3 +94,28 @@ def test_release_recapture_bit_exact(ctx, oracle):
     assert np.all(np.isnan(p0))  # zeros ./ 0 in the reference (basic_experiments.jl:80)
     p1, i1, _ = ctx.release_recapture(TRAP, ATOM, tspan, 33, samples=samples[:33], want_indicators=True)
     assert np.array_equal(i1, oind[:33])
+
+
+def test_metropolis_sampler_on_device(ctx, oracle, pkg):
+    """samples_generate(harmonic=false) (src/atom_sampler.jl:97-120) as independent chains, one per thread."""
+    for K in (1, 37, 0):
+        n = 500
+        s, acc = ctx.sample_atoms_metropolis(TRAP, ATOM, n, freq=10, skip=300, n_chains=K, seed=21)
+        Keff = K if K > 0 else n
+        o, oacc = oracle.sample_atoms_metropolis_chains(TRAP, ATOM, n, freq=10, skip=300, n_chains=Keff, seed=21)
+        # same Philox keys and operation order; libdevice vs glibc log/sincos/exp differ by an ulp at most
+        assert np.abs(s - o).max() < 1e-9 and abs(acc - oacc) < 1e-6
+    # public entry points
+    s, acc = pkg.samples_generate(TRAP, ATOM, 20000, harmonic=False, seed=4)
+    assert s.shape == (20000, 6) and 0.05 < acc < 0.95
+    h, _ = pkg.samples_generate(TRAP, ATOM, 20000, harmonic=True, seed=4)
+    assert abs(s[:, 3].std() / h[:, 3].std() - 1) < 0.04          # thermal velocities
+    assert 1.0 < s[:, 0].std() / h[:, 0].std() < 1.25             # the true trap is softer than its harmonic approximation
+    tspan = np.arange(0.0, 51.0)
+    p, acc = pkg.release_recapture(tspan, TRAP, ATOM, 20000, harmonic=False, seed=6)
+    ph, _ = pkg.release_recapture(tspan, TRAP, ATOM, 20000, harmonic=True, seed=6)
+    assert p[0] == 1.0 and np.all(np.diff(p) <= 0) and 0.05 < acc < 0.95
+    assert np.abs(p - ph).max() < 0.1                              # same physics, slightly different initial ensemble
+    # empty input
+    s0, _ = ctx.sample_atoms_metropolis(TRAP, ATOM, 0)
+    assert s0.shape == (0, 6)

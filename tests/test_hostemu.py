@@ -202,3 +202,29 @@ def test_warp2_adaptive_states_and_modes(pkg, oracle, he, czcfg):
     # ψ0 with |l> components lies outside the block structure: refused, not silently wrong
     rc, *_ = he_traj2(he, model, cz.tspan, pkg.tensor((pkg.ket_l + pkg.ket_1) / np.sqrt(2), pkg.ket_1), None, None, None, None, None, None, ode)
     assert rc == pkg._abi.CA_ERR_UNSUPPORTED
+
+
+def test_metropolis_chains_device_source_vs_oracle(pkg, oracle, he):
+    """Metropolis branch (src/atom_sampler.jl:97-120) as independent chains: device source == oracle restatement on the host;
+    one chain reproduces the reference's sequential chain; many chains keep the thermal widths."""
+    he.he_metropolis.restype = C.c_double
+    trap, atom = np.array([1000.0, 1.0, np.pi / 0.852]), np.array([86.9091835, 50.0])
+    for K, harm in ((1, False), (7, False), (64, True)):
+        N = 300
+        out = np.zeros((N, 6))
+        acc = he.he_metropolis(P(trap), P(atom), C.c_longlong(N), C.c_longlong(10), C.c_longlong(200), int(harm), C.c_double(1e-2),
+                               C.c_longlong(K), C.c_ulonglong(11), C.c_uint(0), P(out))
+        o, oacc = oracle.sample_atoms_metropolis_chains(trap, atom, N, freq=10, skip=200, harmonic=harm, n_chains=K, seed=11)
+        assert np.abs(out - o).max() < 1e-12 and abs(acc - oacc) < 1e-12
+        assert 0.05 < acc < 0.95
+    # n_chains = 1 visits the states of the reference's single chain (legacy oracle routine; operation order differs by rounding)
+    one, _ = oracle.sample_atoms_metropolis_chains(trap, atom, 200, freq=10, skip=100, n_chains=1, seed=5)
+    ref, _ = oracle.sample_atoms_metropolis(trap, atom, 200, freq=10, skip=100, harmonic=False, seed=5)
+    assert np.abs(one - ref).max() < 1e-9
+    # many short chains sample the same Boltzmann distribution as the one long reference chain (the true Gaussian trap is
+    # softer than its harmonic approximation: x-width ~10 % above sqrt(T w0²/4U0)); velocities are exactly thermal
+    big, _ = oracle.sample_atoms_metropolis_chains(trap, atom, 20000, freq=10, skip=1000, n_chains=2000, seed=2)
+    long1, _ = oracle.sample_atoms_metropolis(trap, atom, 20000, freq=10, skip=1000, harmonic=False, seed=3)
+    for q in (0, 2, 3):
+        assert abs(big[:, q].std() / long1[:, q].std() - 1) < 0.06, q
+    assert abs(big[:, 3].std() / (0.09118367518929328 * np.sqrt(50 / 86.9091835)) - 1) < 0.04
