@@ -52,7 +52,7 @@ struct DevWarp {
     Coef2* coef;
     double* smp;
 #ifdef CA_TIMERS
-    long long tm[4] = {0, 0, 0, 0}, tl = clock64();   // cycles: 0 noise+sampling, 1 coefficients, 2 stage-7 RHS, 3 everything else
+    long long tm[4] = {0, 0, 0, 0}, tl = 0;   // cycles: 0 noise+sampling, 1 coefficients, 2 stage-7 RHS, 3 everything else
     __device__ __forceinline__ void tick(int i) { const long long c = clock64(); tm[i] += c - tl; tl = c; }
 #endif
     __device__ __forceinline__ void sync() { __syncwarp(); }
@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
     W.lane = lane; W.xm = base; W.xp = base + kXN; W.kb = base + 2 * kXN + lane;
     W.coef = reinterpret_cast<Coef2*>(base + 2 * kXN + kKB * kS2 * 32);
     W.smp = base + 2 * kXN + kKB * kS2 * 32 + kStages2 * 16;
+#ifdef CA_TIMERS
+    W.tl = clock64();
+#endif
     Lane2 L;
     L.init(lane, m);
     double rho0[kS2];
@@ -163,7 +166,6 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         atomicAdd(P.counters + 3, (unsigned long long)tot_att);
         if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
 #ifdef CA_TIMERS
-        for (int i = 0; i < 3; ++i) atomicAdd(P.counters + 5 + i, (unsigned long long)W.tm[i]);
         if (wg == 0) printf("timers (warp 0, cycles): noise %lld coef %lld rhs7 %lld other %lld\n", W.tm[0], W.tm[1], W.tm[2], W.tm[3]);
 #endif
     }
