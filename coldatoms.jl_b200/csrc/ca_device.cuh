@@ -394,13 +394,14 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
 // ---- anchored evaluation of a Gaussian beam (hot path of the adaptive integrator) -----------------------------------
 // A DP5 step needs the coefficient c(t) = (Ω/2) B(r(t)) e^{iφ(t)} at five times inside [t, t+h] for both beams.  φ(t) is
 // piecewise linear on the phase-noise nodes (rydberg_model.jl:166-167; the lane keeps a three-node window) and ln B along
-// the ballistic trajectory is smooth on the scale w0/v >> h.  Every 16 attempts ALL lanes of a warp re-anchor together
+// the ballistic trajectory is smooth on the scale w0/v >> h.  Every kAnchorEvery attempts ALL lanes of a warp re-anchor together
 // (no divergence): one exact exp + sincos at the current time t_a and a quadratic model of ln B from its values at
-// t_a, t_a + H, t_a + 2H (H = 9 h; exact up to the third difference, ~1e-14 for µm-scale beams, guarded through |b2|).
+// t_a, t_a + H, t_a + 2H (2H = (kAnchorEvery + 2) h; exact up to the third difference, ~1e-14 for µm-scale beams, guarded through |b2|).
 // In between
 //     c(t) = c(t_a) exp(δ),  δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)),  τ = t - t_a,
 // costs a degree-4 Taylor exponential per stage time (|δ| < 2e-3 guarded: truncation < 3e-16).  Nothing accumulates:
 // every value hangs off an exactly evaluated anchor; a lane whose step leaves [t_a, t_a + 2H] re-anchors on the spot.
+constexpr int kAnchorEvery = 32;   // attempts between warp-wide re-anchorings (power of two)
 struct BeamGeom { double s, iq, g; };
 CA_HD BeamGeom beam_geom(const DevBeam& b, double rp, double z) {
     const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
@@ -873,19 +874,22 @@ struct Lane1 {
         for (int q = 0; q < 2; ++q) {
             const DevBeam& bm = q == 0 ? m.red : m.blue;
             double* a = ab + (size_t)q * 7 * kstride;
-            double L[3][2];
-#pragma unroll
+            // rolled on purpose: this code runs once per 16 steps and must not evict the step loop from the instruction cache
+            double L0r = 0.0, L0i = 0.0, L1r = 0.0, L1i = 0.0, L2r = 0.0, L2i = 0.0;
+#pragma unroll 1
             for (int i = 0; i < 3; ++i) {
                 const double tn_ = fma((double)i, H, tt);
                 const double X = fma(vx, tn_, x0), Y = fma(vy, tn_, y0), Z = fma(vz, tn_, z0);
                 const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
-                gauss_log(bm, rp, Z, &L[i][0], &L[i][1]);
+                L0r = L1r; L0i = L1i; L1r = L2r; L1i = L2i;
+                gauss_log(bm, rp, Z, &L2r, &L2i);
                 if (i == 0) {
                     double re, im, anc[5];
                     gauss_exact(bm, rp, Z, q == 0 ? pr : pb, &re, &im, anc);
                     a[0] = re; a[kstride] = im;
                 }
             }
+            const double L[3][2] = {{L0r, L0i}, {L1r, L1i}, {L2r, L2i}};
 #pragma unroll
             for (int c = 0; c < 2; ++c) {   // ln B(tt + τ) - ln B(tt) = τ (b1 + τ b2)
                 const double d1 = L[1][c] - L[0][c], d2 = L[2][c] - L[1][c];
@@ -909,7 +913,7 @@ struct Lane1 {
                 if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
                 ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
             }
-            if (refresh || !(tn <= ab[15 * kstride]) || tt0 < ab[14 * kstride]) refresh_anchor(m, tt0, 9.0 * hh);   // 18 steps of headroom for the 16-attempt cadence
+            if (refresh || !(tn <= ab[15 * kstride]) || tt0 < ab[14 * kstride]) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);   // two steps of headroom over the re-anchoring cadence
             ok = ok && win_ok;
             if (ok) {
                 double ca[2][2], b1[2][2], b2[2][2], pa[2];

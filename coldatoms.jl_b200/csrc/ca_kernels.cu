@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             while (true) {
                 const bool need = valid && L.status == 0 && L.tcommit < T;
                 if (!__any_sync(0xffffffffu, need)) break;
-                if (need) L.attempt(m, rt, P.ode, tstop, (n_att & 15) == 0);   // all lanes re-anchor their beam model together
+                if (need) L.attempt(m, rt, P.ode, tstop, (n_att & (kAnchorEvery - 1)) == 0);   // all lanes re-anchor their beam model together
                 ++n_att;
             }
             double v[kNV];
