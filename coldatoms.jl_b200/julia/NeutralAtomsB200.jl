@@ -198,21 +198,32 @@ end
 
 "`release_recapture(tspan, trap_params, atom_params, N; freq, skip, eps, harmonic)` -- src/basic_experiments.jl:72-81"
 function release_recapture(tspan, trap_params, atom_params, N; freq = 10, skip = 1000, eps = 1e-3, harmonic = true)
-    harmonic || error("release_recapture(harmonic=false) needs the Metropolis sampler, which is not on the GPU path")
     probs = zeros(Float64, length(tspan))
     st = CaStats()
-    check(ccall(sym(:ca_release_recapture), Cint,
+    acc = 1.0
+    smp = null()
+    if !harmonic   # Metropolis branch: multi-chain sampler on the device, its samples go to the recapture kernel
+        samples, acc = samples_generate(trap_params, atom_params, N; freq = freq, skip = skip, harmonic = false)
+        smp = reduce(hcat, samples)   # 6 x N column-major = N x 6 row-major
+    end
+    GC.@preserve smp check(ccall(sym(:ca_release_recapture), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Int32,
          Ptr{Float64}, Ptr{UInt8}, Ref{CaStats}),
-        CTX[], Float64.(trap_params), Float64.(atom_params), Float64.(tspan), length(tspan), N, 0, N, eps, next_seed(), null(), 0,
+        CTX[], Float64.(trap_params), Float64.(atom_params), Float64.(tspan), length(tspan), N, 0, N, eps, next_seed(), smp, 0,
         probs, Ptr{UInt8}(C_NULL), st))
-    return probs, 1.0
+    return probs, acc
 end
 
-"`samples_generate(trap_params, atom_params, N; harmonic=true)` -- src/atom_sampler.jl:80-96 -> (Vector{Vector{Float64}}, 1)"
-function samples_generate(trap_params, atom_params, N; freq = 10, skip = 1000, harmonic = true, eps = 1e-2)
-    harmonic || error("samples_generate(harmonic=false) (Metropolis) is not on the GPU path")
+"`samples_generate(trap_params, atom_params, N; freq, skip, harmonic, eps)` -- src/atom_sampler.jl:80-120 -> (Vector{Vector{Float64}}, acc_rate)"
+function samples_generate(trap_params, atom_params, N; freq = 10, skip = 1000, harmonic = true, eps = 1e-2, n_chains = 0)
     out = zeros(Float64, 6, N)
+    if !harmonic   # Metropolis (:97-120) as n_chains independent chains, one per GPU thread (n_chains = 1: the reference chain)
+        acc = Ref{Float64}(0.0)
+        check(ccall(sym(:ca_sample_atoms_metropolis), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Int32, Float64, Int64, UInt64, Int32, Ptr{Float64}, Ref{Float64}),
+            CTX[], Float64.(trap_params), Float64.(atom_params), N, freq, skip, 0, eps, n_chains, next_seed(), 0, out, acc))
+        return [out[:, i] for i in 1:N], acc[]
+    end
     att = Ref{Int64}(0)
     check(ccall(sym(:ca_sample_atoms), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, UInt64, Int32, Float64, Ptr{Float64}, Ref{Int64}),
