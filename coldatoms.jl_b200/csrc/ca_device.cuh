@@ -399,7 +399,8 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
 // t_a, t_a + H, t_a + 2H (2H = (kAnchorEvery + 2) h; exact up to the third difference, ~1e-14 for µm-scale beams, guarded through |b2|).
 // In between
 //     c(t) = c(t_a) exp(δ),  δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)),  τ = t - t_a,
-// costs a degree-4 Taylor exponential per stage time (|δ| < 2e-3 guarded: truncation < 3e-16).  Nothing accumulates:
+// costs three short real series per stage time (e^{Re δ}, cos Im δ, sin Im δ; |Re δ| < 1e-4, |Im δ| < 2e-3 guarded:
+// truncation < 1e-17).  Nothing accumulates:
 // every value hangs off an exactly evaluated anchor; a lane whose step leaves [t_a, t_a + 2H] re-anchors on the spot.
 constexpr int kAnchorEvery = 32;   // attempts between warp-wide re-anchorings (power of two)
 struct BeamGeom { double s, iq, g; };
@@ -934,24 +935,23 @@ struct Lane1 {
                     if (tab) phases_win(m, tt, ph[0], ph[1]);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        // δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)) ;  e^δ = 1 + δ (1 + δ/2 (1 + δ/3 (1 + δ/4)))
+                        // δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)) = dr + i di ;  e^δ = e^{dr} (cos di + i sin di) by short real series
+                        // under the guards |dr| < 1e-4 (dr⁴/24 < 5e-18) and |di| < 2e-3 (di⁶/720, di⁷/5040 < 1e-19)
                         const double dr = tau * fma(tau, b2[q][0], b1[q][0]);
                         const double di = fma(tau, fma(tau, b2[q][1], b1[q][1]), ph[q] - pa[q]);
-                        worst = fmax(worst, fma(dr, dr, di * di));
-                        double er = fma(0.25, dr, 1.0), ei = 0.25 * di;
-                        double t_r = dr * er - di * ei, t_i = dr * ei + di * er;
-                        er = fma(1.0 / 3.0, t_r, 1.0); ei = (1.0 / 3.0) * t_i;
-                        t_r = dr * er - di * ei; t_i = dr * ei + di * er;
-                        er = fma(0.5, t_r, 1.0); ei = 0.5 * t_i;
-                        t_r = dr * er - di * ei; t_i = dr * ei + di * er;
-                        er = 1.0 + t_r; ei = t_i;
+                        worst = fmax(worst, fmax(fabs(dr) * 20.0, fabs(di)));
+                        const double ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
+                        const double d2 = di * di;
+                        const double cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
+                        const double sn = di * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                        const double er = ed * cs, ei = ed * sn;
                         cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
                         cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
                     }
                 }
 #pragma unroll
                 for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
-                done = worst < 4e-6;   // |δ| < 2e-3: the degree-4 series is exact to 3e-16
+                done = worst < 2e-3;
             }
         }
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
