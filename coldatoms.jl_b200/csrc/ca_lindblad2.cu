@@ -40,6 +40,7 @@ struct R2Params {
     double* scratch;         // per warp: [4][n_nodes] phase-noise tables
     double* accum;           // per warp: [nt][2 (ρ, ρ²)][kAccSlots][32]
     unsigned long long* counters;
+    const unsigned* order;   // NULL or [n_traj]: trajectory indices, most expensive first (k_order2_*)
     OdeOpts ode;
     long long n_traj, traj_offset;
     unsigned long long seed;
@@ -93,8 +94,9 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
     double* tab_w = (m.laser_noise && P.nf > 0) ? P.scratch + (size_t)wg * 4 * m.n_nodes : nullptr;
     // Trajectories are handed out dynamically (step counts vary several-fold with the pair distance: V ~ R^-6 sets the step
     // size), first come first served: counters[7] is the next unassigned index.
-    for (long long tr = wg;;) {
-        if (tr >= P.n_traj) break;
+    for (long long slot = wg;;) {
+        if (slot >= P.n_traj) break;
+        const long long tr = P.order ? (long long)P.order[slot] : slot;
         const uint64_t gi = (uint64_t)(P.traj_offset + tr);
         CA_TICK(W, 3);
         // ---- samples (cz_model.jl:111-125): lanes 0,1 draw / load atom 1,2 and add the centre shift
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         if (st.status) worst = max(worst, -st.status);
         unsigned long long nx = 0;
         if (lane == 0) nx = atomicAdd(P.counters + 7, 1ull);
-        tr = Wn + (long long)__shfl_sync(0xffffffffu, nx, 0);
+        slot = Wn + (long long)__shfl_sync(0xffffffffu, nx, 0);
         __syncwarp();
     }
     tot_att = (long long)W.sum((double)tot_att);
@@ -166,9 +168,66 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         atomicAdd(P.counters + 3, (unsigned long long)tot_att);
         if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
 #ifdef CA_TIMERS
-        if (wg == 0) printf("timers (warp 0, cycles): noise %lld coef %lld rhs7 %lld other %lld\n", W.tm[0], W.tm[1], W.tm[2], W.tm[3]);
+        if (wg == 0 || wg == 777) printf("timers (warp %lld, cycles): noise %lld coef %lld rhs7 %lld other %lld | rhs %lld steps %lld\n", wg, W.tm[0], W.tm[1], W.tm[2], W.tm[3], tot_rhs, tot_acc + tot_rej);
 #endif
     }
+}
+
+// ---- longest-first hand-out --------------------------------------------------------------------------------------
+// The step count of a trajectory scales with the blockade shift V = c6/R^6 of ITS atom pair (a pair 30 % closer needs 8x the
+// steps), so a few trajectories are an order of magnitude longer than the mean.  Handing the expensive ones out first keeps
+// the tail of the persistent grid short.  Cost key: 8 log2 of V at the closest approach of the sampled pair, 256 buckets,
+// counting sort (order inside a bucket is arbitrary: the ensemble sums do not depend on it beyond rounding).
+__device__ __forceinline__ int cost_bucket2(const R2Params& P, long long tr) {
+    const DevModel& m = P.model;
+    double s[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const double* src = a == 0 ? P.samples1 : P.samples2;
+        if (src) { for (int q = 0; q < 6; ++q) s[a][q] = src[tr * 6 + q]; }
+        else {
+            SamplerConsts sc;
+            for (int q = 0; q < 6; ++q) sc.sig[q] = m.sig[q];
+            sc.U0 = m.U0; sc.w0 = m.w0; sc.z0 = m.z0; sc.mfac = m.mfac; sc.ecut = m.ecut;
+            sample_atom_literal(sc, P.seed, (uint64_t)(P.traj_offset + tr), (uint32_t)a, s[a]);
+        }
+        for (int q = 0; q < 3; ++q) s[a][q] += m.center[a][q];
+        if (!m.atom_motion) for (int q = 0; q < 6; ++q) s[a][q] = 0.0;
+    }
+    const double tend = P.tspan[P.nt - 1];
+    double r2min = 1e300;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // start, middle and end of the window
+        const double t = 0.5 * k * tend;
+        double d2 = 0.0;
+        for (int q = 0; q < 3; ++q) {
+            const double d = (s[0][q] - s[1][q]) + (m.free_motion ? (s[0][3 + q] - s[1][3 + q]) * t : 0.0);
+            d2 += d * d;
+        }
+        r2min = fmin(r2min, d2);
+    }
+    double c2 = 0.0;
+    for (int q = 0; q < 3; ++q) { const double d = m.center[0][q] - m.center[1][q]; c2 += d * d; }
+    const double ratio = (1e-18 + c2 * c2 * c2) / (1e-18 + r2min * r2min * r2min);   // V / V_nominal
+    const int b = 128 + (int)rint(8.0 * log2(fmax(ratio, 1e-30)));
+    return b < 0 ? 0 : (b > 255 ? 255 : b);
+}
+__global__ void k_order2_hist(const __grid_constant__ R2Params P, unsigned char* __restrict__ bucket, unsigned* __restrict__ hist) {
+    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= P.n_traj) return;
+    const int b = cost_bucket2(P, tr);
+    bucket[tr] = (unsigned char)b;
+    atomicAdd(hist + b, 1u);
+}
+__global__ void k_order2_scan(unsigned* __restrict__ hist) {   // hist -> start offsets, most expensive bucket first
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned run = 0;
+    for (int b = 255; b >= 0; --b) { const unsigned c = hist[b]; hist[b] = run; run += c; }
+}
+__global__ void k_order2_scatter(long long n, const unsigned char* __restrict__ bucket, unsigned* __restrict__ hist, unsigned* __restrict__ order) {
+    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= n) return;
+    order[atomicAdd(hist + bucket[tr], 1u)] = (unsigned)tr;
 }
 
 // K6 for the two-atom path: reduce the per-warp accumulators in a fixed order and combine every real-packed entry with its
@@ -268,6 +327,20 @@ extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* t
     CA_CUDA2(cudaFuncSetAttribute(k_lindblad2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2));
     CA_CUDA2(cudaEventRecord(e1, s));
     int launches = 0;
+    if (n_traj > 2 * (long long)n_warps && n_traj < 0xffffffffLL && P.model.atom_motion) {   // more than two rounds: order longest-first
+        unsigned char* d_bucket = (unsigned char*)ctx_buf(c, 33, (size_t)n_traj);
+        unsigned* d_hist = (unsigned*)ctx_buf(c, 34, 256 * sizeof(unsigned));
+        unsigned* d_order = (unsigned*)ctx_buf(c, 35, sizeof(unsigned) * (size_t)n_traj);
+        if (!d_bucket || !d_hist || !d_order) return CA_ERR_NOMEM;
+        CA_CUDA2(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned), s));
+        const unsigned nb = (unsigned)((n_traj + 127) / 128);
+        k_order2_hist<<<nb, 128, 0, s>>>(P, d_bucket, d_hist);
+        k_order2_scan<<<1, 32, 0, s>>>(d_hist);
+        k_order2_scatter<<<nb, 128, 0, s>>>(n_traj, d_bucket, d_hist, d_order);
+        CA_CUDA2(cudaGetLastError());
+        launches += 3;
+        P.order = d_order;
+    }
     if (n_traj > 0) {
         k_lindblad2<<<grid, kWarps2 * 32, kSmem2, s>>>(P);
         CA_CUDA2(cudaGetLastError());
