@@ -399,8 +399,8 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
 // t_a, t_a + H, t_a + 2H (2H = (kAnchorEvery + 2) h; exact up to the third difference, ~1e-14 for µm-scale beams, guarded through |b2|).
 // In between
 //     c(t) = c(t_a) exp(δ),  δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)),  τ = t - t_a,
-// costs three short real series per stage time (e^{Re δ}, cos Im δ, sin Im δ; |Re δ| < 1e-4, |Im δ| < 2e-3 guarded:
-// truncation < 1e-17).  Nothing accumulates:
+// costs three short real series per stage time (e^{Re δ}, cos Im δ, sin Im δ; |Re δ| < 3e-4, |Im δ| < 6e-3 guarded:
+// truncation < 4e-16).  Nothing accumulates:
 // every value hangs off an exactly evaluated anchor; a lane whose step leaves [t_a, t_a + 2H] re-anchors on the spot.
 constexpr int kAnchorEvery = 32;   // attempts between warp-wide re-anchorings (power of two)
 struct BeamGeom { double s, iq, g; };
@@ -936,10 +936,10 @@ struct Lane1 {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         // δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)) = dr + i di ;  e^δ = e^{dr} (cos di + i sin di) by short real series
-                        // under the guards |dr| < 1e-4 (dr⁴/24 < 5e-18) and |di| < 2e-3 (di⁶/720, di⁷/5040 < 1e-19)
+                        // under the guards |dr| < 3e-4 (dr⁴/24 < 4e-16) and |di| < 6e-3 (di⁶/720 < 7e-17)
                         const double dr = tau * fma(tau, b2[q][0], b1[q][0]);
                         const double di = fma(tau, fma(tau, b2[q][1], b1[q][1]), ph[q] - pa[q]);
-                        worst = fmax(worst, fmax(fabs(dr) * 20.0, fabs(di)));
+                        worst = fma(di, di, fma(400.0 * dr, dr, worst));   // Σ (di² + (20 dr)²) >= max: one conservative guard per step
                         const double ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
                         const double d2 = di * di;
                         const double cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
@@ -951,7 +951,7 @@ struct Lane1 {
                 }
 #pragma unroll
                 for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
-                done = worst < 2e-3;
+                done = worst < 3.6e-5;   // every |di| < 6e-3 (cos, sin series exact to 7e-17), every |dr| < 3e-4 (dr⁴/24 < 4e-16)
             }
         }
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
