@@ -777,7 +777,7 @@ struct Lane1 {
     double y[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
     long long iters;
-    int n_rhs, n_acc, n_rej;
+    int n_rhs, n_acc, n_rej, n_exact;     // n_exact: steps whose coefficients took the exact (generic / guard-failed) path
     int status;
 
     CA_HD double* kptr(int j) const {     // j = 1..7
@@ -955,6 +955,7 @@ struct Lane1 {
             }
         }
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
+            ++n_exact;
 #pragma unroll 1
             for (int n = 0; n < 5; ++n) {
                 Coef c;
@@ -1009,7 +1010,7 @@ struct Lane1 {
             y[19] = m.rho0[5 + 18]; y[20] = -m.rho0[5 + 19];
         }
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
-        t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; status = 0;
+        t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
         lnq_old = log(1e-4);
         double k1[NS];
         Coef cf0;

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (T / 32) + warp;
     const long long W = (long long)gridDim.x * (T / 32);
-    long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0;
+    long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0, tot_exact = 0;
     long long cyc_noise = 0, cyc_all = -clock64();
     int worst = 0;
     // All warps of a CTA walk the group list in lock-step (one barrier per 32-trajectory group): measured, the warps
@@ -161,11 +161,12 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             atomicAdd(acc_pt + (size_t)j * kNV + lane, mine0);
             if (lane < kNV - 32) atomicAdd(acc_pt + (size_t)j * kNV + 32 + lane, mine1);
         }
-        if (valid) { tot_rhs += L.n_rhs; tot_acc += L.n_acc; tot_rej += L.n_rej; if (L.status) worst = max(worst, -L.status); }
+        if (valid) { tot_rhs += L.n_rhs; tot_acc += L.n_acc; tot_rej += L.n_rej; tot_exact += L.n_exact; if (L.status) worst = max(worst, -L.status); }
     }
     // ---- statistics
     tot_rhs = (long long)warp_sum((double)tot_rhs); tot_acc = (long long)warp_sum((double)tot_acc);
     tot_rej = (long long)warp_sum((double)tot_rej); tot_att = (long long)warp_sum((double)tot_att);
+    tot_exact = (long long)warp_sum((double)tot_exact);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
     if (lane == 0) {
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
         if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
         atomicAdd(P.counters + 5, (unsigned long long)cyc_noise);               // warp-cycles in phase-noise generation
         atomicAdd(P.counters + 6, (unsigned long long)(cyc_all + clock64()));   // warp-cycles in the whole kernel
+        atomicAdd(P.counters + 7, (unsigned long long)tot_exact);               // steps on the exact coefficient path
     }
 }
 
@@ -516,6 +518,7 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     }
     (void)out_mats;
     int status = hc[4] ? -(int)hc[4] : 0;
+    if (std::getenv("CA_DEBUG_STATS")) std::fprintf(stderr, "k_lindblad1: steps %llu, exact-coefficient steps %llu\n", hc[1] + hc[2], hc[7]);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->n_traj = n_all; stats->n_rhs = (int64_t)hc[0]; stats->n_accept = (int64_t)hc[1]; stats->n_reject = (int64_t)hc[2];
