@@ -31,6 +31,10 @@ import __graft_entry__ as graft  # noqa: E402
 F_RHS_1 = 340.0    # canonical flop per one-atom RHS (frozen)
 F_RHS_2 = 7500.0   # canonical flop per two-atom RHS
 F_NOISE_PER = 3.0  # flop per (node, frequency) actually executed by the Reinsch recurrence (SURVEY counts 8)
+# DRAM bytes per trajectory of the dominant kernel from the committed `ncu --set full` captures (dram__bytes_read.sum +
+# dram__bytes_write.sum divided by the trajectories of the captured launch; profiles/r1/k_lindblad{1,2}_ncu_summary.txt).
+# K3: the per-warp phase-noise tables (2 x 1001 nodes x 8 B written and read once) are the only real traffic.
+NCU_DRAM_BYTES_PER_TRAJ = {1: (760.0e6 + 772.5e6) / 37888, 2: (12.3e6 + 13.5e6) / 2368}
 
 
 def workload(pkg, name, n):
@@ -279,7 +283,9 @@ def main():
                        "l2": "flushed between steps (256 MiB write); the path is FP64-compute-bound with KB-sized inputs",
                        "parallelism": f"trajectory shards x{world}, one NCCL all-reduce of the rho sums"},
             "roofline": {"bound": "fp64", "achieved": ach, "peak": max(peak_tf, peak_tf2), "unit": "TFLOP/s",
-                         "frac": ach / max(peak_tf, peak_tf2), "traffic": None,
+                         "frac": ach / max(peak_tf, peak_tf2),
+                         "traffic": NCU_DRAM_BYTES_PER_TRAJ[natoms] * n_per,
+                         "traffic_note": "bytes per launch = ncu dram bytes per trajectory (captured launch, profiles/r1) x trajectories of this launch",
                          "kernel": "k_lindblad1" if natoms == 1 else "k_lindblad2", "kernel_ms": st["kernel_ms"],
                          "flop_model": f"n_rhs*{F_RHS_1 if natoms == 1 else F_RHS_2:.0f} + noise {F_NOISE_PER}/(summed node,freq) + obs (SURVEY 8d canonical, DESIGN.md)",
                          "n_rhs_per_traj": st["n_rhs"] / max(1, n_per),
