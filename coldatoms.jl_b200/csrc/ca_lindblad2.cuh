@@ -13,11 +13,13 @@
 //
 // RHS: with G = Hρ (column B of G only needs column B of ρ because H acts on the row index),
 //     dρ = -i (G - G†) + dissipator,      H = H1 ⊗ 1 + 1 ⊗ H2 + V |rr><rr|   (cz_model.jl:31-65).
-// A lane rebuilds the complex entries of its half column from its own reals and the transposed reals (one exchange
-// through shared memory, conflict-free: rows are padded to 18 doubles), multiplies by H with the SAME register-resident
-// coefficients in every lane (H1 couples rows inside a group of four, H2 couples the two groups and the sibling lane),
-// then needs exactly one real of G_BA from the transposed owner (second exchange):
-//     dM[A][B] = (Im G_AB - Re G_AB) + (Im G_BA + Re G_BA) - (γ_A + γ_B)/2 M[A][B] + feeding.   No gather tables, no per-lane
+// A lane fetches the transposed reals M[B][A'] of its half column (one exchange through shared memory, conflict-free: rows
+// are padded to 18 doubles) and applies H with the SAME register-resident coefficients in every lane (H1 couples rows inside
+// a group of four, H2 couples the two groups and the sibling lane).  The complex product is never formed: a coupling
+// c = H_AA' maps the source reals (m, mt) = (M[A'][B], M[B][A']) onto S = Im G + Re G += Re c m + Im c mt and
+// D = Im G - Re G += Im c m - Re c mt (four FMAs), and the lane needs exactly one real, S_BA, from the transposed owner
+// (second exchange):
+//     dM[A][B] = D_AB + S_BA - (γ_A + γ_B)/2 M[A][B] + feeding.   No gather tables, no per-lane
 // coefficient loads; the only irregular accesses are the few population-feeding terms of the jump operators
 // (JumpOperatorsTwo, cz_model.jl:2-9).
 #pragma once
@@ -35,7 +37,7 @@ constexpr int kAccSlots = 10;      // accumulator slots per lane: 9 + ρ_ll,ll (
 constexpr int kWarpDoubles2 = 2 * kXN + kKB * kS2 * 32 + kStages2 * 16 + 12;
 
 // Hamiltonian coefficients at one stage time: Ωr/2 (σ1p), Ωb/2 (σpr) of both atoms (with phase noise and the phase jump),
-// detunings (H_pp = -dp, H_rr = -dr) and the blockade shift V -- all stored HALVED (rhs2 multiplies them with 2ρ).
+// detunings (H_pp = -dp, H_rr = -dr) and the blockade shift V.
 struct Coef2 { double ar1, ai1, br1, bi1, ar2, ai2, br2, bi2, dp1, dr1, dp2, dr2, V, pad0, pad1, pad2; };
 
 CA_HD int idx5(int A) { return (A & 3) + 5 * (A >> 2); }   // 16-block index a1 + 4 a2 -> reference index a1 + 5 a2
@@ -149,7 +151,19 @@ CA_HD void ld2(const double* p, double& a, double& b) {
 // TWICE the complex entry of a row from its own real `mo` and the transposed real `mt`
 CA_HD void cplx2(double mo, double mt, double& re, double& im) { re = mo + mt; im = mo - mt; }
 
-// dM/dt of this lane's nine reals; `cf` holds HALF the Hamiltonian entries (the lane works with x = 2ρ).
+// One complex coupling c = cr + i ci acting on a source row given by its two reals (m = M[A'][B], mt = M[B][A']):
+// with G = H ρ and 2ρ_A'B = (m + mt) + i (m - mt),   S = Im G + Re G  gets  cr m + ci mt,   D = Im G - Re G  gets  ci m - cr mt.
+#define CA_MMAC(S_, D_, cr, ci, m_, mt_)         \
+    do {                                         \
+        S_ = fma((cr), (m_), S_);                \
+        S_ = fma((ci), (mt_), S_);               \
+        D_ = fma((ci), (m_), D_);                \
+        D_ = fma(-(cr), (mt_), D_);              \
+    } while (0)
+
+// dM/dt of this lane's nine reals.  The complex product G = Hρ is never formed: in the M representation a coupling
+// H_AA' = c maps the source reals (M[A'][B], M[B][A']) straight onto S = Im G + Re G (published for the transposed owner)
+// and D = Im G - Re G (kept), four FMAs per coupling:  dM[A][B] = D_AB + S_BA - (γ_A + γ_B)/2 M[A][B] + feeding.
 // tp[j] returns the transposed partner value: |ρ_AB|² = (u² + tp²)/2 (also on the diagonal, where tp = u).
 template <class W>
 CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const double (&u)[kS2], double (&du)[kS2], double (&tp)[kS2]) {
@@ -160,37 +174,34 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
     for (int j = 0; j < 8; ++j) xm[L.o_pub + j * kRS] = u[j];
     xm[kXL + L.lane] = u[8];
     w.sync();
-    // ---- B: x = 2ρ on this half column, G = (H/2) x
-    double xr[8], xi[8], sr[4], si[4];
+    // ---- B: transposed reals of the own half column and of the sibling rows the 1 <-> p coupling of atom 2 needs
+    double sm_[4], st[4];
     {
 #pragma unroll
         for (int q = 0; q < 4; ++q) ld2(xm + L.o_row + 2 * q, tp[2 * q], tp[2 * q + 1]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cplx2(u[j], tp[j], xr[j], xi[j]);
-        double st[4];
         ld2(xm + L.o_sibrow, st[0], st[1]);
         ld2(xm + L.o_sibrow + 2, st[2], st[3]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cplx2(xm[L.o_sib + i * kRS], st[i], sr[i], si[i]);
+        for (int i = 0; i < 4; ++i) sm_[i] = xm[L.o_sib + i * kRS];
     }
-    double Gr[8], Gi[8];
+    double S[8], D[8];
     {
         const double e2lo = L.h ? -cf.dr2 : 0.0, e2hi = L.h ? -cf.dp2 : 0.0, vrr = L.h ? cf.V : 0.0;
         const double e1[4] = {0.0, 0.0, -cf.dr1, -cf.dp1};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j) {   // real diagonal of H: S += e m, D -= e mt
             double e = e1[j & 3] + (j < 4 ? e2lo : e2hi);
             if (j == 2) e += vrr;   // |rr><rr| (get_V, cz_model.jl:12-17,63)
-            Gr[j] = e * xr[j]; Gi[j] = e * xi[j];
+            S[j] = e * u[j]; D[j] = -e * tp[j];
         }
         // H1 ⊗ 1: rows (1, r, p) of each group of four
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             const int j0 = 4 * g;
-            CA_CMAC(Gr[j0 + 1], Gi[j0 + 1], cf.ar1, cf.ai1, xr[j0 + 3], xi[j0 + 3]);     // H[1,p] = Ωr/2
-            CA_CMAC(Gr[j0 + 2], Gi[j0 + 2], cf.br1, -cf.bi1, xr[j0 + 3], xi[j0 + 3]);    // H[r,p] = (Ωb/2)*
-            CA_CMAC(Gr[j0 + 3], Gi[j0 + 3], cf.ar1, -cf.ai1, xr[j0 + 1], xi[j0 + 1]);    // H[p,1] = (Ωr/2)*
-            CA_CMAC(Gr[j0 + 3], Gi[j0 + 3], cf.br1, cf.bi1, xr[j0 + 2], xi[j0 + 2]);     // H[p,r] = Ωb/2
+            CA_MMAC(S[j0 + 1], D[j0 + 1], cf.ar1, cf.ai1, u[j0 + 3], tp[j0 + 3]);     // H[1,p] = Ωr/2
+            CA_MMAC(S[j0 + 2], D[j0 + 2], cf.br1, -cf.bi1, u[j0 + 3], tp[j0 + 3]);    // H[r,p] = (Ωb/2)*
+            CA_MMAC(S[j0 + 3], D[j0 + 3], cf.ar1, -cf.ai1, u[j0 + 1], tp[j0 + 1]);    // H[p,1] = (Ωr/2)*
+            CA_MMAC(S[j0 + 3], D[j0 + 3], cf.br1, cf.bi1, u[j0 + 2], tp[j0 + 2]);     // H[p,r] = Ωb/2
         }
         // 1 ⊗ H2: h = 0 holds a2 = (0, 1), h = 1 holds a2 = (r, p); the 1 <-> p coupling crosses to the sibling lane
         const double k01r = L.h ? cf.br2 : 0.0, k01i = L.h ? -cf.bi2 : 0.0;   // row r <- (Ωb/2)* p
@@ -198,19 +209,15 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
         const double ksr = cf.ar2, ksi = L.h ? -cf.ai2 : cf.ai2;              // row p <- (Ωr/2)* 1 ; row 1 <- Ωr/2 p
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            CA_CMAC(Gr[a], Gi[a], k01r, k01i, xr[4 + a], xi[4 + a]);
-            CA_CMAC(Gr[4 + a], Gi[4 + a], ksr, ksi, sr[a], si[a]);
-            CA_CMAC(Gr[4 + a], Gi[4 + a], k10r, k10i, xr[a], xi[a]);
+            CA_MMAC(S[a], D[a], k01r, k01i, u[4 + a], tp[4 + a]);
+            CA_MMAC(S[4 + a], D[4 + a], ksr, ksi, sm_[a], st[a]);
+            CA_MMAC(S[4 + a], D[4 + a], k10r, k10i, u[a], tp[a]);
         }
     }
-    // l-block element (a8, b): G = H_s L with H_s the Hamiltonian of the surviving atom
-    double G8r, G8i;
+    // l-block element (a8, b): H_s L with H_s the Hamiltonian of the surviving atom
+    double S8, D8;
     {
-        double x8r, x8i, n1r, n1i, n2r, n2i;
         tp[8] = xm[L.o8_t];
-        cplx2(u[8], tp[8], x8r, x8i);
-        cplx2(xm[L.o8_n1], xm[L.o8_n1t], n1r, n1i);
-        cplx2(xm[L.o8_n2], xm[L.o8_n2t], n2r, n2i);
         const double alr = L.blk ? cf.ar1 : cf.ar2, ali = L.blk ? cf.ai1 : cf.ai2, ber = L.blk ? cf.br1 : cf.br2, bei = L.blk ? cf.bi1 : cf.bi2;
         const double dpx = L.blk ? cf.dp1 : cf.dp2, drx = L.blk ? cf.dr1 : cf.dr2;
         // a = 1: Ωr/2 L_p ; a = r: (Ωb/2)* L_p - dr L_r ; a = p: (Ωr/2)* L_1 + Ωb/2 L_r - dp L_p
@@ -218,19 +225,19 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
         const double c1i = L.a8 == 0 ? 0.0 : (L.a8 == 1 ? ali : (L.a8 == 2 ? -bei : -ali));
         const double c2r = L.a8 == 3 ? ber : 0.0, c2i = L.a8 == 3 ? bei : 0.0;
         const double e = L.a8 == 2 ? -drx : (L.a8 == 3 ? -dpx : 0.0);
-        G8r = e * x8r; G8i = e * x8i;
-        CA_CMAC(G8r, G8i, c1r, c1i, n1r, n1i);
-        CA_CMAC(G8r, G8i, c2r, c2i, n2r, n2i);
+        S8 = e * u[8]; D8 = -e * tp[8];
+        CA_MMAC(S8, D8, c1r, c1i, xm[L.o8_n1], xm[L.o8_n1t]);
+        CA_MMAC(S8, D8, c2r, c2i, xm[L.o8_n2], xm[L.o8_n2t]);
     }
-    // publish Im G + Re G for the transposed owner, keep Im G - Re G; decay and population feeding
+    // publish S for the transposed owner, keep D; decay and population feeding
     {
         const double ga[4] = {0.0, 0.0, 0.5 * m.Gr, 0.5 * (m.G0 + m.G1 + m.Gl)};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            xp[L.o_pub + j * kRS] = Gi[j] + Gr[j];
-            du[j] = fma(-((j < 4 ? L.dlo : L.dhi) + ga[j & 3]), u[j], Gi[j] - Gr[j]);
+            xp[L.o_pub + j * kRS] = S[j];
+            du[j] = fma(-((j < 4 ? L.dlo : L.dhi) + ga[j & 3]), u[j], D[j]);
         }
-        xp[kXL + L.lane] = G8i + G8r;
+        xp[kXL + L.lane] = S8;
         const double vlo = xm[L.o_f1lo], vhi = xm[L.o_f1hi];
         du[0] = fma(L.w0, vlo, du[0]); du[1] = fma(L.w1, vlo, du[1]);
         du[4] = fma(L.w0, vhi, du[4]); du[5] = fma(L.w1, vhi, du[5]);
@@ -239,13 +246,13 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
             const double v = xm[L.o_f2 + a * kRS];
             du[a] = fma(L.u0, v, du[a]); du[4 + a] = fma(L.u1, v, du[4 + a]);
         }
-        double d8 = fma(-L.dec8, u[8], G8i - G8r);
+        double d8 = fma(-L.dec8, u[8], D8);
         d8 = fma(m.Gl, xm[L.o8_fp], d8);
         d8 = fma(m.Gr, xm[L.o8_fr], d8);
         du[8] = fma(L.w8, xm[L.o8_pp], d8);
     }
     w.sync();
-    // ---- C: add the transposed owner's half of -i (G - G†)
+    // ---- C: add the transposed owner's S
     {
         double q[8];
 #pragma unroll
@@ -298,17 +305,17 @@ CA_HD void eval_coefficients2(W& w, const DevModel& m, const double* tab, double
                 const double rp = sqrt_d(fmax(pos[a][0] * pos[a][0] + pos[a][1] * pos[a][1], 1e-300));
                 gauss_exact(bm, rp, pos[a][2], ph, &re, &im, anc);
             } else beam_half_omega(bm, pos[a][0], pos[a][1], pos[a][2], ph, &re, &im);
-            o[2 * q] = 0.5 * re; o[2 * q + 1] = 0.5 * im;
+            o[2 * q] = re; o[2 * q + 1] = im;
         } else {
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const double Dd = m.aDx * vel[a][0] + m.aDz * vel[a][1], dd = m.bDx * vel[a][0] + m.bDz * vel[a][1];
-                o[8 + 2 * a] = 0.5 * (m.Delta0 - m.dsign * Dd);      // dp/2: H_pp = -dp
-                o[9 + 2 * a] = 0.5 * (m.delta0 - m.dsign * dd);      // dr/2: H_rr = -dr
+                o[8 + 2 * a] = m.Delta0 - m.dsign * Dd;      // dp: H_pp = -dp
+                o[9 + 2 * a] = m.delta0 - m.dsign * dd;      // dr: H_rr = -dr
             }
             const double dx = pos[0][0] - pos[1][0], dy = pos[0][1] - pos[1][1], dz = pos[0][2] - pos[1][2];
             const double r2 = dx * dx + dy * dy + dz * dz;
-            o[12] = 0.5 * m.c6 * rcp_d(1e-18 + r2 * r2 * r2);      // V/2, get_V: cz_model.jl:12-17
+            o[12] = m.c6 * rcp_d(1e-18 + r2 * r2 * r2);      // get_V: cz_model.jl:12-17
         }
     }
     w.sync();
