@@ -750,6 +750,37 @@ struct OdeOpts {
     int adaptive, dense;
 };
 
+// PI step-size controller of OrdinaryDiffEq's DP5 (β1 = 0.17, β2 = 0.04, γ = 0.9, q in [1/qmax, 1/qmin] = [0.1, 5], qoldinit = 1e-4):
+// accept: q = EEst^β1 qold^-β2 / γ, dt <- h/q, qold <- max(EEst, 1e-4);  reject: dt <- h / min(1/qmin, EEst^β1/γ).
+// The accept/reject DECISION (EEst² <= 1) is taken in double by the caller.  The fractional powers only size the next step, so
+// they are evaluated in single precision through log2/exp2 (two MUFU ops instead of a ~60-deep double log/exp chain on the
+// critical path of every step; relative error ~1e-7 in dt).  DiffEqBase itself evaluates them with an approximate `fastpower`.
+struct StepCtrl {
+    float l2q_old;   // log2(qold)
+    CA_HD void reset() { l2q_old = -13.287712f; }   // log2(1e-4)
+    static CA_HD float lg2(float x) {
+#if defined(__CUDA_ARCH__)
+        return __log2f(x);
+#else
+        return log2f(x);
+#endif
+    }
+    // returns the factor dt/h
+    CA_HD double accept(double EEst2) {
+        if (EEst2 == 0.0) { reset(); return 10.0; }
+        const float l2E = 0.5f * lg2((float)EEst2);                                   // log2(EEst); -inf / +inf saturate in the clamp
+        float l2q = fmaf(0.17f, l2E, fmaf(-0.04f, l2q_old, 0.15200309f));             // - log2(0.9)
+        l2q = fmaxf(-3.3219281f, fminf(2.3219281f, l2q));                             // q in [0.1, 5]
+        l2q_old = fmaxf(l2E, -13.287712f);
+        return (double)exp2f(-l2q);
+    }
+    CA_HD double reject(double EEst2) const {
+        const float l2E = 0.5f * lg2((float)EEst2);
+        const float l2q = fminf(2.3219281f, fmaf(0.17f, l2E, 0.15200309f));
+        return (double)exp2f(-l2q);
+    }
+};
+
 // Per-trajectory integrator state. NS = 9 (+6 per spectator row).
 //
 // Storage plan (from the first ncu profile: at 255 registers/thread only 8 warps/SM were resident and spill reloads
@@ -773,7 +804,8 @@ struct Lane1 {
     double* ab;                           // per beam q: ab[(q*7 + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a); ab[14] = t_a, ab[15] = t_a + 2H
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
     bool win_ok;                          // the anchor's quadratic model of ln B passed its guard
-    double t, h, dt, lnq_old, tcommit;
+    double t, h, dt, tcommit;
+    StepCtrl ctrl;
     double y[NS], un[NS];
     double P[2], Pn[2], g1[2], g7[2], SD[2];
     long long iters;
@@ -1011,7 +1043,7 @@ struct Lane1 {
         }
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
         t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
-        lnq_old = log(1e-4);
+        ctrl.reset();
         double k1[NS];
         Coef cf0;
         coefficients(m, t, cf0);
@@ -1154,20 +1186,12 @@ struct Lane1 {
             for (int i = 3; i < NS; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
             double EEst2 = s * (1.0 / 25.0);
             if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; return; }
-            // PI controller: q = EEst^β1 / qold^β2 / γ clipped to [1/qmax, 1/qmin]; β1 = 0.17, β2 = 0.04
-            const double beta1 = 0.17, beta2 = 0.04, gam = 0.9, qmin = 0.2, qmax = 10.0;
-            const double ln_qoldinit = -9.210340371976182;  // log(1e-4)
-            double q, lnE = 0.0;
-            if (EEst2 == 0.0) q = 1.0 / qmax;
-            else { lnE = 0.5 * log(EEst2); q = exp_d(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
             if (EEst2 <= 1.0) {
-                lnq_old = (EEst2 == 0.0) ? ln_qoldinit : fmax(lnE, ln_qoldinit);
-                double prop = hh * rcp_d(q);
+                const double prop = hh * ctrl.accept(EEst2);
                 dt = clipped ? fmax(dt, prop) : prop;
             } else {
                 accept = false;
-                double q11 = exp_d(beta1 * lnE);
-                dt = hh * rcp_d(fmin(1.0 / qmin, q11 * (1.0 / gam)));
+                dt = hh * ctrl.reject(EEst2);
                 n_rej++;
                 if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; return; }
             }

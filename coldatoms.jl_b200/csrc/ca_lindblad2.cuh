@@ -359,7 +359,9 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
 #pragma unroll
     for (int s = 0; s < kS2; ++s) { y[s] = rho0[s]; un[s] = y[s]; }
     const double t0 = tspan[0], tend = tspan[nt - 1];
-    double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0, lnq_old = log(1e-4);
+    double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0;
+    StepCtrl ctrl;
+    ctrl.reset();
     long long iters = 0;
     int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0;
     auto diag_sum = [&](const double (&v)[kS2]) {
@@ -483,17 +485,12 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 }
                 const double EEst2 = sacc * (1.0 / 625.0);
                 if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; break; }
-                const double beta1 = 0.17, beta2 = 0.04, gam = 0.9, qmin = 0.2, qmax = 10.0, ln_qoldinit = -9.210340371976182;
-                double q, lnE = 0.0;
-                if (EEst2 == 0.0) q = 1.0 / qmax;
-                else { lnE = 0.5 * log(EEst2); q = exp_d(beta1 * lnE - beta2 * lnq_old) * (1.0 / gam); q = fmax(1.0 / qmax, fmin(1.0 / qmin, q)); }
                 if (EEst2 <= 1.0) {
-                    lnq_old = (EEst2 == 0.0) ? ln_qoldinit : fmax(lnE, ln_qoldinit);
-                    const double prop = hh * rcp_d(q);
+                    const double prop = hh * ctrl.accept(EEst2);
                     dt = clipped ? fmax(dt, prop) : prop;
                 } else {
                     accept = false;
-                    dt = hh * rcp_d(fmin(1.0 / qmin, exp_d(beta1 * lnE) * (1.0 / gam)));
+                    dt = hh * ctrl.reject(EEst2);
                     n_rej++;
                     if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; break; }
                 }

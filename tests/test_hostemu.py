@@ -186,8 +186,10 @@ def test_warp2_adaptive_states_and_modes(pkg, oracle, he, czcfg):
         rc, r, r2, st = he_traj2(he, model, cz.tspan, cz.ψ0, None, None, None, cz.f, kw["amp_red"], kw["amp_blue"], ode, seed=17, gi=5)
         assert rc == 0
         o, o2, ost = oracle.rydberg2_run(model, cz.tspan, cz.ψ0, 1, seed=17, traj_offset=5, ode=ode, **kw)
+        # same accept/reject decisions (taken in double); the controller's fractional powers are single precision on the device
+        # path, so step SIZES agree to ~1e-7 and the solutions to ~1e-9 (requirement: 1e-6)
         assert st == [ost["n_rhs"], ost["n_accept"], ost["n_reject"]]
-        assert np.abs(r - o).max() < 1e-10 and np.abs(r2 - o2).max() < 1e-10
+        assert np.abs(r - o).max() < 1e-8 and np.abs(r2 - o2).max() < 1e-8
     # other initial states, |ρ_ij|² second moment, a decay channel switched off, no noise
     cz.laser_noise = False
     cz.spontaneous_decay_rydberg = False
