@@ -321,10 +321,11 @@ CA_HD void eval_coefficients2(W& w, const DevModel& m, const double* tab, double
     w.sync();
 }
 
-// Later uses of k3 / k5 read the shared-memory copy (they are stored there for the dense output anyway) instead of
-// pinning 18 registers each across three / two RHS evaluations.
+// The kernel is bound by shared-memory wavefronts, so k3 and k5 stay in registers for their later uses (switches kept for
+// experiments); their shared-memory copies (and k6's) exist only for Hairer's dense output and are written only by a step that
+// overshoots the next output time.
 #ifndef CA_K3_SMEM
-#define CA_K3_SMEM 1
+#define CA_K3_SMEM 0
 #endif
 #ifndef CA_K5_SMEM
 #define CA_K5_SMEM 0
@@ -425,6 +426,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             const double tn = clipped ? tstop : t + hh;
             CA_TICK(w, 3);
             eval_coefficients2(w, m, tab, t, hh, tn);
+            const bool for_dense = tn > T || CA_K3_SMEM || CA_K5_SMEM;   // this step may be interpolated at T (warp-uniform)
             CA_TICK(w, 1);
             double k2[kS2], k3[kS2], k5[kS2], kk[kS2], er[kS2], dum[kS2];
 #pragma unroll
@@ -435,7 +437,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             rhs2(w, L, m, w.coef[1], ut, k3, dum);
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
-                kb[(KB_3 * kS2 + s) * 32] = k3[s];
+                if (for_dense) kb[(KB_3 * kS2 + s) * 32] = k3[s];
                 ut[s] = fma(hh, fma(MC.a43, k3[s], fma(MC.a42, k2[s], MC.a41 * k1[s])), y[s]);
             }
             rhs2(w, L, m, w.coef[2], ut, kk, dum);   // k4
@@ -447,14 +449,14 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             rhs2(w, L, m, w.coef[3], ut, k5, dum);
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
-                kb[(KB_5 * kS2 + s) * 32] = k5[s];
+                if (for_dense) kb[(KB_5 * kS2 + s) * 32] = k5[s];
                 const double k4 = kb[(KB_4 * kS2 + s) * 32];
                 ut[s] = fma(hh, fma(MC.a65, k5[s], fma(MC.a64, k4, fma(MC.a63, CA_K3L(s), fma(MC.a62, k2[s], MC.a61 * k1[s])))), y[s]);
             }
             rhs2(w, L, m, w.coef[4], ut, kk, dum);   // k6
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
-                kb[(KB_6 * kS2 + s) * 32] = kk[s];
+                if (for_dense) kb[(KB_6 * kS2 + s) * 32] = kk[s];
                 const double k4 = kb[(KB_4 * kS2 + s) * 32];
                 const double k3v = CA_K3L(s), k5v = CA_K5L(s);
                 un[s] = fma(hh, fma(MC.b6, kk[s], fma(MC.b5, k5v, fma(MC.b4, k4, fma(MC.b3, k3v, MC.b1 * k1[s])))), y[s]);
