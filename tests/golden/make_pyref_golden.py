@@ -1,0 +1,53 @@
+"""Generates tests/golden/pyref_trajectories.npz: converged single-trajectory solutions (scipy DOP853, rtol 1e-12) of the
+reference's one-atom and two-atom models from the INDEPENDENT numpy/scipy restatement tests/pyref.py (dense operators and
+closures the way the Julia source reads), together with the host-side samples and phase draws that produced them.
+The C oracle (CPU suite) and the CUDA path (GPU suite) are both checked against these committed numbers.
+
+    python tests/golden/make_pyref_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+import __graft_entry__ as g  # noqa: E402
+import pyref  # noqa: E402
+
+pkg = g.load_package()
+rng = np.random.default_rng(20261020)
+cfg, cz = pkg.get_default_configs()
+
+# one atom: R1 model on a short window, free and trapped motion, |1> and a superposition with |0>
+cfg.laser_noise = True
+cfg.tspan = np.linspace(0.0, 0.1, 6)
+σ = np.array([0.158, 0.158, 0.864, 0.0978, 0.0978, 0.0978])   # thermal widths of the default trap
+r1_samples = rng.normal(size=(3, 6)) * σ * 0.7
+r1_phases = rng.uniform(0, 2 * np.pi, (2, 3, len(cfg.f)))
+r1_rho = []
+cases = [(True, pkg.ket_1), (False, pkg.ket_1), (True, (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2))]
+for i, (free, psi) in enumerate(cases):
+    c = cfg.copy()
+    c.free_motion = free
+    c.ψ0 = psi
+    ref, _ = pyref.one_atom_traj(c, r1_samples[i], r1_phases[0, i], r1_phases[1, i])
+    r1_rho.append(ref)
+
+# two atoms: CZ model with the phase jump inside the window
+cz.laser_noise = True
+cz.tspan = np.array([0.0, 0.004, 0.008])
+cz.ξ = 1.3
+z1_s1 = rng.normal(size=(2, 6)) * σ * 0.7
+z1_s2 = rng.normal(size=(2, 6)) * σ * 0.7
+z1_phases = rng.uniform(0, 2 * np.pi, (4, 2, len(cz.f)))
+z1_rho = []
+for i in range(2):
+    ref, _ = pyref.two_atom_traj(cz, z1_s1[i], z1_s2[i], [z1_phases[q, i] for q in range(4)], rtol=1e-11, atol=1e-13)
+    z1_rho.append(ref)
+
+np.savez_compressed(os.path.join(HERE, "pyref_trajectories.npz"), r1_tspan=cfg.tspan, r1_samples=r1_samples, r1_phases=r1_phases,
+                    r1_rho=np.array(r1_rho), r1_free=np.array([c[0] for c in cases]), r1_psi0=np.array([c[1] for c in cases]),
+                    z1_tspan=cz.tspan, z1_xi=cz.ξ, z1_s1=z1_s1, z1_s2=z1_s2, z1_phases=z1_phases, z1_rho=np.array(z1_rho))
+print("written", os.path.join(HERE, "pyref_trajectories.npz"))
