@@ -788,7 +788,7 @@ struct StepCtrl {
 // [slot][component][thread] (conflict-free), six slots per thread (k7 reuses k2's slot; FSAL k1 <- k7 is a toggle of
 // the slot index, not a copy).  Registers hold only y, the stage input, the stage output and y_new.  The stage loop is
 // rolled (dynamic slot / tableau indexing works in shared and constant memory), so the whole step is a few KB of code.
-template <int NS>
+template <int NS, int BEAMS = 0>   // BEAMS: 0 decide at run time (both coefficient paths compiled), 1 Gaussian pair only, 2 other beam kinds only
 struct Lane1 {
     // trajectory
     double x0, y0, z0, vx, vy, vz, vzq;  // vzq: velocity used for "Vz" (vy when the B1 quirk is on)
@@ -801,7 +801,7 @@ struct Lane1 {
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
-    double* ab;                           // per beam q: ab[(q*7 + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a); ab[14] = t_a, ab[15] = t_a + 2H
+    double* ab;                           // per beam q: ab[(q*9 + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a) | b3 re,im; ab[18] = t_a, ab[19] = end of validity
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
     bool win_ok;                          // the anchor's quadratic model of ln B passed its guard
     double t, h, dt, tcommit;
@@ -888,11 +888,60 @@ struct Lane1 {
         if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
     }
 
-    CA_HD bool fast_model(const DevModel& m) const {
-        return NS == 9 && ab != nullptr && m.free_motion && m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS && m.xi == 0.0 &&
-               m.dtn > 0.0;
+    CA_HD bool fast_model(const DevModel& m) const {   // anchored coefficients are available (any beam kind)
+        return NS == 9 && ab != nullptr && m.free_motion && m.xi == 0.0 && m.dtn > 0.0;
     }
+    CA_HD bool gauss_pair(const DevModel& m) const { return m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS; }
     CA_HD double stage_time(int n, double tt0, double hh, double tn) const { return n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0); }
+
+    // Anchor for ANY beam kind (flat-top HG / LG, uniform): the exact coefficient at tt and a CUBIC model of ln c on [tt, tt + 3H]
+    // from the exact values at tt, tt+H, tt+2H, tt+3H through complex logarithms of their ratios to the anchor.  µm-scale flat-top
+    // beams (and their e^{-ikz} factor) vary faster than the wide Gaussian ones, hence one order more here and in the series below.
+    CA_HD void refresh_anchor_generic(const DevModel& m, double tt, double H) {
+        double pr = 0.0, pb = 0.0;
+        if (tab) {
+            if (!(tt < tnx) || tt < tj) window_at(m, tt);
+            phases_win(m, tt, pr, pb);
+        }
+        win_ok = true;
+        const double iH = rcp_d(H);
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+            const DevBeam& bm = q == 0 ? m.red : m.blue;
+            double* a = ab + (size_t)q * 9 * kstride;
+            double c0r = 0.0, c0i = 0.0, inv0 = 0.0, l[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const double tn_ = fma((double)i, H, tt);
+                double re, im;
+                beam_half_omega(bm, fma(vx, tn_, x0), fma(vy, tn_, y0), fma(vz, tn_, z0), 0.0, &re, &im);
+                if (i == 0) {
+                    c0r = re; c0i = im;
+                    const double n2 = re * re + im * im;
+                    win_ok = win_ok && n2 > 1e-280;
+                    inv0 = n2 > 1e-280 ? 1.0 / n2 : 0.0;
+                } else {   // ln(c_i / c_0) = ln|r| + i arg r  (the flat-top fields carry e^{-ikz}: the phase moves by mrad over the window)
+                    const double rr = (re * c0r + im * c0i) * inv0, ri = (im * c0r - re * c0i) * inv0, wr = rr - 1.0;
+                    win_ok = win_ok && (wr * wr + ri * ri < 0.01);
+                    const double lr = 0.5 * log1p(fma(wr, 2.0 + wr, ri * ri)), li = atan2(ri, rr);
+                    if (i == 1) { l[0][0] = lr; l[0][1] = li; } else if (i == 2) { l[1][0] = lr; l[1][1] = li; } else { l[2][0] = lr; l[2][1] = li; }
+                }
+            }
+            double sn = 0.0, cs = 1.0;
+            const double ph = q == 0 ? pr : pb;
+            if (tab) sincos_fast(ph, &sn, &cs);
+            a[0] = c0r * cs - c0i * sn; a[kstride] = c0r * sn + c0i * cs;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {   // Newton forward differences -> monomials in τ
+                const double d1 = l[0][c], d2 = l[1][c] - 2.0 * l[0][c], d3 = l[2][c] - 3.0 * l[1][c] + 3.0 * l[0][c];
+                a[(2 + c) * kstride] = (d1 - 0.5 * d2 + (1.0 / 3.0) * d3) * iH;
+                a[(4 + c) * kstride] = (0.5 * d2 - 0.5 * d3) * iH * iH;
+                a[(7 + c) * kstride] = (1.0 / 6.0) * d3 * iH * iH * iH;
+            }
+            a[6 * kstride] = ph;
+        }
+        ab[18 * kstride] = tt; ab[19 * kstride] = fma(3.0, H, tt);
+    }
 
     // Exact anchor at time tt: c(tt) with its noise phase and the quadratic model of ln B on [tt, tt + 2H].
     CA_HD void refresh_anchor(const DevModel& m, double tt, double H) {
@@ -906,7 +955,7 @@ struct Lane1 {
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
             const DevBeam& bm = q == 0 ? m.red : m.blue;
-            double* a = ab + (size_t)q * 7 * kstride;
+            double* a = ab + (size_t)q * 9 * kstride;
             // rolled on purpose: this code runs once per 16 steps and must not evict the step loop from the instruction cache
             double L0r = 0.0, L0i = 0.0, L1r = 0.0, L1i = 0.0, L2r = 0.0, L2i = 0.0;
 #pragma unroll 1
@@ -933,7 +982,62 @@ struct Lane1 {
             }
             a[6 * kstride] = q == 0 ? pr : pb;
         }
-        ab[14 * kstride] = tt; ab[15 * kstride] = fma(2.0, H, tt);
+        ab[18 * kstride] = tt; ab[19 * kstride] = fma(2.0, H, tt);
+    }
+
+    // c(t) = c(t_a) exp(δ) at the five stage times.  GP (both beams Gaussian): quadratic ln B, guards |Re δ| < 3e-4, |Im δ| < 6e-3.
+    // Otherwise (flat-top HG / LG, uniform): cubic model and three more series orders, guards |Re δ| < 5e-3, |Im δ| < 0.1 (the
+    // e^{-ikz} factor of those fields turns the phase by ~1e-2 rad over an anchor window).  One compiled copy runs per launch.
+    template <bool GP>
+    CA_HD bool eval_anchored(const DevModel& m, double tt0, double hh, double tn) {
+        double ca[2][2], b1[2][2], b2[2][2], b3[2][2], pa[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double* a = ab + (size_t)q * 9 * kstride;
+            ca[q][0] = a[0]; ca[q][1] = a[kstride];
+            b1[q][0] = a[2 * kstride]; b1[q][1] = a[3 * kstride]; b2[q][0] = a[4 * kstride]; b2[q][1] = a[5 * kstride];
+            pa[q] = a[6 * kstride];
+            b3[q][0] = GP ? 0.0 : a[7 * kstride]; b3[q][1] = GP ? 0.0 : a[8 * kstride];
+        }
+        const double ta = ab[18 * kstride];
+        double worst = 0.0;
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+            const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
+            const double tau = tt - ta;
+            double ph[2] = {0.0, 0.0};
+            if (tab) phases_win(m, tt, ph[0], ph[1]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                // δ = ln B(t) - ln B(t_a) + i (φ(t) - φ(t_a)) = dr + i di ;  e^δ = e^{dr} (cos di + i sin di) by short real series
+                double dr, di, ed, cs, sn;
+                if (GP) {
+                    dr = tau * fma(tau, b2[q][0], b1[q][0]);
+                    di = fma(tau, fma(tau, b2[q][1], b1[q][1]), ph[q] - pa[q]);
+                } else {
+                    dr = tau * fma(tau, fma(tau, b3[q][0], b2[q][0]), b1[q][0]);
+                    di = fma(tau, fma(tau, fma(tau, b3[q][1], b2[q][1]), b1[q][1]), ph[q] - pa[q]);
+                }
+                worst = fma(di, di, fma(400.0 * dr, dr, worst));   // Σ (di² + (20 dr)²) >= max: one conservative guard per step
+                const double d2 = di * di;
+                if (GP) {
+                    ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
+                    cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
+                    sn = di * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                } else {
+                    ed = fma(dr, fma(dr, fma(dr, fma(dr, fma(dr, fma(dr, 1.0 / 720.0, 1.0 / 120.0), 1.0 / 24.0), 1.0 / 6.0), 0.5), 1.0), 1.0);
+                    cs = fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 40320.0, -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+                    sn = di * fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 362880.0, -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+                }
+                const double er = ed * cs, ei = ed * sn;
+                cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
+                cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
+        // Gaussian pair: every |di| < 6e-3 (di⁶/720 < 7e-17), |dr| < 3e-4 (dr⁴/24 < 4e-16); else |di| < 0.1 (di¹⁰/3.6e6 < 3e-17), |dr| < 5e-3 (dr⁷/5040 < 2e-20)
+        return worst < (GP ? 3.6e-5 : 1e-2);
     }
 
     // Coefficients of the five distinct stage times of one step (c2..c5 and t+h; stage 7 and the next stage 1 share the
@@ -946,45 +1050,13 @@ struct Lane1 {
                 if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
                 ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
             }
-            if (refresh || !(tn <= ab[15 * kstride]) || tt0 < ab[14 * kstride]) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);   // two steps of headroom over the re-anchoring cadence
-            ok = ok && win_ok;
-            if (ok) {
-                double ca[2][2], b1[2][2], b2[2][2], pa[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const double* a = ab + (size_t)q * 7 * kstride;
-                    ca[q][0] = a[0]; ca[q][1] = a[kstride];
-                    b1[q][0] = a[2 * kstride]; b1[q][1] = a[3 * kstride]; b2[q][0] = a[4 * kstride]; b2[q][1] = a[5 * kstride];
-                    pa[q] = a[6 * kstride];
-                }
-                const double ta = ab[14 * kstride];
-                double worst = 0.0;
-#pragma unroll
-                for (int n = 0; n < 5; ++n) {
-                    const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
-                    const double tau = tt - ta;
-                    double ph[2] = {0.0, 0.0};
-                    if (tab) phases_win(m, tt, ph[0], ph[1]);
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        // δ = τ (b1 + τ b2) + i (φ(t) - φ(t_a)) = dr + i di ;  e^δ = e^{dr} (cos di + i sin di) by short real series
-                        // under the guards |dr| < 3e-4 (dr⁴/24 < 4e-16) and |di| < 6e-3 (di⁶/720 < 7e-17)
-                        const double dr = tau * fma(tau, b2[q][0], b1[q][0]);
-                        const double di = fma(tau, fma(tau, b2[q][1], b1[q][1]), ph[q] - pa[q]);
-                        worst = fma(di, di, fma(400.0 * dr, dr, worst));   // Σ (di² + (20 dr)²) >= max: one conservative guard per step
-                        const double ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
-                        const double d2 = di * di;
-                        const double cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
-                        const double sn = di * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
-                        const double er = ed * cs, ei = ed * sn;
-                        cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
-                        cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
-                    }
-                }
-#pragma unroll
-                for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
-                done = worst < 3.6e-5;   // every |di| < 6e-3 (cos, sin series exact to 7e-17), every |dr| < 3e-4 (dr⁴/24 < 4e-16)
+            const bool gp = BEAMS == 1 ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
+            if (refresh || !(tn <= ab[19 * kstride]) || tt0 < ab[18 * kstride]) {   // two steps of headroom over the re-anchoring cadence
+                if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
+                else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
             }
+            ok = ok && win_ok;
+            if (ok) done = gp ? eval_anchored<true>(m, tt0, hh, tn) : eval_anchored<false>(m, tt0, hh, tn);
         }
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
             ++n_exact;
@@ -1013,7 +1085,7 @@ struct Lane1 {
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
                     double t0, double* kbase, int kstr, double* cbase, double* abase) {
         kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false;
-        if (ab) { ab[14 * kstride] = 1e300; ab[15 * kstride] = -1e300; }
+        if (ab) { ab[18 * kstride] = 1e300; ab[19 * kstride] = -1e300; }
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
         vzq = m.vz_from_vy ? vy : vz;

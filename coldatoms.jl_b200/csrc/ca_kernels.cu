@@ -2,7 +2,7 @@
 // the samplers and release-recapture.  The two-atom kernel lives in ca_lindblad2.cu.
 //
 // Kernels (SURVEY §8a "Kernel <-> reference mapping"):
-//   k_lindblad1<NS,SWEEP>  K1+K2+K3 fused: Philox atom sampler, phase-noise table generation and the DP5
+//   k_lindblad1<NS,SWEEP,BEAMS>  K1+K2+K3 fused: Philox atom sampler, phase-noise table generation and the DP5
 //                          Lindblad integrator, one trajectory per thread, state in registers; observables
 //                          reduced by warp shuffles and accumulated with fp64 RED atomics.
 //   k_finalize             K6: packed sums -> full column-major complex matrices, scaled by 1/N.
@@ -61,7 +61,7 @@ struct R1Params {
 template <int NS>
 __host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 1 : (NS == 15 ? 2 : 1); }
 
-template <int NS, bool SWEEP>
+template <int NS, bool SWEEP, int BEAMS>
 __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
     constexpr int T = threads_for<NS>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             cyc_noise += clock64();
         }
         // ---- K3: integrate
-        Lane1<NS> L;
+        Lane1<NS, BEAMS> L;
         L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS == 9 ? sab + threadIdx.x : nullptr);
         const double tend = tsp[P.nt - 1];
         unsigned n_att = 0;
@@ -362,12 +362,12 @@ void* ctx_buf(ca_ctx* c, int which, size_t bytes) {
     return b.p;
 }
 
-template <int NS, bool SWEEP>
+template <int NS, bool SWEEP, int BEAMS>
 static int launch_lindblad1(ca_ctx* c, const R1Params& P, int grid) {
     constexpr int T = threads_for<NS>();
     const size_t smem = sizeof(double) * smem_doubles_per_thread<NS>() * T + (SWEEP ? sizeof(DevModel) * (T / 32) : 0);
-    CA_CUDA(cudaFuncSetAttribute(k_lindblad1<NS, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_lindblad1<NS, SWEEP><<<grid, T, smem, c->stream>>>(P);
+    CA_CUDA(cudaFuncSetAttribute(k_lindblad1<NS, SWEEP, BEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_lindblad1<NS, SWEEP, BEAMS><<<grid, T, smem, c->stream>>>(P);
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
@@ -464,9 +464,15 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     CA_CUDA(cudaEventRecord(c->ev[1], c->stream));
     if (n_all > 0) {
         const int ns = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
-        if (ns == 9) rc = sweep ? launch_lindblad1<9, true>(c, P, grid) : launch_lindblad1<9, false>(c, P, grid);
-        else if (ns == 15) rc = sweep ? launch_lindblad1<15, true>(c, P, grid) : launch_lindblad1<15, false>(c, P, grid);
-        else rc = sweep ? launch_lindblad1<21, true>(c, P, grid) : launch_lindblad1<21, false>(c, P, grid);
+        // the anchored-coefficient code of the NS = 9 kernel is compiled per beam class (all points Gaussian pairs / none / mixed sweep)
+        int n_gp = 0;
+        for (int p = 0; p < n_points; ++p) n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
+        if (ns == 9) {
+            if (n_gp == n_points) rc = sweep ? launch_lindblad1<9, true, 1>(c, P, grid) : launch_lindblad1<9, false, 1>(c, P, grid);
+            else if (n_gp == 0) rc = sweep ? launch_lindblad1<9, true, 2>(c, P, grid) : launch_lindblad1<9, false, 2>(c, P, grid);
+            else rc = launch_lindblad1<9, true, 0>(c, P, grid);
+        } else if (ns == 15) rc = sweep ? launch_lindblad1<15, true, 0>(c, P, grid) : launch_lindblad1<15, false, 0>(c, P, grid);
+        else rc = sweep ? launch_lindblad1<21, true, 0>(c, P, grid) : launch_lindblad1<21, false, 0>(c, P, grid);
         if (rc) return rc;
         ++launches;
     }

@@ -33,7 +33,7 @@ static int run_lane(const DevModel& m, const OdeOpts& oo, const double* tspan, i
         second_moment<(NS > 9)>(v, m.rho2_mode, v + 25);
         std::memcpy(out + (size_t)j * kNV, v, sizeof v);
     }
-    stats[0] += L.n_rhs; stats[1] += L.n_acc; stats[2] += L.n_rej;
+    stats[0] += L.n_rhs; stats[1] += L.n_acc; stats[2] += L.n_rej; stats[3] += L.n_exact;
     return 0;
 }
 
@@ -182,7 +182,7 @@ int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const d
         sc.U0 = m.U0; sc.w0 = m.w0; sc.z0 = m.z0; sc.mfac = m.mfac; sc.ecut = m.ecut;
         sample_atom_literal(sc, seed, gi, 0u, smp);
     }
-    stats[0] = stats[1] = stats[2] = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (m.rows == 0) return run_lane<9>(m, oo, tspan, nt, smp, tp, out, stats);
     if (m.rows == 3) return run_lane<21>(m, oo, tspan, nt, smp, tp, out, stats);
     return run_lane<15>(m, oo, tspan, nt, smp, tp, out, stats);

@@ -40,14 +40,15 @@ def he_traj(he, model, tspan, psi0, sample, pr, pb, f, ar, ab, ode, seed=1, gi=0
     tspan = np.ascontiguousarray(tspan, float)
     nt = len(tspan)
     out = np.zeros((nt, 50))
-    st = (C.c_longlong * 3)()
+    st = (C.c_longlong * 4)()
     psi = np.ascontiguousarray(np.asarray(psi0, complex)).view(float)
     arrs = [None if a is None else np.ascontiguousarray(a, float) for a in (sample, pr, pb, f, ar, ab)]
     nf = 0 if f is None else len(f)
     rc = he.he_rydberg1_traj(C.byref(model), P(tspan), nt, P(psi), P(arrs[0]), P(arrs[1]), P(arrs[2]), P(arrs[3]), P(arrs[4]), P(arrs[5]), nf,
                              C.byref(ode), C.c_ulonglong(seed), C.c_ulonglong(gi), P(out), st)
     assert rc == 0, rc
-    return unpack(out[:, :25]), unpack(out[:, 25:]), list(st)
+    he_traj.n_exact = st[3]   # steps whose coefficients took the exact path
+    return unpack(out[:, :25]), unpack(out[:, 25:]), list(st)[:3]
 
 
 @pytest.mark.parametrize("psi", ["1", "0+i1", "l", "general"])
@@ -103,6 +104,7 @@ def test_lane_arbitrary_beams(pkg, oracle, he):
         r1, r2, st = he_traj(he, m, tspan, pkg.ket_1, samples[0], None, None, None, None, None, ode)
         o1, o2, ost = oracle.rydberg1_run(m, tspan, pkg.ket_1, 1, samples=samples, ode=ode)
         assert st[0] == ost["n_rhs"]
+        assert he_traj.n_exact == 0   # flat-top HG / LG beams ride the cubic anchor model, no exact fallback
         assert np.abs(r1 - o1).max() < 1e-10 and np.abs(r2 - o2).max() < 1e-10
 
 
