@@ -56,7 +56,9 @@ def workload(pkg, name, n):
 def noise_coarse(cfg):
     """The coarsening factor the one-atom kernel picks for its phase-noise tables (choose_noise_coarse, ca_device.cuh)."""
     dtn = cfg.tspan[-1] / 1000.0
-    for c in (8, 4, 2):
+    for c in (32, 16, 8, 4, 2):
+        if ((1000 + c - 1) // c + 8) * c > 2 * 1001:
+            continue
         b = max(float(np.sum(np.abs(a) * (2 * np.pi * np.abs(cfg.f) * c * dtn) ** 8))
                 for a in (cfg.red_laser_phase_amplitudes, cfg.blue_laser_phase_amplitudes))
         if b * 43.07 / 40320.0 <= 1e-14:

@@ -608,11 +608,11 @@ inline void fill_noise_k(const double* f, const double* amp, int nf, double dtn,
 
 // ---- band-limited shortcut -----------------------------------------------------------------------------------------
 // The trace is a sum of cosines with f <= f_max, and the node grid (rydberg_model.jl:216) oversamples it hundreds of
-// times.  Only every c-th node (c = 8, 4 or 2) is summed exactly; the nodes in between follow from 8-point (degree 7)
+// times.  Only every c-th node (c = 32, 16, 8, 4 or 2) is summed exactly; the nodes in between follow from 8-point (degree 7)
 // Lagrange interpolation of the exact ones, whose error Σ_k a_k (ω_k c dtn)^8 · 43.07/8! is kept below 1e-14 rad by the
 // choice of c (observed: 6e-16 for the R1 workload at c = 4) -- the table equals the directly summed one to rounding
 // while the O(nodes x frequencies) work drops by c.
-struct LagrangeW { double w[11][8]; };   // rows: c=2 (r=1), c=4 (r=1..3), c=8 (r=1..7); columns: nodes at offsets -3..4
+struct LagrangeW { double w[57][8]; };   // rows: c=2 (r=1), c=4 (r=1..3), c=8, c=16, c=32 (r=1..c-1); columns: nodes at offsets -3..4
 #define CA_LAGRANGE_INIT {{ \
     {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
     {-495.0 / 262144.0, 5005.0 / 262144.0, -27027.0 / 262144.0, 225225.0 / 262144.0, 75075.0 / 262144.0, -19305.0 / 262144.0, 4095.0 / 262144.0, -429.0 / 262144.0}, \
@@ -624,7 +624,53 @@ struct LagrangeW { double w[11][8]; };   // rows: c=2 (r=1), c=4 (r=1..3), c=8 (
     {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
     {-73359.0 / 33554432.0, 709137.0 / 33554432.0, -3436587.0 / 33554432.0, 14891877.0 / 33554432.0, 24819795.0 / 33554432.0, -4061421.0 / 33554432.0, 783783.0 / 33554432.0, -78793.0 / 33554432.0}, \
     {-429.0 / 262144.0, 4095.0 / 262144.0, -19305.0 / 262144.0, 75075.0 / 262144.0, 225225.0 / 262144.0, -27027.0 / 262144.0, 5005.0 / 262144.0, -495.0 / 262144.0}, \
-    {-29325.0 / 33554432.0, 276675.0 / 33554432.0, -1272705.0 / 33554432.0, 4545375.0 / 33554432.0, 31817625.0 / 33554432.0, -2121175.0 / 33554432.0, 374325.0 / 33554432.0, -36363.0 / 33554432.0} }}
+    {-29325.0 / 33554432.0, 276675.0 / 33554432.0, -1272705.0 / 33554432.0, 4545375.0 / 33554432.0, 31817625.0 / 33554432.0, -2121175.0 / 33554432.0, 374325.0 / 33554432.0, -36363.0 / 33554432.0}, \
+    {-2452131.0 / 4294967296.0, 25487301.0 / 4294967296.0, -148426047.0 / 4294967296.0, 4205404665.0 / 4294967296.0, 280360311.0 / 4294967296.0, -81394929.0 / 4294967296.0, 17895339.0 / 4294967296.0, -1907213.0 / 4294967296.0}, \
+    {-36363.0 / 33554432.0, 374325.0 / 33554432.0, -2121175.0 / 33554432.0, 31817625.0 / 33554432.0, 4545375.0 / 33554432.0, -1272705.0 / 33554432.0, 276675.0 / 33554432.0, -29325.0 / 33554432.0}, \
+    {-6554145.0 / 4294967296.0, 66852279.0 / 4294967296.0, -369446805.0 / 4294967296.0, 3899716275.0 / 4294967296.0, 899934525.0 / 4294967296.0, -242051355.0 / 4294967296.0, 51996217.0 / 4294967296.0, -5479695.0 / 4294967296.0}, \
+    {-495.0 / 262144.0, 5005.0 / 262144.0, -27027.0 / 262144.0, 225225.0 / 262144.0, 75075.0 / 262144.0, -19305.0 / 262144.0, 4095.0 / 262144.0, -429.0 / 262144.0}, \
+    {-9293031.0 / 4294967296.0, 93181473.0 / 4294967296.0, -492530643.0 / 4294967296.0, 3447714501.0 / 4294967296.0, 1567142955.0 / 4294967296.0, -383079389.0 / 4294967296.0, 80179407.0 / 4294967296.0, -8347977.0 / 4294967296.0}, \
+    {-78793.0 / 33554432.0, 783783.0 / 33554432.0, -4061421.0 / 33554432.0, 24819795.0 / 33554432.0, 14891877.0 / 33554432.0, -3436587.0 / 33554432.0, 709137.0 / 33554432.0, -73359.0 / 33554432.0}, \
+    {-10481445.0 / 4294967296.0, 103470675.0 / 4294967296.0, -526350825.0 / 4294967296.0, 2882397375.0 / 4294967296.0, 2241864625.0 / 4294967296.0, -484242759.0 / 4294967296.0, 98423325.0 / 4294967296.0, -10113675.0 / 4294967296.0}, \
+    {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
+    {-10113675.0 / 4294967296.0, 98423325.0 / 4294967296.0, -484242759.0 / 4294967296.0, 2241864625.0 / 4294967296.0, 2882397375.0 / 4294967296.0, -526350825.0 / 4294967296.0, 103470675.0 / 4294967296.0, -10481445.0 / 4294967296.0}, \
+    {-73359.0 / 33554432.0, 709137.0 / 33554432.0, -3436587.0 / 33554432.0, 14891877.0 / 33554432.0, 24819795.0 / 33554432.0, -4061421.0 / 33554432.0, 783783.0 / 33554432.0, -78793.0 / 33554432.0}, \
+    {-8347977.0 / 4294967296.0, 80179407.0 / 4294967296.0, -383079389.0 / 4294967296.0, 1567142955.0 / 4294967296.0, 3447714501.0 / 4294967296.0, -492530643.0 / 4294967296.0, 93181473.0 / 4294967296.0, -9293031.0 / 4294967296.0}, \
+    {-429.0 / 262144.0, 4095.0 / 262144.0, -19305.0 / 262144.0, 75075.0 / 262144.0, 225225.0 / 262144.0, -27027.0 / 262144.0, 5005.0 / 262144.0, -495.0 / 262144.0}, \
+    {-5479695.0 / 4294967296.0, 51996217.0 / 4294967296.0, -242051355.0 / 4294967296.0, 899934525.0 / 4294967296.0, 3899716275.0 / 4294967296.0, -369446805.0 / 4294967296.0, 66852279.0 / 4294967296.0, -6554145.0 / 4294967296.0}, \
+    {-29325.0 / 33554432.0, 276675.0 / 33554432.0, -1272705.0 / 33554432.0, 4545375.0 / 33554432.0, 31817625.0 / 33554432.0, -2121175.0 / 33554432.0, 374325.0 / 33554432.0, -36363.0 / 33554432.0}, \
+    {-1907213.0 / 4294967296.0, 17895339.0 / 4294967296.0, -81394929.0 / 4294967296.0, 280360311.0 / 4294967296.0, 4205404665.0 / 4294967296.0, -148426047.0 / 4294967296.0, 25487301.0 / 4294967296.0, -2452131.0 / 4294967296.0}, \
+    {-160452435.0 / 549755813888.0, 1676110821.0 / 549755813888.0, -9904291215.0 / 549755813888.0, 544736016825.0 / 549755813888.0, 17572129575.0 / 549755813888.0, -5187962065.0 / 549755813888.0, 1146812667.0 / 549755813888.0, -122550285.0 / 549755813888.0}, \
+    {-2452131.0 / 4294967296.0, 25487301.0 / 4294967296.0, -148426047.0 / 4294967296.0, 4205404665.0 / 4294967296.0, 280360311.0 / 4294967296.0, -81394929.0 / 4294967296.0, 17895339.0 / 4294967296.0, -1907213.0 / 4294967296.0}, \
+    {-459276625.0 / 549755813888.0, 4750428375.0 / 549755813888.0, -27281031525.0 / 549755813888.0, 530464501875.0 / 549755813888.0, 54875638125.0 / 549755813888.0, -15653050875.0 / 549755813888.0, 3422351625.0 / 549755813888.0, -363747087.0 / 549755813888.0}, \
+    {-36363.0 / 33554432.0, 374325.0 / 33554432.0, -2121175.0 / 33554432.0, 31817625.0 / 33554432.0, 4545375.0 / 33554432.0, -1272705.0 / 33554432.0, 276675.0 / 33554432.0, -29325.0 / 33554432.0}, \
+    {-722557719.0 / 549755813888.0, 7403598657.0 / 549755813888.0, -41420133027.0 / 549755813888.0, 510848307333.0 / 549755813888.0, 94601538395.0 / 549755813888.0, -25975337661.0 / 549755813888.0, 5613717663.0 / 549755813888.0, -593319753.0 / 549755813888.0}, \
+    {-6554145.0 / 4294967296.0, 66852279.0 / 4294967296.0, -369446805.0 / 4294967296.0, 3899716275.0 / 4294967296.0, 899934525.0 / 4294967296.0, -242051355.0 / 4294967296.0, 51996217.0 / 4294967296.0, -5479695.0 / 4294967296.0}, \
+    {-944279765.0 / 549755813888.0, 9589094515.0 / 549755813888.0, -52371208505.0 / 549755813888.0, 486304078975.0 / 549755813888.0, 136165142113.0 / 549755813888.0, -35832932135.0 / 549755813888.0, 7649727085.0 / 549755813888.0, -803808395.0 / 549755813888.0}, \
+    {-495.0 / 262144.0, 5005.0 / 262144.0, -27027.0 / 262144.0, 225225.0 / 262144.0, 75075.0 / 262144.0, -19305.0 / 262144.0, 4095.0 / 262144.0, -429.0 / 262144.0}, \
+    {-1119941691.0 / 549755813888.0, 11276125245.0 / 549755813888.0, -60231010455.0 / 549755813888.0, 457309523825.0 / 549755813888.0, 178947204975.0 / 549755813888.0, -44899480521.0 / 549755813888.0, 9461576355.0 / 549755813888.0, -988183845.0 / 549755813888.0}, \
+    {-9293031.0 / 4294967296.0, 93181473.0 / 4294967296.0, -492530643.0 / 4294967296.0, 3447714501.0 / 4294967296.0, 1567142955.0 / 4294967296.0, -383079389.0 / 4294967296.0, 80179407.0 / 4294967296.0, -8347977.0 / 4294967296.0}, \
+    {-1246556025.0 / 549755813888.0, 12448939503.0 / 549755813888.0, -65139799725.0 / 549755813888.0, 424395664875.0 / 549755813888.0, 222302491125.0 / 549755813888.0, -52849271475.0 / 549755813888.0, 10984358385.0 / 549755813888.0, -1140012775.0 / 549755813888.0}, \
+    {-78793.0 / 33554432.0, 783783.0 / 33554432.0, -4061421.0 / 33554432.0, 24819795.0 / 33554432.0, 14891877.0 / 33554432.0, -3436587.0 / 33554432.0, 709137.0 / 33554432.0, -73359.0 / 33554432.0}, \
+    {-1322622015.0 / 549755813888.0, 13105981785.0 / 549755813888.0, -67277373163.0 / 549755813888.0, 388138691325.0 / 549755813888.0, 265568578275.0 / 549755813888.0, -59362388085.0 / 549755813888.0, 12158561415.0 / 549755813888.0, -1253615649.0 / 549755813888.0}, \
+    {-10481445.0 / 4294967296.0, 103470675.0 / 4294967296.0, -526350825.0 / 4294967296.0, 2882397375.0 / 4294967296.0, 2241864625.0 / 4294967296.0, -484242759.0 / 4294967296.0, 98423325.0 / 4294967296.0, -10113675.0 / 4294967296.0}, \
+    {-1348075197.0 / 549755813888.0, 13258916811.0 / 549755813888.0, -66858793281.0 / 549755813888.0, 349151476023.0 / 549755813888.0, 308074831785.0 / 549755813888.0, -64129862943.0 / 549755813888.0, 12931536149.0 / 549755813888.0, -1324215459.0 / 549755813888.0}, \
+    {-5.0 / 2048.0, 49.0 / 2048.0, -245.0 / 2048.0, 1225.0 / 2048.0, 1225.0 / 2048.0, -245.0 / 2048.0, 49.0 / 2048.0, -5.0 / 2048.0}, \
+    {-1324215459.0 / 549755813888.0, 12931536149.0 / 549755813888.0, -64129862943.0 / 549755813888.0, 308074831785.0 / 549755813888.0, 349151476023.0 / 549755813888.0, -66858793281.0 / 549755813888.0, 13258916811.0 / 549755813888.0, -1348075197.0 / 549755813888.0}, \
+    {-10113675.0 / 4294967296.0, 98423325.0 / 4294967296.0, -484242759.0 / 4294967296.0, 2241864625.0 / 4294967296.0, 2882397375.0 / 4294967296.0, -526350825.0 / 4294967296.0, 103470675.0 / 4294967296.0, -10481445.0 / 4294967296.0}, \
+    {-1253615649.0 / 549755813888.0, 12158561415.0 / 549755813888.0, -59362388085.0 / 549755813888.0, 265568578275.0 / 549755813888.0, 388138691325.0 / 549755813888.0, -67277373163.0 / 549755813888.0, 13105981785.0 / 549755813888.0, -1322622015.0 / 549755813888.0}, \
+    {-73359.0 / 33554432.0, 709137.0 / 33554432.0, -3436587.0 / 33554432.0, 14891877.0 / 33554432.0, 24819795.0 / 33554432.0, -4061421.0 / 33554432.0, 783783.0 / 33554432.0, -78793.0 / 33554432.0}, \
+    {-1140012775.0 / 549755813888.0, 10984358385.0 / 549755813888.0, -52849271475.0 / 549755813888.0, 222302491125.0 / 549755813888.0, 424395664875.0 / 549755813888.0, -65139799725.0 / 549755813888.0, 12448939503.0 / 549755813888.0, -1246556025.0 / 549755813888.0}, \
+    {-8347977.0 / 4294967296.0, 80179407.0 / 4294967296.0, -383079389.0 / 4294967296.0, 1567142955.0 / 4294967296.0, 3447714501.0 / 4294967296.0, -492530643.0 / 4294967296.0, 93181473.0 / 4294967296.0, -9293031.0 / 4294967296.0}, \
+    {-988183845.0 / 549755813888.0, 9461576355.0 / 549755813888.0, -44899480521.0 / 549755813888.0, 178947204975.0 / 549755813888.0, 457309523825.0 / 549755813888.0, -60231010455.0 / 549755813888.0, 11276125245.0 / 549755813888.0, -1119941691.0 / 549755813888.0}, \
+    {-429.0 / 262144.0, 4095.0 / 262144.0, -19305.0 / 262144.0, 75075.0 / 262144.0, 225225.0 / 262144.0, -27027.0 / 262144.0, 5005.0 / 262144.0, -495.0 / 262144.0}, \
+    {-803808395.0 / 549755813888.0, 7649727085.0 / 549755813888.0, -35832932135.0 / 549755813888.0, 136165142113.0 / 549755813888.0, 486304078975.0 / 549755813888.0, -52371208505.0 / 549755813888.0, 9589094515.0 / 549755813888.0, -944279765.0 / 549755813888.0}, \
+    {-5479695.0 / 4294967296.0, 51996217.0 / 4294967296.0, -242051355.0 / 4294967296.0, 899934525.0 / 4294967296.0, 3899716275.0 / 4294967296.0, -369446805.0 / 4294967296.0, 66852279.0 / 4294967296.0, -6554145.0 / 4294967296.0}, \
+    {-593319753.0 / 549755813888.0, 5613717663.0 / 549755813888.0, -25975337661.0 / 549755813888.0, 94601538395.0 / 549755813888.0, 510848307333.0 / 549755813888.0, -41420133027.0 / 549755813888.0, 7403598657.0 / 549755813888.0, -722557719.0 / 549755813888.0}, \
+    {-29325.0 / 33554432.0, 276675.0 / 33554432.0, -1272705.0 / 33554432.0, 4545375.0 / 33554432.0, 31817625.0 / 33554432.0, -2121175.0 / 33554432.0, 374325.0 / 33554432.0, -36363.0 / 33554432.0}, \
+    {-363747087.0 / 549755813888.0, 3422351625.0 / 549755813888.0, -15653050875.0 / 549755813888.0, 54875638125.0 / 549755813888.0, 530464501875.0 / 549755813888.0, -27281031525.0 / 549755813888.0, 4750428375.0 / 549755813888.0, -459276625.0 / 549755813888.0}, \
+    {-1907213.0 / 4294967296.0, 17895339.0 / 4294967296.0, -81394929.0 / 4294967296.0, 280360311.0 / 4294967296.0, 4205404665.0 / 4294967296.0, -148426047.0 / 4294967296.0, 25487301.0 / 4294967296.0, -2452131.0 / 4294967296.0}, \
+    {-122550285.0 / 549755813888.0, 1146812667.0 / 549755813888.0, -5187962065.0 / 549755813888.0, 17572129575.0 / 549755813888.0, 544736016825.0 / 549755813888.0, -9904291215.0 / 549755813888.0, 1676110821.0 / 549755813888.0, -160452435.0 / 549755813888.0} }}
 #if defined(__CUDACC__)
 static __constant__ LagrangeW c_lw = CA_LAGRANGE_INIT;
 #endif
@@ -640,7 +686,8 @@ CA_HD int noise_coarse_count(int n_nodes, int c) { return (n_nodes - 1 + c - 1) 
 // host: largest coarsening factor whose interpolation error bound stays below 1e-14 rad (1 = sum every node)
 inline int choose_noise_coarse(const double* f, const double* amp_a, const double* amp_b, int nf, double dtn, int n_nodes) {
     if (n_nodes < 64) return 1;
-    for (int c = 8; c >= 2; c >>= 1) {
+    for (int c = 32; c >= 2; c >>= 1) {
+        if (noise_coarse_count(n_nodes, c) * c > 2 * n_nodes) continue;   // the 8 padding nodes must not dominate
         double ba = 0.0, bb = 0.0;
         for (int k = 0; k < nf; ++k) {
             const double x = kTwoPi * fabs(f[k]) * c * dtn, x2 = x * x, x8 = (x2 * x2) * (x2 * x2);
@@ -658,7 +705,7 @@ CA_HD void gen_noise_trace_c(const NoiseK* __restrict__ nk, int nf, int n_nodes,
     if (c <= 1) { gen_noise_trace<CH>(nk, nf, n_nodes, dtn, 0.0, phases, seed, gi, stream, out, stride); return; }
     const int n_c = noise_coarse_count(n_nodes, c);
     gen_noise_trace<CH>(nk, nf, n_c, c * dtn, -3.0 * c * dtn, phases, seed, gi, stream, tmp, tstride);
-    const int row0 = c == 2 ? 0 : (c == 4 ? 1 : 4);
+    const int row0 = c == 2 ? 0 : (c == 4 ? 1 : (c == 8 ? 4 : (c == 16 ? 11 : 26)));
     double win[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) win[i] = tmp[(size_t)i * tstride];
