@@ -188,3 +188,26 @@ def test_arbitrary_beams_blue_intens(pkg, oracle, ctx, kind, parallel):
     r, r2, _ = ctx.rydberg1_run(m, a["tspan"][:3], a["ψ0"], n, samples=samples, ode=ode)
     o, o2, _ = oracle.rydberg1_run(m, a["tspan"][:3], a["ψ0"], n, samples=samples, ode=ode)
     assert np.abs(r - o).max() < 1e-10 and np.abs(r2 - o2).max() < 1e-10
+
+
+def test_sweep_over_beam_classes(pkg, oracle, ctx, r1cfg):
+    """The anchored-coefficient code is compiled per beam class; a sweep may mix them (Gaussian pair / flat-top points in one launch)
+    or consist of flat-top points only.  Every point must equal its own single-model oracle run on the same trajectory indices."""
+    a = _r2_args(pkg, "HG")
+    hg = pkg.blue_intens_model(a["atom_params"], a["trap_params"], a["red_laser_params"], a["blue_laser_params"], a["detuning_params"],
+                               a["decay_params"])
+    b = _r2_args(pkg, "LG")
+    lg = pkg.blue_intens_model(b["atom_params"], b["trap_params"], b["red_laser_params"], b["blue_laser_params"], b["detuning_params"],
+                               b["decay_params"])
+    cfg = r1cfg.copy()
+    cfg.laser_noise = False
+    gauss = pkg.model_from_config(cfg)
+    n_pp = 40
+    for models in ([gauss, hg, lg], [hg, lg]):
+        tends = [0.12, 0.2, 0.17][:len(models)]
+        psis = [pkg.ket_1] * len(models)
+        srho, srho2, _ = ctx.rydberg1_sweep(models, psis, tends, n_pp, seed=13)
+        for k, m in enumerate(models):
+            o, o2, _ = oracle.rydberg1_run(m, [0.0, tends[k]], psis[k], n_pp, traj_offset=k * n_pp, seed=13)
+            assert np.abs(srho[k] - o[-1]).max() < TOL_ADAPTIVE, k
+            assert np.abs(srho2[k] - o2[-1]).max() < TOL_ADAPTIVE, k
