@@ -100,3 +100,25 @@ def test_partition_independence_and_api(pkg, oracle, ctx, czcfg):
     # empty ensemble
     z, _, st = ctx.rydberg2_run(model, cz.tspan, cz.ψ0, 0, f=cz.f, amp_red=cz.red_laser_phase_amplitudes, amp_blue=cz.blue_laser_phase_amplitudes)
     assert np.all(z == 0)
+
+
+def test_longest_first_handout_keeps_the_ensemble(pkg, oracle, ctx, czcfg):
+    """More than two rounds of trajectories switch on the longest-first ordering (bucket sort by the blockade shift of the sampled
+    pair): the ensemble sums must not depend on the hand-out order, with host-supplied and with device-drawn samples."""
+    cz = czcfg.copy()
+    cz.tspan = np.array([0.0, 0.006])
+    n = 2600   # > 2 x 148 SMs x 8 warps
+    model = pkg.model_from_config(cz, two_atom=True)
+    ode = pkg._abi.ode_opts(maxiters=10 ** 7)   # adaptive: a fixed step is unstable for the closest pairs (V ~ R^-6) of 2600 samples
+    kw = _inputs(oracle, cz, n)
+    rho, rho2, st = ctx.rydberg2_run(model, cz.tspan, cz.ψ0, n, ode=ode, **kw)
+    assert st["n_launches"] == 5   # three ordering kernels + integration + finalize
+    o, o2, _ = oracle.rydberg2_run(model, cz.tspan, cz.ψ0, n, ode=ode, **kw)
+    assert np.abs(rho - o).max() < TOL_ADAPTIVE and np.abs(rho2 - o2).max() < TOL_ADAPTIVE
+    # device-drawn samples: same ensemble as two unordered shards
+    kw = dict(f=cz.f, amp_red=cz.red_laser_phase_amplitudes, amp_blue=cz.blue_laser_phase_amplitudes, seed=3, ode=ode, out_flags=pkg._abi.CA_OUT_SUMS)
+    full, _, _ = ctx.rydberg2_run(model, cz.tspan, cz.ψ0, n, **kw)
+    a, _, sa = ctx.rydberg2_run(model, cz.tspan, cz.ψ0, 1300, traj_offset=0, **kw)
+    b, _, _ = ctx.rydberg2_run(model, cz.tspan, cz.ψ0, 1300, traj_offset=1300, **kw)
+    assert sa["n_launches"] == 2
+    assert np.abs(full - (a + b)).max() < 1e-9
