@@ -1316,6 +1316,7 @@ struct Lane1 {
             }
         } else {
             dt = oo.dt0;
+            if (!(fabs(un[0] + un[1] + un[2]) < 1e300)) { status = CA_ERR_NONFINITE; return; }   // fixed step beyond the stability limit
         }
         if (accept) {
             n_acc++;

@@ -499,6 +499,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             } else {
                 dt = oo.dt0;
                 un_ll_new = tr0 - w.sum(diag_sum(un));
+                if (!(fabs(un_ll_new) < 1e300)) { status = CA_ERR_NONFINITE; break; }   // a fixed step beyond the stability limit blows up: report it
             }
             if (accept) {
                 n_acc++; h = hh; tcommit = tn; un_ll = un_ll_new;

@@ -122,3 +122,14 @@ def test_longest_first_handout_keeps_the_ensemble(pkg, oracle, ctx, czcfg):
     b, _, _ = ctx.rydberg2_run(model, cz.tspan, cz.ψ0, 1300, traj_offset=1300, **kw)
     assert sa["n_launches"] == 2
     assert np.abs(full - (a + b)).max() < 1e-9
+
+
+def test_unstable_fixed_step_is_reported(pkg, ctx, czcfg):
+    """A fixed step beyond the stability limit of the closest pairs blows up: CA_ERR_NONFINITE, not silent NaNs."""
+    cz = czcfg.copy()
+    cz.tspan = np.array([0.0, 0.05])
+    cz.laser_noise = False
+    cz.atom_centers = [[-0.35, 0.0, 0.0], [0.35, 0.0, 0.0]]   # V ~ 2π·135298/0.7^6 ≈ 7e6 rad/µs: dt·V >> 3
+    with pytest.raises(pkg._lib.ColdAtomsError) as e:
+        ctx.rydberg2_run(pkg.model_from_config(cz, two_atom=True), cz.tspan, cz.ψ0, 8, seed=2, ode=pkg._abi.ode_opts(dt=1e-4, adaptive=False))
+    assert e.value.code == pkg._abi.CA_ERR_NONFINITE
