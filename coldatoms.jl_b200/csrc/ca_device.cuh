@@ -835,7 +835,8 @@ struct StepCtrl {
 // [slot][component][thread] (conflict-free), six slots per thread (k7 reuses k2's slot; FSAL k1 <- k7 is a toggle of
 // the slot index, not a copy).  Registers hold only y, the stage input, the stage output and y_new.  The stage loop is
 // rolled (dynamic slot / tableau indexing works in shared and constant memory), so the whole step is a few KB of code.
-template <int NS, int BEAMS = 0>   // BEAMS: 0 decide at run time (both coefficient paths compiled), 1 Gaussian pair only, 2 other beam kinds only
+template <int NS, int BEAMS = 0>   // BEAMS: 0 decide at run time (all coefficient paths compiled), 1 Gaussian pair + free flight only,
+                                     // 2 other beam kinds (free flight), 3 Gaussian pair + trap oscillation
 struct Lane1 {
     // trajectory
     double x0, y0, z0, vx, vy, vz, vzq;  // vzq: velocity used for "Vz" (vy when the B1 quirk is on)
@@ -935,8 +936,19 @@ struct Lane1 {
         if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
     }
 
-    CA_HD bool fast_model(const DevModel& m) const {   // anchored coefficients are available (any beam kind)
-        return NS == 9 && ab != nullptr && m.free_motion && m.xi == 0.0 && m.dtn > 0.0;
+    CA_HD bool fast_model(const DevModel& m) const {   // anchored coefficients are available
+        if (!(NS == 9 && ab != nullptr && m.xi == 0.0 && m.dtn > 0.0)) return false;
+        if (m.free_motion) return true;                       // any beam kind in free flight
+        return (BEAMS == 0 || BEAMS == 3) && gauss_pair(m);   // trap oscillation: Gaussian pairs only
+    }
+    // position at time tn_ (free flight or oscillation about the trap centre: atom_sampler.jl:125-143)
+    CA_HD void position_at(const DevModel& m, double tn_, double& X, double& Y, double& Z) const {
+        if (BEAMS == 1 || BEAMS == 2 || m.free_motion) { X = fma(vx, tn_, x0); Y = fma(vy, tn_, y0); Z = fma(vz, tn_, z0); }
+        else {
+            double sr, cr, sz, cz;
+            sincos_fast(m.wr * tn_, &sr, &cr); sincos_fast(m.wz * tn_, &sz, &cz);
+            X = x0 * cr + vx / m.wr * sr; Y = y0 * cr + vy / m.wr * sr; Z = z0 * cz + vz / m.wz * sz;
+        }
     }
     CA_HD bool gauss_pair(const DevModel& m) const { return m.red.kind == CA_BEAM_GAUSS && m.blue.kind == CA_BEAM_GAUSS; }
     CA_HD double stage_time(int n, double tt0, double hh, double tn) const { return n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0); }
@@ -1008,7 +1020,8 @@ struct Lane1 {
 #pragma unroll 1
             for (int i = 0; i < 3; ++i) {
                 const double tn_ = fma((double)i, H, tt);
-                const double X = fma(vx, tn_, x0), Y = fma(vy, tn_, y0), Z = fma(vz, tn_, z0);
+                double X, Y, Z;
+                position_at(m, tn_, X, Y, Z);
                 const double rp = sqrt_d(fmax(X * X + Y * Y, 1e-300));
                 L0r = L1r; L0i = L1i; L1r = L2r; L1i = L2i;
                 gauss_log(bm, rp, Z, &L2r, &L2i);
@@ -1030,6 +1043,11 @@ struct Lane1 {
             a[6 * kstride] = q == 0 ? pr : pb;
         }
         ab[18 * kstride] = tt; ab[19 * kstride] = fma(2.0, H, tt);
+        if ((BEAMS == 0 || BEAMS == 3) && !m.free_motion) {   // cos/sin(ω t_a) for the time-dependent Doppler shifts (the Gaussian layout leaves slots 7,8,16,17 free)
+            double sr, cr, sz, cz;
+            sincos_fast(m.wr * tt, &sr, &cr); sincos_fast(m.wz * tt, &sz, &cz);
+            ab[7 * kstride] = cr; ab[8 * kstride] = sr; ab[16 * kstride] = cz; ab[17 * kstride] = sz;
+        }
     }
 
     // c(t) = c(t_a) exp(δ) at the five stage times.  GP (both beams Gaussian): quadratic ln B, guards |Re δ| < 3e-4, |Im δ| < 6e-3.
@@ -1081,8 +1099,26 @@ struct Lane1 {
                 cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
             }
         }
+        if (GP && (BEAMS == 0 || BEAMS == 3) && !m.free_motion) {
+            // trap oscillation: V(t) from the anchored cos/sin(ω t_a) by a rotation through ω τ (|ω τ| < 1e-2: series exact to 1e-18),
+            // then Δ_D, δ_D as in `coefficients`
+            const double cra = ab[7 * kstride], sra = ab[8 * kstride], cza = ab[16 * kstride], sza = ab[17 * kstride];
 #pragma unroll
-        for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
+            for (int n = 0; n < 5; ++n) {
+                const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
+                const double xr = m.wr * (tt - ta), xz = m.wz * (tt - ta), xr2 = xr * xr, xz2 = xz * xz;
+                const double cr_ = fma(xr2, fma(xr2, 1.0 / 24.0, -0.5), 1.0), sr_ = xr * fma(xr2, fma(xr2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                const double cz_ = fma(xz2, fma(xz2, 1.0 / 24.0, -0.5), 1.0), sz_ = xz * fma(xz2, fma(xz2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                const double cr = cra * cr_ - sra * sr_, sr = sra * cr_ + cra * sr_, cz = cza * cz_ - sza * sz_, sz = sza * cz_ + cza * sz_;
+                const double Vx = vx * cr - x0 * m.wr * sr, Vz = vzq * cz - z0 * m.wz * sz;
+                double Dd = m.aDx * Vx + m.aDz * Vz, dd = m.bDx * Vx + m.bDz * Vz;
+                if (m.doppler_z_legacy) { const double Vzt = vz * cz - z0 * m.wz * sz; Dd = m.aDz * Vzt; dd = m.bDz * Vzt; }
+                cb[(n * 6 + 4) * kstride] = m.Delta0 - m.dsign * Dd; cb[(n * 6 + 5) * kstride] = m.delta0 - m.dsign * dd;
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
+        }
         // Gaussian pair: every |di| < 6e-3 (di⁶/720 < 7e-17), |dr| < 3e-4 (dr⁴/24 < 4e-16); else |di| < 0.1 (di¹⁰/3.6e6 < 3e-17), |dr| < 5e-3 (dr⁷/5040 < 2e-20)
         return worst < (GP ? 3.6e-5 : 1e-2);
     }
@@ -1097,7 +1133,7 @@ struct Lane1 {
                 if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
                 ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
             }
-            const bool gp = BEAMS == 1 ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
+            const bool gp = (BEAMS == 1 || BEAMS == 3) ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
             if (refresh || !(tn <= ab[19 * kstride]) || tt0 < ab[18 * kstride]) {   // two steps of headroom over the re-anchoring cadence
                 if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
                 else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);

@@ -465,12 +465,16 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     if (n_all > 0) {
         const int ns = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
         // the anchored-coefficient code of the NS = 9 kernel is compiled per beam class (all points Gaussian pairs / none / mixed sweep)
-        int n_gp = 0;
-        for (int p = 0; p < n_points; ++p) n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
+        int n_gp = 0, n_free = 0;
+        for (int p = 0; p < n_points; ++p) {
+            n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
+            n_free += dm[p].free_motion != 0;
+        }
         if (ns == 9) {
-            if (n_gp == n_points) rc = sweep ? launch_lindblad1<9, true, 1>(c, P, grid) : launch_lindblad1<9, false, 1>(c, P, grid);
-            else if (n_gp == 0) rc = sweep ? launch_lindblad1<9, true, 2>(c, P, grid) : launch_lindblad1<9, false, 2>(c, P, grid);
-            else rc = launch_lindblad1<9, true, 0>(c, P, grid);
+            if (n_gp == n_points && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 1>(c, P, grid) : launch_lindblad1<9, false, 1>(c, P, grid);
+            else if (n_gp == 0 && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 2>(c, P, grid) : launch_lindblad1<9, false, 2>(c, P, grid);
+            else if (n_gp == n_points && n_free == 0) rc = sweep ? launch_lindblad1<9, true, 3>(c, P, grid) : launch_lindblad1<9, false, 3>(c, P, grid);
+            else rc = sweep ? launch_lindblad1<9, true, 0>(c, P, grid) : launch_lindblad1<9, false, 0>(c, P, grid);
         } else if (ns == 15) rc = sweep ? launch_lindblad1<15, true, 0>(c, P, grid) : launch_lindblad1<15, false, 0>(c, P, grid);
         else rc = sweep ? launch_lindblad1<21, true, 0>(c, P, grid) : launch_lindblad1<21, false, 0>(c, P, grid);
         if (rc) return rc;
