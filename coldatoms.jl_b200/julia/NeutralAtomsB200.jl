@@ -240,6 +240,49 @@ function ϕ(tspan, f, amplitudes)
     return out
 end
 
+"""
+`get_rydberg_infidelity(cfg; U, states, n_samples, ode_kwargs...)` -- src/fidelity.jl:67-95 with the 5 configurations x
+`length(states)` initial states batched into ONE `ca_rydberg1_sweep` launch per trajectory-count group (instead of 30 serial
+ensembles).  Returns the same `Dict(name => infidelity)`.
+"""
+function get_rydberg_infidelity(cfg::NeutralAtoms.RydbergConfig;
+        U = NeutralAtoms.dense(NeutralAtoms.identityoperator(cfg.ψ0.basis)),
+        states = NeutralAtoms.basis_fidelity_states, n_samples = 100, ode_kwargs...)
+    configs = NeutralAtoms.get_rydberg_fidelity_configs(cfg, n_samples)
+    names = collect(keys(configs))
+    points = [(name, configs[name], st) for name in names for st in states]
+    ρend = Vector{Matrix{ComplexF64}}(undef, length(points))
+    seed = next_seed(); offset = 0
+    f, ar, ab = Float64.(cfg.f), Float64.(cfg.red_laser_phase_amplitudes), Float64.(cfg.blue_laser_phase_amplitudes)
+    for n in sort(unique([c.n_samples for (_, c, _) in points]))
+        idx = [i for (i, (_, c, _)) in enumerate(points) if c.n_samples == n]
+        models = [model(points[i][2]) for i in idx]
+        psis = reduce(vcat, [ComplexF64.(points[i][3].data) for i in idx])
+        tends = Float64[points[i][2].tspan[end] for i in idx]
+        ρ = zeros(ComplexF64, 25 * length(idx)); ρ2 = similar(ρ)
+        st = CaStats()
+        GC.@preserve models psis tends f ar ab check(ccall(sym(:ca_rydberg1_sweep), Cint,
+            (Ptr{Cvoid}, Ptr{CaModel}, Ptr{ComplexF64}, Ptr{Float64}, Int32, Int64, Int64, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
+            CTX[], models, psis, tends, length(idx), n, offset, 0, seed, f, ar, ab, length(f), ode(; ode_kwargs...), 0, ρ, ρ2, st))
+        for (k, i) in enumerate(idx)
+            ρend[i] = reshape(ρ[(k-1)*25+1:k*25], 5, 5)
+        end
+        offset += n * length(idx)
+    end
+    infidelities = Dict()
+    for name in names
+        acc = 0.0
+        for (i, (nm, _, st)) in enumerate(points)
+            nm == name || continue
+            ψ = (U * st).data
+            acc += 1.0 - real(ψ' * ρend[i] * ψ)
+        end
+        infidelities[name] = acc / length(states)
+    end
+    return infidelities
+end
+
 "Route the reference's own entry points through the GPU path (fidelity.jl and user scripts keep working unchanged)."
 function override!()
     @eval NeutralAtoms begin
