@@ -16,6 +16,7 @@ CA_COMPAT_VZ_FROM_VY = 1
 CA_COMPAT_DEFAULT = CA_COMPAT_VZ_FROM_VY
 CA_RHO2_MATSQ, CA_RHO2_ABS2 = 0, 1
 CA_OUT_MEAN, CA_OUT_SUMS, CA_OUT_DEVICE = 0, 1, 2
+CA_AVG_TWOPHOTON, CA_AVG_RM6 = 0, 1
 
 # Philox stream ids (shared by the device sampler and the oracle)
 STREAM_ATOM1, STREAM_ATOM2, STREAM_RED1, STREAM_BLUE1, STREAM_RED2, STREAM_BLUE2 = range(6)

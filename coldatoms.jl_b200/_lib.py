@@ -22,7 +22,7 @@ _lock = threading.Lock()
 EXPORTS = [
     "ca_version", "ca_last_error", "ca_init", "ca_finalize", "ca_set_stream", "ca_reset_stream", "ca_synchronize",
     "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg1_sweep", "ca_release_recapture",
-    "ca_sample_atoms", "ca_sample_atoms_metropolis", "ca_phase_noise", "ca_eval_beam",
+    "ca_sample_atoms", "ca_sample_atoms_metropolis", "ca_phase_noise", "ca_eval_beam", "ca_thermal_average",
 ]
 
 
@@ -226,6 +226,16 @@ class Context:
         _check(load().ca_phase_noise(self._h, _p(tnodes), C.c_int32(len(tnodes)), _p(f), _p(amp), C.c_int32(len(f)), C.c_int64(n),
                                      C.c_int64(traj_offset), C.c_uint64(seed), C.c_int32(stream), _p(phases), _p(out)))
         return out
+
+    def thermal_average(self, kind, model, n, traj_offset=0, seed=_abi.DEFAULT_SEED, eps=1e-2, samples1=None, samples2=None):
+        """Device-reduced SUMS of the calibrate_two_photon / get_blockade_stark_shift_factor functionals (ca_thermal_average)."""
+        samples1 = _arr(samples1, (n, 6)) if samples1 is not None else None
+        samples2 = _arr(samples2, (n, 6)) if samples2 is not None else None
+        sums = np.zeros(2)
+        att = C.c_int64()
+        _check(load().ca_thermal_average(self._h, C.c_int32(kind), C.byref(model), C.c_int64(n), C.c_int64(traj_offset), C.c_uint64(seed),
+                                         C.c_double(eps), _p(samples1), _p(samples2), _p(sums), C.byref(att)))
+        return sums, att.value
 
     def eval_beam(self, beam, xyz):
         xyz = _arr(xyz, (-1, 3))

@@ -163,29 +163,21 @@ def HG_coeff(k, n):
 # ---------------------------------------------------------------------------------------------------------
 # one-atom ensemble
 # ---------------------------------------------------------------------------------------------------------
-def calibrate_two_photon(cfg, n_samples=1000, seed=None, device=None):
-    """`calibrate_two_photon` (src/rydberg_model.jl:285-306): host pre-pass over 1000 thermal samples."""
-    from .physics import A, A_phase
+def calibrate_two_photon(cfg, n_samples=1000, seed=None, device=None, samples=None):
+    """`calibrate_two_photon` (src/rydberg_model.jl:285-306).  The two sample loops (:293, :300) are device reductions
+    (`ca_thermal_average`, CA_AVG_TWOPHOTON) over the same thermal ensemble: Philox-drawn on the device, or host `samples[n,6]`."""
+    from .config import model_from_config
+    ctx = _lib.default_context(device)
+    sd = _next_seed(seed)
     c = cfg.copy()
     Ωr, Ωb = cfg.red_laser_params[0], cfg.blue_laser_params[0]
-    s, _ = samples_generate(cfg.trap_params, cfg.atom_params, n_samples, seed=seed, device=device)
-    x, y, z, vx, vz = s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 5]
-
-    def Om(p):
-        Ω0, w0, z0, θ, _n = p
-        return Ω0 * A(x, y, z, w0, z0, n=1, θ=θ) * A_phase(x, y, z, w0, z0, θ=θ)
-
-    def Dop(p):
-        w0, z0, θ = p[1:4]
-        k = 2.0 * z0 / w0 ** 2
-        return k * math.sin(θ) * vx + k * math.cos(θ) * vz
-
-    Ω2 = np.abs(Om(c.blue_laser_params) * Om(c.red_laser_params) / (2.0 * Dop(c.red_laser_params)))
-    factor = math.sqrt(float(np.mean(Ω2)) / Ω_twophoton(Ωr, Ωb, cfg.detuning_params[0]))
+    n = n_samples if samples is None else len(samples)
+    sums, _ = ctx.thermal_average(_abi.CA_AVG_TWOPHOTON, model_from_config(c), n, seed=sd, samples1=samples)
+    factor = math.sqrt((sums[0] / n) / Ω_twophoton(Ωr, Ωb, cfg.detuning_params[0]))
     c.red_laser_params[0] = Ωr / factor
     c.blue_laser_params[0] = Ωb / factor
-    δs = (np.abs(Om(c.red_laser_params)) ** 2 - np.abs(Om(c.blue_laser_params)) ** 2) / (4.0 * Dop(c.red_laser_params))
-    c.detuning_params[1] += float(np.mean(δs)) - δ_twophoton(Ωr, Ωb, cfg.detuning_params[0])
+    sums, _ = ctx.thermal_average(_abi.CA_AVG_TWOPHOTON, model_from_config(c), n, seed=sd, samples1=samples)
+    c.detuning_params[1] += sums[1] / n - δ_twophoton(Ωr, Ωb, cfg.detuning_params[0])
     return c
 
 
@@ -284,15 +276,21 @@ def simulation_czlp(cfg: CZLPConfig, seed=None, device=None, distributed=False, 
     return ρ, ρ2
 
 
-def get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples=10000, seed=None, device=None):
-    """src/cz_model.jl:77-104: thermal mean of R^-6 -> -Ω / (2 c6 <R^-6>)."""
+def get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples=10000, seed=None, device=None,
+                                    samples1=None, samples2=None):
+    """src/cz_model.jl:77-104: thermal mean of R^-6 -> -Ω / (2 c6 <R^-6>); the map/mean of :101 is a device reduction
+    (`ca_thermal_average`, CA_AVG_RM6) over Philox-drawn pairs (streams atom1/atom2) or host `samples1/2[n,6]`."""
     ctx = _lib.default_context(device)
-    sd = _next_seed(seed)
-    s1, _ = ctx.sample_atoms(trap_params, atom_params, n_samples, seed=sd, stream=_abi.STREAM_ATOM1)
-    s2, _ = ctx.sample_atoms(trap_params, atom_params, n_samples, seed=sd, stream=_abi.STREAM_ATOM2)
-    d = (s1[:, :3] + np.asarray(atom_centers[0])) - (s2[:, :3] + np.asarray(atom_centers[1]))
-    Rm6 = float(np.mean(1.0 / (1e-18 + np.sum(d ** 2, axis=1) ** 3)))
-    return -Ω / (2.0 * c6 * Rm6)
+    m = _abi.ca_model()
+    m.atom_m, m.atom_T = map(float, atom_params)
+    m.trap_U0, m.trap_w0, m.trap_z0 = map(float, trap_params)
+    m.red.kind = m.blue.kind = _abi.CA_BEAM_UNIFORM
+    m.blue.w0 = m.blue.z0 = 1.0
+    m.center1[:] = [float(v) for v in atom_centers[0]]
+    m.center2[:] = [float(v) for v in atom_centers[1]]
+    n = n_samples if samples1 is None else len(samples1)
+    sums, _ = ctx.thermal_average(_abi.CA_AVG_RM6, m, n, seed=_next_seed(seed), samples1=samples1, samples2=samples2)
+    return -Ω / (2.0 * c6 * (sums[0] / n))
 
 
 # ---------------------------------------------------------------------------------------------------------

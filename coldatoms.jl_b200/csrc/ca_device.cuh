@@ -485,6 +485,31 @@ CA_HD int sample_atom_literal(const SamplerConsts& sc, uint64_t seed, uint64_t i
     return -1;
 }
 
+// Thermal averages of scalar functionals of one sampled atom / atom pair.
+//   kind 0 (calibrate_two_photon, rydberg_model.jl:285-306): with Δ = the red beam's Doppler shift Δ(vx, vz, red) ALONE -- the
+//     reference passes it as the detuning of Ω_twophoton / δ_twophoton (:293, :300) --, |Ωr|, |Ωb| at the sampled position:
+//     o[0] = |Ωb Ωr / (2Δ)| (:267-269), o[1] = (|Ωr|² − |Ωb|²)/(4Δ) (:275-277).
+//   kind 1 (get_blockade_stark_shift_factor, cz_model.jl:77-104): o[0] = 1/(1e-18 + |r1 + c1 − r2 − c2|²·³) (:101).
+struct AvgConsts { DevBeam red, blue; double aDx, aDz; double center[2][3]; int kind; };
+CA_HD void thermal_terms(const AvgConsts& ac, const double* s1, const double* s2, double* o) {
+    if (ac.kind == 0) {
+        double rr, ri, br, bi;
+        beam_half_omega(ac.red, s1[0], s1[1], s1[2], 0.0, &rr, &ri);
+        beam_half_omega(ac.blue, s1[0], s1[1], s1[2], 0.0, &br, &bi);
+        const double r2 = 4.0 * (rr * rr + ri * ri), b2 = 4.0 * (br * br + bi * bi);   // |Ωr|², |Ωb|²
+        const double D = ac.aDx * s1[3] + ac.aDz * s1[5];
+        o[0] = sqrt(r2 * b2) / fabs(2.0 * D);
+        o[1] = (r2 - b2) / (4.0 * D);
+    } else {
+        const double dx = (s1[0] + ac.center[0][0]) - (s2[0] + ac.center[1][0]);
+        const double dy = (s1[1] + ac.center[0][1]) - (s2[1] + ac.center[1][1]);
+        const double dz = (s1[2] + ac.center[0][2]) - (s2[2] + ac.center[1][2]);
+        const double q = dx * dx + dy * dy + dz * dz;
+        o[0] = 1.0 / (1e-18 + q * q * q);
+        o[1] = 0.0;
+    }
+}
+
 // Metropolis branch of samples_generate (atom_sampler.jl:97-120) as MANY independent chains: chain c starts at the
 // reference's initial state, burns `skip` transitions in and then emits every freq-th state; its k-th sample is global
 // sample c + k*n_chains.  One chain (n_chains = 1) is exactly the reference algorithm.  RNG: Philox(seed; index =

@@ -279,6 +279,50 @@ __global__ void k_eval_beam(DevBeam b, const double* __restrict__ xyz, long long
     out[2 * i] = 2.0 * re; out[2 * i + 1] = 2.0 * im;
 }
 
+// Thermal averages (calibrate_two_photon rydberg_model.jl:285-306, get_blockade_stark_shift_factor cz_model.jl:77-104): grid-stride
+// over samples (device-drawn with the same Philox streams as the ensembles, or host-supplied), per-thread partial sums in index
+// order, fixed-order block reduction -> partials[block][2]; k_sum_partials adds the blocks in order, so a given (n, grid) is
+// bit-reproducible and shards of one ensemble add up.
+__global__ void __launch_bounds__(128) k_thermal_avg(AvgConsts ac, SamplerConsts sc, long long n, long long traj_offset, unsigned long long seed,
+                                                     const double* __restrict__ s1_in, const double* __restrict__ s2_in,
+                                                     double* __restrict__ partials, unsigned long long* __restrict__ attempts) {
+    __shared__ double red[4][2];
+    double a0 = 0.0, a1 = 0.0;
+    long long att = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double s1[6], s2[6] = {0, 0, 0, 0, 0, 0}, o[2];
+        if (s1_in) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) s1[q] = s1_in[i * 6 + q];
+        } else att += sample_atom_literal(sc, seed, (uint64_t)(traj_offset + i), 0u, s1);
+        if (ac.kind == 1) {
+            if (s2_in) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s2[q] = s2_in[i * 6 + q];
+            } else att += sample_atom_literal(sc, seed, (uint64_t)(traj_offset + i), 1u, s2);
+        }
+        thermal_terms(ac, s1, s2, o);
+        a0 += o[0]; a1 += o[1];
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    const double fa = warp_sum((double)att);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { red[w][0] = a0; red[w][1] = a1; if (fa > 0) atomicAdd(attempts, (unsigned long long)fa); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+        partials[2 * blockIdx.x + 1] = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+    }
+}
+__global__ void k_sum_partials(const double* __restrict__ partials, int nb, double* __restrict__ out) {
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int b = 0; b < nb; ++b) s += partials[2 * b + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
 // FP64 FMA-chain microbenchmark: 8 independent chains per thread.
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -805,6 +849,43 @@ int ca_eval_beam(ca_ctx* c, const ca_beam* beam, const double* xyz, int64_t n, d
     CA_CUDA(cudaGetLastError());
     CA_CUDA(cudaMemcpyAsync(out, c->out.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CA_CUDA(cudaStreamSynchronize(c->stream));
+    return CA_OK;
+}
+
+int ca_thermal_average(ca_ctx* c, int32_t kind, const ca_model* model, int64_t n, int64_t traj_offset, uint64_t seed, double eps,
+                       const double* samples1, const double* samples2, double* sums_out, int64_t* attempts_out) {
+    if (!c || !model || n < 0 || !sums_out || (kind != CA_AVG_TWOPHOTON && kind != CA_AVG_RM6)) { set_error("bad argument"); return CA_ERR_ARG; }
+    if (kind == CA_AVG_RM6 && ((samples1 != nullptr) != (samples2 != nullptr))) { set_error("supply both sample sets or neither"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    DevModel d;
+    int rc = derive_model(*model, nullptr, 0, 0.0, 1.0, &d);
+    if (rc) return rc;
+    AvgConsts ac;
+    ac.red = d.red; ac.blue = d.blue; ac.aDx = d.aDx; ac.aDz = d.aDz; ac.kind = kind;
+    std::memcpy(ac.center, d.center, sizeof ac.center);
+    SamplerConsts sc;
+    for (int q = 0; q < 6; ++q) sc.sig[q] = d.sig[q];
+    sc.U0 = d.U0; sc.w0 = d.w0; sc.z0 = d.z0; sc.mfac = d.mfac; sc.ecut = d.U0 * (1.0 - (eps > 0 ? eps : 1e-2));
+    sums_out[0] = sums_out[1] = 0.0;
+    if (attempts_out) *attempts_out = 0;
+    if (n == 0) return CA_OK;
+    const double *d1 = nullptr, *d2 = nullptr;
+    if (samples1) { if ((rc = upload(c, c->in_samples, samples1, sizeof(double) * 6 * (size_t)n))) return rc; d1 = (const double*)c->in_samples.p; }
+    if (samples2 && kind == CA_AVG_RM6) { if ((rc = upload(c, c->in_ph[0], samples2, sizeof(double) * 6 * (size_t)n))) return rc; d2 = (const double*)c->in_ph[0].p; }
+    const int nb = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sm_count * 8);
+    if ((rc = c->misc.ensure(sizeof(double) * 2 * (size_t)(nb + 1)))) return rc;
+    if ((rc = c->counters.ensure(64))) return rc;
+    CA_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    double* part = (double*)c->misc.p;
+    k_thermal_avg<<<nb, 128, 0, c->stream>>>(ac, sc, n, traj_offset, seed, d1, d2, part, (unsigned long long*)c->counters.p);
+    CA_CUDA(cudaGetLastError());
+    k_sum_partials<<<1, 32, 0, c->stream>>>(part, nb, part + 2 * (size_t)nb);
+    CA_CUDA(cudaGetLastError());
+    unsigned long long att = 0;
+    CA_CUDA(cudaMemcpyAsync(sums_out, part + 2 * (size_t)nb, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaMemcpyAsync(&att, c->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    if (attempts_out) *attempts_out = (int64_t)att;
     return CA_OK;
 }
 

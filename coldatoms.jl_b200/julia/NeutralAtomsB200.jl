@@ -16,6 +16,8 @@
 #   release_recapture(tspan, trap_params, atom_params, N; ...)                   src/basic_experiments.jl:72-81
 #   samples_generate(trap_params, atom_params, N; harmonic=true, ...)            src/atom_sampler.jl:80-96
 #   ϕ(tspan, f, amplitudes)                                                      src/lasernoise_sampler.jl:31-37
+#   calibrate_two_photon(cfg, n_samples=1000)                                    src/rydberg_model.jl:285-306
+#   get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples=10000)   src/cz_model.jl:77-104
 # The ensemble loop (rydberg_model.jl:260-262, cz_model.jl:151), the samplers and every master_dynamic call run
 # inside ONE ccall.  There is no CUDA.jl fallback and no CPU fallback: if the library or a B200 is missing, init!
 # throws.  Julia is not available in the build container of this repository, so this file is exercised off-box
@@ -26,7 +28,8 @@ using NeutralAtoms
 using QuantumOptics
 using Libdl
 
-export simulation, simulation_czlp, simulation_blue_intens, release_recapture, samples_generate, ϕ
+export simulation, simulation_czlp, simulation_blue_intens, release_recapture, samples_generate, ϕ,
+       calibrate_two_photon, get_blockade_stark_shift_factor
 
 # ---- mirror of include/coldatoms_b200.h ---------------------------------------------------------------
 struct CaBeam
@@ -150,9 +153,43 @@ function run1(m::CaModel, tspan, ψ0data, n; samples = nothing, seed = next_seed
     return ρ, ρ2, st
 end
 
+# un-normalised device-reduced sums of the thermal-average functionals (ca_thermal_average)
+function thermal_sums(kind::Integer, m::CaModel, n::Integer; seed = next_seed())
+    sums = zeros(Float64, 2)
+    att = Ref{Int64}(0)
+    check(ccall(sym(:ca_thermal_average), Cint,
+        (Ptr{Cvoid}, Int32, Ref{CaModel}, Int64, Int64, UInt64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+        CTX[], kind, m, n, 0, seed, 1e-2, null(), null(), sums, att))
+    return sums
+end
+
+"`calibrate_two_photon(cfg, n_samples=1000)` -- src/rydberg_model.jl:285-306; the two sample loops (:293, :300) run on the device"
+function calibrate_two_photon(cfg::NeutralAtoms.RydbergConfig, n_samples = 1000)
+    c = deepcopy(cfg)
+    Ωr, Ωb = cfg.red_laser_params[1], cfg.blue_laser_params[1]
+    seed = next_seed()                      # one thermal ensemble for both loops, as in the reference
+    s = thermal_sums(0, model(c), n_samples; seed = seed)
+    factor = sqrt((s[1] / n_samples) / NeutralAtoms.Ω_twophoton(Ωr, Ωb, cfg.detuning_params[1]))
+    c.red_laser_params[1] = Ωr / factor
+    c.blue_laser_params[1] = Ωb / factor
+    s = thermal_sums(0, model(c), n_samples; seed = seed)
+    c.detuning_params[2] += s[2] / n_samples - NeutralAtoms.δ_twophoton(Ωr, Ωb, cfg.detuning_params[1])
+    return c
+end
+
+"`get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples=10000)` -- src/cz_model.jl:77-104"
+function get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples = 10000)
+    b = CaBeam(0.0, 1.0, 1.0, 0.0, 1.0, 1.0, BEAM_UNIFORM, 0, 0, 0, 0)
+    m = CaModel(atom_params[1], atom_params[2], trap_params[1], trap_params[2], trap_params[3], b, b, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,
+                1, 1, 0, 0, 0, DOPPLER_XZ, 0, SIGN_CZ, COMPAT_DEFAULT, 0, 1001, 0,
+                Tuple(Float64.(atom_centers[1])), Tuple(Float64.(atom_centers[2])), Float64(c6), 0.0)
+    Rm6 = thermal_sums(1, m, n_samples)[1] / n_samples
+    return -Ω / (2.0 * c6 * Rm6)
+end
+
 "`simulation(cfg::RydbergConfig; temperature_calibrate=false, ode_kwargs...)` -- src/rydberg_model.jl:194-265"
 function simulation(cfg::NeutralAtoms.RydbergConfig; temperature_calibrate = false, ode_kwargs...)
-    cfg_t = temperature_calibrate ? NeutralAtoms.calibrate_two_photon(cfg) : deepcopy(cfg)
+    cfg_t = temperature_calibrate ? calibrate_two_photon(cfg) : deepcopy(cfg)
     noise = cfg_t.laser_noise
     ρ, ρ2, _ = run1(model(cfg_t), cfg_t.tspan, cfg_t.ψ0.data, cfg_t.n_samples;
                     f = noise ? cfg_t.f : nothing, ar = noise ? cfg_t.red_laser_phase_amplitudes : nothing,
@@ -289,6 +326,9 @@ function override!()
         simulation(cfg::RydbergConfig; kw...) = Main.NeutralAtomsB200.simulation(cfg; kw...)
         simulation_czlp(cfg::CZLPConfig; kw...) = Main.NeutralAtomsB200.simulation_czlp(cfg; kw...)
         release_recapture(tspan, trap_params, atom_params, N; kw...) = Main.NeutralAtomsB200.release_recapture(tspan, trap_params, atom_params, N; kw...)
+        calibrate_two_photon(cfg::RydbergConfig, n_samples=1000) = Main.NeutralAtomsB200.calibrate_two_photon(cfg, n_samples)
+        get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples=10000) =
+            Main.NeutralAtomsB200.get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples)
     end
     return nothing
 end

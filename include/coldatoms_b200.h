@@ -13,6 +13,8 @@
  *   ca_sample_atoms_metropolis <- samples_generate (harmonic=false branch) src/atom_sampler.jl:97-120
  *   ca_phase_noise       <- ϕ                         src/lasernoise_sampler.jl:31-37
  *   ca_rydberg1_sweep    <- the (config, ψ0) loops of src/fidelity.jl:78-88 and BASELINE config 5
+ *   ca_thermal_average   <- the sample loops of calibrate_two_photon src/rydberg_model.jl:285-306 and
+ *                           get_blockade_stark_shift_factor src/cz_model.jl:77-104
  *
  * Conventions
  *   - plain C types only; the caller owns every host buffer, the library owns device memory
@@ -228,6 +230,23 @@ int ca_phase_noise(ca_ctx* ctx, const double* tnodes, int32_t n_nodes, const dou
  * out[i] = Ω(x[i],y[i],z[i]) as (re,im). */
 int ca_eval_beam(ca_ctx* ctx, const ca_beam* beam, const double* xyz /* n x 3 host */, int64_t n,
                  double* out /* n x 2 host */);
+
+/*
+ * Thermal averages of scalar functionals of the sampled atoms, reduced on the device (un-normalised SUMS over
+ * [traj_offset, traj_offset+n), so shards add and the caller divides by the ensemble size):
+ *   CA_AVG_TWOPHOTON  the two sample loops of calibrate_two_photon (src/rydberg_model.jl:293 and :300) for model->red/blue:
+ *       sums[0] = Σ Ω_twophoton(Ωr(x), Ωb(x), Δ(vx,vz,red)), sums[1] = Σ δ_twophoton(Ωr(x), Ωb(x), Δ(vx,vz,red))
+ *       (Δ is the red Doppler shift alone, as the reference passes it);
+ *   CA_AVG_RM6        the map/mean of get_blockade_stark_shift_factor (src/cz_model.jl:101) for model->center1/center2:
+ *       sums[0] = Σ 1/(1e-18 + |r1+c1-r2-c2|^6), sums[1] = 0.
+ * samples1/samples2: NULL -> Philox harmonic sampler (streams atom1/atom2, the ensembles' own), or host n x 6 arrays
+ * (samples2 only for CA_AVG_RM6).  eps <= 0 -> the sampler's default 1e-2 (atom_sampler.jl:80).
+ */
+#define CA_AVG_TWOPHOTON 0
+#define CA_AVG_RM6 1
+int ca_thermal_average(ca_ctx* ctx, int32_t kind, const ca_model* model, int64_t n, int64_t traj_offset,
+                       uint64_t seed, double eps, const double* samples1, const double* samples2,
+                       double* sums_out /* 2 host */, int64_t* attempts_out);
 
 #ifdef __cplusplus
 }

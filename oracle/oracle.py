@@ -187,3 +187,26 @@ def release_recapture(trap, atom, tspan, n, traj_offset=0, n_total=0, eps=1e-3, 
                                C.c_int64(n_total), C.c_double(eps), C.c_uint64(seed), _p(samples), C.c_int32(out_flags),
                                _p(probs), None if ind is None else ind.ctypes.data_as(C.POINTER(C.c_uint8)))
     return probs, ind
+
+
+# ---- thermal averages (numpy restatement of the reference's sample loops; the Ω values come from the C oracle's beam code) ----
+def doppler_red(vx, vz, beam):
+    """Δ(vx, vz, laser_params) -- src/rydberg_model.jl:77-84."""
+    k = 2.0 * beam.z0 / beam.w0 ** 2
+    return k * np.sin(beam.theta) * vx + k * np.cos(beam.theta) * vz
+
+
+def twophoton_terms(red, blue, samples):
+    """Per-sample Ω_twophoton and δ_twophoton as calibrate_two_photon evaluates them (src/rydberg_model.jl:293 and :300, with
+    Ω_twophoton :267-269 = abs(Ωb Ωr / 2Δ) and δ_twophoton :275-277 = (|Ωr|² − |Ωb|²)/4Δ; Δ = the red Doppler shift alone)."""
+    s = _arr(samples).reshape(-1, 6)
+    Or, Ob = eval_beam(red, s[:, :3]), eval_beam(blue, s[:, :3])
+    D = doppler_red(s[:, 3], s[:, 5], red)
+    return np.abs(Ob * Or / (2.0 * D)), (np.abs(Or) ** 2 - np.abs(Ob) ** 2) / (4.0 * D)
+
+
+def rm6_terms(samples1, samples2, centers):
+    """1/(1e-18 + sum((s1[1:3] - s2[1:3]).^2)^3) after the centre shifts -- src/cz_model.jl:98-101."""
+    s1 = _arr(samples1).reshape(-1, 6)[:, :3] + np.asarray(centers[0], float)
+    s2 = _arr(samples2).reshape(-1, 6)[:, :3] + np.asarray(centers[1], float)
+    return 1.0 / (1e-18 + np.sum((s1 - s2) ** 2, axis=1) ** 3)

@@ -242,5 +242,18 @@ double he_metropolis(const double* trap, const double* atom, long long N, long l
     return visited ? (double)acc / (double)visited : 0.0;
 }
 
+// thermal-average functionals of ca_device.cuh (thermal_terms) for n host-supplied samples: out[n][2]
+int he_thermal_terms(int kind, const ca_model* model, const double* s1, const double* s2, long long n, double* out) {
+    DevModel d;
+    int rc = derive_model(*model, nullptr, 0, 0.0, 1.0, &d);
+    if (rc) return rc;
+    AvgConsts ac;
+    ac.red = d.red; ac.blue = d.blue; ac.aDx = d.aDx; ac.aDz = d.aDz; ac.kind = kind;
+    std::memcpy(ac.center, d.center, sizeof ac.center);
+    const double zero[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = 0; i < n; ++i) thermal_terms(ac, s1 + 6 * i, s2 ? s2 + 6 * i : zero, out + 2 * i);
+    return 0;
+}
+
 const char* he_last_error() { return get_error(); }
 }

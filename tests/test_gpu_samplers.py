@@ -119,3 +119,56 @@ def test_metropolis_sampler_on_device(ctx, oracle, pkg):
     # empty input
     s0, _ = ctx.sample_atoms_metropolis(TRAP, ATOM, 0)
     assert s0.shape == (0, 6)
+
+
+def test_thermal_average_device_reduction_vs_reference_loops(ctx, pkg, oracle):
+    """ca_thermal_average against the numpy restatement of the reference's sample loops over the SAME Philox ensemble
+    (device-drawn) and over host-supplied samples; shards add up; the API mirrors reproduce calibrate_two_photon /
+    get_blockade_stark_shift_factor computed on the host from the oracle's samples (rydberg_model.jl:285-306, cz_model.jl:77-104)."""
+    cfg, cz = pkg.get_default_configs()
+    abi = pkg._abi
+    m = pkg.config.model_from_config(cfg)
+    n = 20000
+    s1, att1 = oracle.sample_atoms(cfg.trap_params, cfg.atom_params, n, seed=11, stream=0)
+    o2, d2 = oracle.twophoton_terms(m.red, m.blue, s1)
+    sums, att = ctx.thermal_average(abi.CA_AVG_TWOPHOTON, m, n, seed=11)
+    assert att == att1
+    # Σ 1/|Δ| is heavy-tailed: compare on the scale of Σ|terms|
+    assert abs(sums[0] - o2.sum()) < 1e-12 * o2.sum() and abs(sums[1] - d2.sum()) < 1e-12 * o2.sum()
+    sums_h, att_h = ctx.thermal_average(abi.CA_AVG_TWOPHOTON, m, n, samples1=s1)
+    assert att_h == 0 and abs(sums_h[0] - o2.sum()) < 1e-12 * o2.sum() and abs(sums_h[1] - d2.sum()) < 1e-12 * o2.sum()
+    a, _ = ctx.thermal_average(abi.CA_AVG_TWOPHOTON, m, 7000, traj_offset=0, seed=11)
+    b, _ = ctx.thermal_average(abi.CA_AVG_TWOPHOTON, m, n - 7000, traj_offset=7000, seed=11)
+    assert np.all(np.abs(a + b - sums) < 1e-12 * o2.sum())
+    again, _ = ctx.thermal_average(abi.CA_AVG_TWOPHOTON, m, n, seed=11)
+    assert np.array_equal(again, sums)   # fixed-order reduction: bit-reproducible
+
+    m2 = pkg.config.model_from_config(cz, two_atom=True)
+    t1, a1 = oracle.sample_atoms(cz.trap_params, cz.atom_params, n, seed=12, stream=0)
+    t2, a2 = oracle.sample_atoms(cz.trap_params, cz.atom_params, n, seed=12, stream=1)
+    ref = oracle.rm6_terms(t1, t2, cz.atom_centers)
+    sums, att = ctx.thermal_average(abi.CA_AVG_RM6, m2, n, seed=12)
+    assert att == a1 + a2 and abs(sums[0] / ref.sum() - 1) < 1e-12 and sums[1] == 0.0
+    sums_h, _ = ctx.thermal_average(abi.CA_AVG_RM6, m2, n, samples1=t1, samples2=t2)
+    assert abs(sums_h[0] / ref.sum() - 1) < 1e-12
+    with pytest.raises(pkg._lib.ColdAtomsError):
+        ctx.thermal_average(abi.CA_AVG_RM6, m2, n, samples1=t1)
+    assert np.array_equal(ctx.thermal_average(abi.CA_AVG_RM6, m2, 0)[0], [0.0, 0.0])
+
+    # API mirrors
+    Ω2 = pkg.Ω_twophoton(cfg.red_laser_params[0], cfg.blue_laser_params[0], cfg.detuning_params[0])
+    got = pkg.get_blockade_stark_shift_factor(cz.trap_params, cz.atom_params, cz.atom_centers, Ω2, cz.c6, n_samples=n, seed=12)
+    assert abs(got / (-Ω2 / (2.0 * cz.c6 * ref.mean())) - 1) < 1e-12
+    cal = pkg.calibrate_two_photon(cfg, n_samples=n, seed=11)
+    Ωr, Ωb = cfg.red_laser_params[0], cfg.blue_laser_params[0]
+    factor = np.sqrt(o2.mean() / Ω2)
+    assert abs(cal.red_laser_params[0] / (Ωr / factor) - 1) < 1e-12 and abs(cal.blue_laser_params[0] / (Ωb / factor) - 1) < 1e-12
+    mc = pkg.config.model_from_config(cal)
+    _, d2c = oracle.twophoton_terms(mc.red, mc.blue, s1)
+    want = cfg.detuning_params[1] + d2c.mean() - pkg.δ_twophoton(Ωr, Ωb, cfg.detuning_params[0])
+    assert abs(cal.detuning_params[1] - want) < 1e-12 * np.abs(o2).mean()
+    # the calibrated config runs through the ensemble entry point (temperature_calibrate=true, rydberg_model.jl:201-203)
+    cfg.tspan = np.linspace(0.0, 0.25, 3)
+    cfg.n_samples = 64
+    ρ, _ = pkg.simulation(cfg, temperature_calibrate=True, seed=11)
+    assert abs(np.trace(ρ[-1]).real - 1) < 1e-9

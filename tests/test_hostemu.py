@@ -232,3 +232,21 @@ def test_metropolis_chains_device_source_vs_oracle(pkg, oracle, he):
     for q in (0, 2, 3):
         assert abs(big[:, q].std() / long1[:, q].std() - 1) < 0.06, q
     assert abs(big[:, 3].std() / (0.09118367518929328 * np.sqrt(50 / 86.9091835)) - 1) < 0.04
+
+
+def test_thermal_average_functionals_device_source_vs_reference_loops(pkg, oracle, he):
+    """thermal_terms (ca_device.cuh) against the numpy restatement of calibrate_two_photon's and get_blockade_stark_shift_factor's
+    sample loops (src/rydberg_model.jl:293,300; src/cz_model.jl:98-101)."""
+    cfg, cz = pkg.get_default_configs()
+    m = pkg.config.model_from_config(cfg)
+    s1, _ = oracle.sample_atoms(cfg.trap_params, cfg.atom_params, 400, seed=5, stream=0)
+    out = np.zeros((400, 2))
+    assert he.he_thermal_terms(0, C.byref(m), P(s1), None, C.c_longlong(400), P(out)) == 0
+    o2, d2 = oracle.twophoton_terms(m.red, m.blue, s1)
+    # δ_twophoton is a cancelling difference (Ωr = Ωb on axis): its error is measured on the scale of each term, |Ωr Ωb / 2Δ|
+    assert np.abs(out[:, 0] / o2 - 1).max() < 1e-13 and (np.abs(out[:, 1] - d2) / o2).max() < 1e-13
+    m2 = pkg.config.model_from_config(cz, two_atom=True)
+    s2, _ = oracle.sample_atoms(cz.trap_params, cz.atom_params, 400, seed=5, stream=1)
+    assert he.he_thermal_terms(1, C.byref(m2), P(s1), P(s2), C.c_longlong(400), P(out)) == 0
+    ref = oracle.rm6_terms(s1, s2, cz.atom_centers)
+    assert np.abs(out[:, 0] / ref - 1).max() < 1e-14 and not out[:, 1].any()
