@@ -33,6 +33,13 @@ constexpr int kMaxModes = 17;  // flat-top orders up to 32
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10: counter = (traj_lo, traj_hi, draw, stream), key = (seed_lo, seed_hi)
 // ---------------------------------------------------------------------------------------------------
+// CA_NORM_SHORT: precision of the reciprocals / square roots inside the step-size controller's error norm (device code only).
+//   2 (default) raw MUFU seeds (relative error ~1e-6 in EEst², i.e. ~1e-7 in the next dt, the size the controller's single-precision
+//     log2/exp2 already has), 1 one refinement (~1e-11), 0 the full-precision rcp_d / sqrt_d.  The norm only steers the controller
+//     (accept iff EEst <= 1, next dt ~ EEst^-0.17); its serial sqrt -> rcp chains sat on every step's critical path.
+#ifndef CA_NORM_SHORT
+#define CA_NORM_SHORT 2
+#endif
 struct U4 { uint32_t x, y, z, w; };
 
 CA_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -130,6 +137,36 @@ CA_HD double rcp_d(double x) {  // 1/x for normal x (no special cases): MUFU see
     return fma(r, e, r);
 #else
     return 1.0 / x;
+#endif
+}
+// Short forms for the step-size controller's error norm only (relative error ~1e-11: one refinement of the MUFU seed).
+CA_HD double rcp_norm(double x) {
+#if defined(__CUDA_ARCH__) && CA_NORM_SHORT
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if CA_NORM_SHORT >= 2
+    return r;
+#else
+    return fma(r, fma(-x, r, 1.0), r);
+#endif
+#else
+    return rcp_d(x);
+#endif
+}
+CA_HD double sqrt_d(double x);
+CA_HD double sqrt_norm(double x) {
+#if defined(__CUDA_ARCH__) && CA_NORM_SHORT
+    if (!(x > 0.0)) return 0.0;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if CA_NORM_SHORT >= 2
+    return x * y;
+#else
+    const double g = x * y, h = 0.5 * y;
+    return fma(g, fma(-h, g, 0.5), g);
+#endif
+#else
+    return sqrt_d(x);
 #endif
 }
 CA_HD double sqrt_d(double x) {  // sqrt for x >= 0 (0 -> 0)
@@ -840,7 +877,7 @@ struct StepCtrl {
     // returns the factor dt/h
     CA_HD double accept(double EEst2) {
         if (EEst2 == 0.0) { reset(); return 10.0; }
-        const float l2E = 0.5f * lg2((float)EEst2);                                   // log2(EEst); -inf / +inf saturate in the clamp
+        const float l2E = 0.5f * lg2((float)EEst2);                                // log2(EEst); -inf / +inf saturate in the clamp
         float l2q = fmaf(0.17f, l2E, fmaf(-0.04f, l2q_old, 0.15200309f));             // - log2(0.9)
         l2q = fmaxf(-3.3219281f, fminf(2.3219281f, l2q));                             // q in [0.1, 5]
         l2q_old = fmaxf(l2E, -13.287712f);
@@ -885,6 +922,11 @@ struct Lane1 {
     int n_rhs, n_acc, n_rej, n_exact;     // n_exact: steps whose coefficients took the exact (generic / guard-failed) path
     int status;
 
+    // anchor time and end of the anchor's validity window (registers: the check at the top of every step must not wait for shared memory)
+    double anc_t0, anc_t1;
+    CA_HD void set_anchor_window(double a, double b) { anc_t0 = a; anc_t1 = b; }
+    CA_HD double anchor_t0() const { return anc_t0; }
+    CA_HD double anchor_t1() const { return anc_t1; }
     CA_HD double* kptr(int j) const {     // j = 1..7
         const int slot = (j == 1) ? p : ((j == 2 || j == 7) ? 1 - p : j - 1);
         return kb + (size_t)slot * NS * kstride;
@@ -1024,7 +1066,7 @@ struct Lane1 {
             }
             a[6 * kstride] = ph;
         }
-        ab[18 * kstride] = tt; ab[19 * kstride] = fma(3.0, H, tt);
+        set_anchor_window(tt, fma(3.0, H, tt));
     }
 
     // Exact anchor at time tt: c(tt) with its noise phase and the quadratic model of ln B on [tt, tt + 2H].
@@ -1064,10 +1106,12 @@ struct Lane1 {
                 const double b2 = 0.5 * (d2 - d1) * iH * iH;
                 a[(4 + c) * kstride] = b2;
                 win_ok = win_ok && fabs(d2 - d1) < 1e-6;
+                // Re δ(τ) = τ(b1 + τ b2) on the whole validity window 0 <= τ <= 2H: bounded here so that eval_anchored does not re-check it
+                if (c == 0) win_ok = win_ok && 2.0 * H * (fabs(a[2 * kstride]) + 2.0 * H * fabs(b2)) < 3e-4;
             }
             a[6 * kstride] = q == 0 ? pr : pb;
         }
-        ab[18 * kstride] = tt; ab[19 * kstride] = fma(2.0, H, tt);
+        set_anchor_window(tt, fma(2.0, H, tt));
         if ((BEAMS == 0 || BEAMS == 3) && !m.free_motion) {   // cos/sin(ω t_a) for the time-dependent Doppler shifts (the Gaussian layout leaves slots 7,8,16,17 free)
             double sr, cr, sz, cz;
             sincos_fast(m.wr * tt, &sr, &cr); sincos_fast(m.wz * tt, &sz, &cz);
@@ -1089,7 +1133,7 @@ struct Lane1 {
             pa[q] = a[6 * kstride];
             b3[q][0] = GP ? 0.0 : a[7 * kstride]; b3[q][1] = GP ? 0.0 : a[8 * kstride];
         }
-        const double ta = ab[18 * kstride];
+        const double ta = anchor_t0();
         double worst = 0.0;
 #pragma unroll
         for (int n = 0; n < 5; ++n) {
@@ -1108,8 +1152,9 @@ struct Lane1 {
                     dr = tau * fma(tau, fma(tau, b3[q][0], b2[q][0]), b1[q][0]);
                     di = fma(tau, fma(tau, fma(tau, b3[q][1], b2[q][1]), b1[q][1]), ph[q] - pa[q]);
                 }
-                worst = fma(di, di, fma(400.0 * dr, dr, worst));   // Σ (di² + (20 dr)²) >= max: one conservative guard per step
                 const double d2 = di * di;
+                if (GP) worst += d2;   // |Re δ| is bounded once per anchor (refresh_anchor); Σ di² >= max di² is the per-step guard
+                else worst = fma(400.0 * dr, dr, worst + d2);
                 if (GP) {
                     ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
                     cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
@@ -1159,7 +1204,7 @@ struct Lane1 {
                 ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
             }
             const bool gp = (BEAMS == 1 || BEAMS == 3) ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
-            if (refresh || !(tn <= ab[19 * kstride]) || tt0 < ab[18 * kstride]) {   // two steps of headroom over the re-anchoring cadence
+            if (refresh || !(tn <= anchor_t1()) || tt0 < anchor_t0()) {   // two steps of headroom over the re-anchoring cadence
                 if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
                 else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
             }
@@ -1181,19 +1226,19 @@ struct Lane1 {
     // error-norm contribution helpers (DiffEqBase: |err| / (atol + rtol max(|u0|,|u1|)), complex modulus)
     static CA_HD double nrm_real(double e, double a, double b, double atol, double rtol) {
         double sc = atol + rtol * fmax(fabs(a), fabs(b));
-        double r = e * rcp_d(sc);
+        double r = e * rcp_norm(sc);
         return r * r;
     }
     static CA_HD double nrm_cplx(double er, double ei, double ar, double ai, double br, double bi, double atol, double rtol) {
-        double sc = atol + rtol * sqrt_d(fmax(ar * ar + ai * ai, br * br + bi * bi));
-        double isc = rcp_d(sc);
+        double sc = atol + rtol * sqrt_norm(fmax(ar * ar + ai * ai, br * br + bi * bi));
+        double isc = rcp_norm(sc);
         return 2.0 * (er * er + ei * ei) * (isc * isc);  // both (i,j) and (j,i) entries of the full matrix
     }
 
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
                     double t0, double* kbase, int kstr, double* cbase, double* abase) {
         kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false;
-        if (ab) { ab[18 * kstride] = 1e300; ab[19 * kstride] = -1e300; }
+        if (ab) set_anchor_window(1e300, -1e300);
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
         vzq = m.vz_from_vy ? vy : vz;

@@ -514,6 +514,10 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
             n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
             n_free += dm[p].free_motion != 0;
         }
+#ifdef CA_FAST_BUILD   // developer builds (profiles/dev_fast.sh): only the R1 variant is compiled
+        if (ns == 9 && !sweep && n_gp == n_points && n_free == n_points) rc = launch_lindblad1<9, false, 1>(c, P, grid);
+        else { set_error("CA_FAST_BUILD: only the Gaussian-pair free-flight ket_1 variant is compiled"); rc = CA_ERR_UNSUPPORTED; }
+#else
         if (ns == 9) {
             if (n_gp == n_points && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 1>(c, P, grid) : launch_lindblad1<9, false, 1>(c, P, grid);
             else if (n_gp == 0 && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 2>(c, P, grid) : launch_lindblad1<9, false, 2>(c, P, grid);
@@ -521,6 +525,7 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
             else rc = sweep ? launch_lindblad1<9, true, 0>(c, P, grid) : launch_lindblad1<9, false, 0>(c, P, grid);
         } else if (ns == 15) rc = sweep ? launch_lindblad1<15, true, 0>(c, P, grid) : launch_lindblad1<15, false, 0>(c, P, grid);
         else rc = sweep ? launch_lindblad1<21, true, 0>(c, P, grid) : launch_lindblad1<21, false, 0>(c, P, grid);
+#endif
         if (rc) return rc;
         ++launches;
     }

@@ -474,7 +474,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 for (int s = 0; s < kS2; ++s) {
                     const double e = hh * fma(MC.e7, k7[s], er[s]);
                     const double yt = kb[(KB_YT * kS2 + s) * 32];
-                    const double isc = rcp_d(atol + rtol * sqrt_d(0.5 * fmax(y[s] * y[s] + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
+                    const double isc = rcp_norm(atol + rtol * sqrt_norm(0.5 * fmax(y[s] * y[s] + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
                     const bool eq = L.is_eq(s);
                     sacc += (e * e) * (isc * isc);
                     sdu += eq ? un[s] : 0.0; sde += eq ? e : 0.0;
@@ -482,7 +482,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 w.sum3(sacc, sdu, sde);
                 un_ll_new = tr0 - sdu;
                 {
-                    const double isc = rcp_d(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
+                    const double isc = rcp_norm(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
                     sacc += (sde * sde) * (isc * isc);   // err of ρ_ll,ll = -Σ err of the other diagonal entries
                 }
                 const double EEst2 = sacc * (1.0 / 625.0);

@@ -1,0 +1,42 @@
+"""A/B driver for developer builds (profiles/dev_fast.sh): runs the R1 workload once per library given on the command line, each in
+its own process, and prints kernel time, trajectories/s, RHS count and the largest deviation of rho(t) from the FIRST library's.
+    python profiles/ab.py n lib1.so lib2.so ..."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if len(sys.argv) > 2 and sys.argv[1] == "--child":
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    n = int(sys.argv[2])
+    cfg, _ = pkg.get_default_configs()
+    cfg.laser_noise = True
+    ctx = pkg._lib.default_context(0)
+    model = pkg.model_from_config(cfg)
+    best = None
+    for r in range(3):
+        rho, rho2, st = ctx.rydberg1_run(model, cfg.tspan, cfg.ψ0, n, seed=7, f=cfg.f, amp_red=cfg.red_laser_phase_amplitudes,
+                                         amp_blue=cfg.blue_laser_phase_amplitudes)
+        best = st["kernel_ms"] if best is None else min(best, st["kernel_ms"])
+    np.save(sys.argv[3], rho)
+    print("kernel_ms %.2f traj/s %.0f rhs/traj %.1f rej %d" % (best, n / best * 1e3, st["n_rhs"] / n, st["n_reject"]), flush=True)
+    sys.exit(0)
+
+n = int(sys.argv[1])
+ref = None
+for lib in sys.argv[2:]:
+    out = "/tmp/ab_%s.npy" % os.path.basename(lib)
+    env = dict(os.environ, COLDATOMS_B200_LIB=os.path.join(ROOT, lib))
+    r = subprocess.run([sys.executable, __file__, "--child", str(n), out], env=env, capture_output=True, text=True)
+    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + r.stderr[-300:]
+    dev = ""
+    if os.path.exists(out):
+        rho = np.load(out)
+        if ref is None:
+            ref = rho
+        dev = " max|drho| vs first %.2e" % np.abs(rho - ref).max()
+    print("%-28s %s%s" % (lib, line, dev), flush=True)
