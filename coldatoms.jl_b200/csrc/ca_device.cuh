@@ -40,6 +40,9 @@ constexpr int kMaxModes = 17;  // flat-top orders up to 32
 #ifndef CA_NORM_SHORT
 #define CA_NORM_SHORT 2
 #endif
+#ifndef CA_PREMUL_ST
+#define CA_PREMUL_ST 1
+#endif
 struct U4 { uint32_t x, y, z, w; };
 
 CA_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -906,8 +909,10 @@ struct Lane1 {
     // noise cache
     const double* tab;                    // table base for this lane: tab[(trace*n_nodes + node)*stride]
     int stride, jc;
-    double nr0, nr1, nr2, nb0, nb1, nb2;  // node values j, j+1 and the PREFETCHED j+2 of the red / blue trace
-    double tj, tnx;                       // time of node jc and of node jc+1 (+inf in the last interval)
+    double nr1, nr2, sr0, sr1, nb1, nb2, sb0, sb1;  // node values jc+1 and the PREFETCHED jc+2, slopes of the intervals [jc, jc+1] and [jc+1, jc+2] (red / blue trace)
+    double tmid, tnx, twend;              // time of node jc+1; the same, but +inf in the last interval (or without a table): the time at which the window
+                                          // advances; end of the two cached intervals (+inf without a table)
+    bool fastm;                           // fast_model(m), fixed per trajectory
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
@@ -917,7 +922,7 @@ struct Lane1 {
     double t, h, dt, tcommit;
     StepCtrl ctrl;
     double y[NS], un[NS];
-    double P[2], Pn[2], g1[2], g7[2], SD[2];
+    double P[2], Pn[2], SD[2];             // ρ00, ρll quadratures; SD = Σ_j d_j (ρpp, ρrr)(stage j) of the last accepted step (dense output)
     long long iters;
     int n_rhs, n_acc, n_rej, n_exact;     // n_exact: steps whose coefficients took the exact (generic / guard-failed) path
     int status;
@@ -963,30 +968,36 @@ struct Lane1 {
     // ---- phase noise: Gridded(Linear) on the node table (rydberg_model.jl:166-167) --------------------------------
     // The lane caches THREE consecutive nodes (jc, jc+1 and jc+2), i.e. two intervals: a step shorter than the node
     // spacing never leaves the window, so the window is advanced at most once per step (advance_window below).
-    CA_HD void window_at(const DevModel& m, double tt) {   // make tj <= tt < tnx
+    CA_HD void window_at(const DevModel& m, double tt) {   // make t_jc <= tt < tnx
         int j = (int)(tt * m.inv_dtn);
         j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
         if (j != jc) {
             const double* q0 = tab + (size_t)j * stride;
             const double* q1 = q0 + (size_t)m.n_nodes * stride;
-            if (j == jc + 1) { nr0 = nr1; nr1 = nr2; nb0 = nb1; nb1 = nb2; }
-            else { nr0 = q0[0]; nr1 = q0[stride]; nb0 = q1[0]; nb1 = q1[stride]; }
+            if (j == jc + 1) { sr0 = sr1; nr1 = nr2; sb0 = sb1; nb1 = nb2; }
+            else {
+                const double a0 = q0[0], b0 = q1[0];
+                nr1 = q0[stride]; nb1 = q1[stride];
+                sr0 = (nr1 - a0) * m.inv_dtn; sb0 = (nb1 - b0) * m.inv_dtn;
+            }
             const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
-            nr2 = q0[o2]; nb2 = q1[o2];   // prefetch: first used at the next advance
+            nr2 = q0[o2]; nb2 = q1[o2];   // prefetch: the node value is first needed at the next advance
+            sr1 = (nr2 - nr1) * m.inv_dtn; sb1 = (nb2 - nb1) * m.inv_dtn;   // (zero slope past the last node)
             jc = j;
         }
-        tj = j * m.dtn;
-        tnx = (j >= m.n_nodes - 2) ? 1e300 : (j + 1) * m.dtn;
+        tmid = (j + 1) * m.dtn;
+        tnx = (j >= m.n_nodes - 2) ? 1e300 : tmid;
+        twend = (j >= m.n_nodes - 2) ? 1e300 : tmid + m.dtn;
     }
-    CA_HD void phases_win(const DevModel& m, double tt, double& pr, double& pb) const {  // needs tj <= tt < tj + 2 dtn
-        pr = 0.0; pb = 0.0;
-        if (tab) {
-            const double w = (tt - tj) * m.inv_dtn;
-            const bool hi = !(tt < tnx);
-            const double w2 = hi ? w - 1.0 : w;
-            const double ra = hi ? nr1 : nr0, rb = hi ? nr2 : nr1, ba = hi ? nb1 : nb0, bb = hi ? nb2 : nb1;
-            pr = fma(w2, rb - ra, ra); pb = fma(w2, bb - ba, ba);
-        }
+    // Both cached intervals are anchored at their common node jc+1: φ(t) = φ_{jc+1} + (t - t_{jc+1}) · slope(left | right interval).
+    // Branch-free: without a table the node values and slopes stay zero (init), so the result is 0 for any finite tt.
+    CA_HD void phases_lin(const DevModel& m, double tt, double& pr, double& pb) const {  // needs t_jc <= tt < twend
+        const double dtm = tt - tmid;
+        const bool hi = !(tt < tnx);
+        pr = fma(dtm, hi ? sr1 : sr0, nr1); pb = fma(dtm, hi ? sb1 : sb0, nb1);
+    }
+    CA_HD void phases_win(const DevModel& m, double tt, double& pr, double& pb) const {
+        phases_lin(m, tt, pr, pb);
         if (m.xi != 0.0 && tt >= m.tau) pr += m.xi;
     }
     CA_HD void noise_at(const DevModel& m, double tt, double& pr, double& pb) const {   // stateless generic lookup
@@ -1026,7 +1037,7 @@ struct Lane1 {
     CA_HD void refresh_anchor_generic(const DevModel& m, double tt, double H) {
         double pr = 0.0, pb = 0.0;
         if (tab) {
-            if (!(tt < tnx) || tt < tj) window_at(m, tt);
+            if (!(tt < tnx) || tt < tmid - m.dtn) window_at(m, tt);
             phases_win(m, tt, pr, pb);
         }
         win_ok = true;
@@ -1073,7 +1084,7 @@ struct Lane1 {
     CA_HD void refresh_anchor(const DevModel& m, double tt, double H) {
         double pr = 0.0, pb = 0.0;
         if (tab) {
-            if (!(tt < tnx) || tt < tj) window_at(m, tt);
+            if (!(tt < tnx) || tt < tmid - m.dtn) window_at(m, tt);
             phases_win(m, tt, pr, pb);
         }
         win_ok = true;
@@ -1139,8 +1150,8 @@ struct Lane1 {
         for (int n = 0; n < 5; ++n) {
             const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
             const double tau = tt - ta;
-            double ph[2] = {0.0, 0.0};
-            if (tab) phases_win(m, tt, ph[0], ph[1]);
+            double ph[2];
+            phases_lin(m, tt, ph[0], ph[1]);   // fast_model() excludes the CZ phase jump (ξ = 0); no table -> zeros, no branch
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 // δ = ln B(t) - ln B(t_a) + i (φ(t) - φ(t_a)) = dr + i di ;  e^δ = e^{dr} (cos di + i sin di) by short real series
@@ -1197,18 +1208,24 @@ struct Lane1 {
     // last) into the shared-memory buffer cb.  `refresh`: warp-uniform request to re-anchor now.
     CA_HD void stage_coefficients(const DevModel& m, double tt0, double hh, double tn, bool refresh) {
         bool done = false;
-        if (fast_model(m)) {
-            bool ok = true;
-            if (tab) {
-                if (!(tt0 < tnx) || tt0 < tj) window_at(m, tt0);
-                ok = tn < tj + 2.0 * m.dtn || jc >= m.n_nodes - 2;
-            }
+        if (fastm) {
             const bool gp = (BEAMS == 1 || BEAMS == 3) ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
-            if (refresh || !(tn <= anchor_t1()) || tt0 < anchor_t0()) {   // two steps of headroom over the re-anchoring cadence
-                if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
-                else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
+            // ONE decision on the common path: no re-anchoring requested, the anchor model still covers the step, the step lies inside the
+            // two cached noise intervals (time only moves forward, so only the upper ends are checked; a fresh trajectory starts with
+            // tnx = -inf and an empty anchor window and therefore takes the careful path below)
+            bool ok = !refresh && win_ok && tn <= anchor_t1() && tt0 < tnx && tn < twend;
+            if (!ok) {
+                ok = true;
+                if (tab) {
+                    if (!(tt0 < tnx) || tt0 < tmid - m.dtn) window_at(m, tt0);
+                    ok = tn < twend;
+                }
+                if (refresh || !(tn <= anchor_t1()) || tt0 < anchor_t0()) {   // two steps of headroom over the re-anchoring cadence
+                    if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
+                    else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
+                }
+                ok = ok && win_ok;
             }
-            ok = ok && win_ok;
             if (ok) done = gp ? eval_anchored<true>(m, tt0, hh, tn) : eval_anchored<false>(m, tt0, hh, tn);
         }
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
@@ -1237,7 +1254,7 @@ struct Lane1 {
 
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
                     double t0, double* kbase, int kstr, double* cbase, double* abase) {
-        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false;
+        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false; fastm = fast_model(m);
         if (ab) set_anchor_window(1e300, -1e300);
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
@@ -1247,7 +1264,7 @@ struct Lane1 {
             if (m.doppler_z_legacy) { Dd = m.aDz * vz; dd = m.bDz * vz; }
             dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
         }
-        tab = table; stride = tstride; jc = -5; nr0 = nr1 = nr2 = nb0 = nb1 = nb2 = 0.0; tj = 1e300; tnx = -1e300;
+        tab = table; stride = tstride; jc = -5; nr1 = nr2 = sr0 = sr1 = nb1 = nb2 = sb0 = sb1 = 0.0; tmid = 0.0; tnx = table ? -1e300 : 1e300; twend = 1e300;
         // initial state
         y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
         y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
@@ -1278,7 +1295,7 @@ struct Lane1 {
 #pragma unroll
             for (int i = 0; i < NS; ++i) k1p[i * kstride] = k1[i];
         }
-        g1[0] = g.G0 * y[2]; g1[1] = g.Gl * y[2] + g.Gr * y[1];
+        const double g1[2] = {g.G0 * y[2], g.Gl * y[2] + g.Gr * y[1]};
         n_rhs = 1;
 #pragma unroll
         for (int i = 0; i < NS; ++i) un[i] = y[i];
@@ -1331,7 +1348,7 @@ struct Lane1 {
         if (h != 0.0) {  // commit: y <- un, k1 <- k7 (slot toggle), t <- t+h
 #pragma unroll
             for (int i = 0; i < NS; ++i) y[i] = un[i];
-            P[0] = Pn[0]; P[1] = Pn[1]; g1[0] = g7[0]; g1[1] = g7[1];
+            P[0] = Pn[0]; P[1] = Pn[1];
             t = tcommit;
             h = 0.0;
             p ^= 1;
@@ -1344,11 +1361,23 @@ struct Lane1 {
         double us[NS], ko[NS];
         stage_coefficients(m, t, hh, tn, refresh);
         Coef cf;
-        // population quadratures: ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr, accumulated with the b/e/d weights
-        double SB0 = MC.rb[1] * g1[0], SB1 = MC.rb[1] * g1[1], SE0 = MC.re[1] * g1[0], SE1 = MC.re[1] * g1[1], SD0 = MC.rd[1] * g1[0],
-               SD1 = MC.rd[1] * g1[1];
+        // population quadratures ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr: the b/e/d-weighted sums of the STAGE VALUES of ρpp and ρrr are
+        // accumulated (the rates are applied once per step to the sums, not to every stage)
+        double SBp = MC.rb[1] * y[2], SBr = MC.rb[1] * y[1], SEp = MC.re[1] * y[2], SEr = MC.re[1] * y[1], SDp = MC.rd[1] * y[2],
+               SDr = MC.rd[1] * y[1];
 #pragma unroll
         for (int s = 2; s <= 6; ++s) {   // fully unrolled: tableau weights become constant-bank operands, slots immediates
+#if CA_PREMUL_ST
+#pragma unroll
+            for (int i = 0; i < NS; ++i) us[i] = y[i];
+#pragma unroll
+            for (int j = 1; j < s; ++j) {
+                const double w = hh * MC.ra[s][j];
+                const double* kp = kptr(j);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
+            }
+#else
 #pragma unroll
             for (int i = 0; i < NS; ++i) us[i] = 0.0;
 #pragma unroll
@@ -1360,16 +1389,16 @@ struct Lane1 {
             }
 #pragma unroll
             for (int i = 0; i < NS; ++i) us[i] = fma(hh, us[i], y[i]);
+#endif
             {
                 const double* o = cb + (size_t)(s - 2) * 6 * kstride;
                 cf.Ar = o[0]; cf.Ai = o[kstride]; cf.Br = o[2 * kstride]; cf.Bi = o[3 * kstride]; cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride];
             }
             lindblad_rhs<NS>(cf, g, us, ko);
             {
-                const double gg0 = g.G0 * us[2], gg1 = g.Gl * us[2] + g.Gr * us[1];
                 const double wb = MC.rb[s], we = MC.re[s], wd = MC.rd[s];
-                SB0 = fma(wb, gg0, SB0); SB1 = fma(wb, gg1, SB1); SE0 = fma(we, gg0, SE0); SE1 = fma(we, gg1, SE1);
-                SD0 = fma(wd, gg0, SD0); SD1 = fma(wd, gg1, SD1);
+                SBp = fma(wb, us[2], SBp); SBr = fma(wb, us[1], SBr); SEp = fma(we, us[2], SEp); SEr = fma(we, us[1], SEr);
+                SDp = fma(wd, us[2], SDp); SDr = fma(wd, us[1], SDr);
             }
             double* ks = kptr(s);
 #pragma unroll
@@ -1396,20 +1425,19 @@ struct Lane1 {
         {
             double* k7p = kptr(7);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { k7p[i * kstride] = ko[i]; er[i] = hh * fma(MC.re[7], ko[i], er[i]); }
+            for (int i = 0; i < NS; ++i) { k7p[i * kstride] = ko[i]; er[i] = fma(MC.re[7], ko[i], er[i]); }   // error / h (h² goes into EEst² once)
         }
-        g7[0] = g.G0 * un[2]; g7[1] = g.Gl * un[2] + g.Gr * un[1];
-        SE0 = fma(MC.re[7], g7[0], SE0); SE1 = fma(MC.re[7], g7[1], SE1); SD0 = fma(MC.rd[7], g7[0], SD0); SD1 = fma(MC.rd[7], g7[1], SD1);
-        Pn[0] = P[0] + hh * SB0; Pn[1] = P[1] + hh * SB1;
+        SEp = fma(MC.re[7], un[2], SEp); SEr = fma(MC.re[7], un[1], SEr); SDp = fma(MC.rd[7], un[2], SDp); SDr = fma(MC.rd[7], un[1], SDr);
+        Pn[0] = fma(hh * g.G0, SBp, P[0]); Pn[1] = fma(hh, fma(g.Gl, SBp, g.Gr * SBr), P[1]);
         n_rhs += 6;
         bool accept = true;
         if (oo.adaptive) {
-            double s = nrm_real(hh * SE0, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(hh * SE1, P[1], Pn[1], oo.atol, oo.rtol);
+            double s = nrm_real(g.G0 * SEp, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(fma(g.Gl, SEp, g.Gr * SEr), P[1], Pn[1], oo.atol, oo.rtol);
 #pragma unroll
             for (int i = 0; i < 3; ++i) s += nrm_real(er[i], y[i], un[i], oo.atol, oo.rtol);
 #pragma unroll
             for (int i = 3; i < NS; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
-            double EEst2 = s * (1.0 / 25.0);
+            double EEst2 = s * (hh * hh * (1.0 / 25.0));
             if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; return; }
             if (EEst2 <= 1.0) {
                 const double prop = hh * ctrl.accept(EEst2);
@@ -1427,7 +1455,7 @@ struct Lane1 {
         if (accept) {
             n_acc++;
             h = hh; tcommit = tn;
-            SD[0] = SD0; SD[1] = SD1;
+            SD[0] = SDp; SD[1] = SDr;
         }
     }
 
@@ -1451,9 +1479,11 @@ struct Lane1 {
                 s[i] = y[i] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
             }
             {
-                double r2 = Pn[0] - P[0], r3 = h * g1[0] - r2, r4 = r2 - h * g7[0] - r3, r5 = h * SD[0];
+                // stage-1 / stage-7 derivatives and the d-weighted sums of the quadratures from ρpp, ρrr at the step ends and SD
+                const double g10 = m.G0 * y[2], g11 = m.Gl * y[2] + m.Gr * y[1], g70 = m.G0 * un[2], g71 = m.Gl * un[2] + m.Gr * un[1];
+                double r2 = Pn[0] - P[0], r3 = h * g10 - r2, r4 = r2 - h * g70 - r3, r5 = h * (m.G0 * SD[0]);
                 p0 = P[0] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
-                r2 = Pn[1] - P[1]; r3 = h * g1[1] - r2; r4 = r2 - h * g7[1] - r3; r5 = h * SD[1];
+                r2 = Pn[1] - P[1]; r3 = h * g11 - r2; r4 = r2 - h * g71 - r3; r5 = h * (m.Gl * SD[0] + m.Gr * SD[1]);
                 p1 = P[1] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
             }
         }
