@@ -879,7 +879,7 @@ struct StepCtrl {
     }
     // returns the factor dt/h
     CA_HD double accept(double EEst2) {
-        if (EEst2 == 0.0) { reset(); return 10.0; }
+        // EEst² = 0 needs no special case: log2(0) = -inf saturates both clamps (dt x 10, qold <- 1e-4), as any tiny value does
         const float l2E = 0.5f * lg2((float)EEst2);                                // log2(EEst); -inf / +inf saturate in the clamp
         float l2q = fmaf(0.17f, l2E, fmaf(-0.04f, l2q_old, 0.15200309f));             // - log2(0.9)
         l2q = fmaxf(-3.3219281f, fminf(2.3219281f, l2q));                             // q in [0.1, 5]
@@ -909,7 +909,7 @@ struct Lane1 {
     // noise cache
     const double* tab;                    // table base for this lane: tab[(trace*n_nodes + node)*stride]
     int stride, jc;
-    double nr1, nr2, sr0, sr1, nb1, nb2, sb0, sb1;  // node values jc+1 and the PREFETCHED jc+2, slopes of the intervals [jc, jc+1] and [jc+1, jc+2] (red / blue trace)
+    double nr1, nr2, nr3, sr0, sr1, nb1, nb2, nb3, sb0, sb1;  // node values jc+1, jc+2 and the PREFETCHED jc+3, slopes of the intervals [jc, jc+1] and [jc+1, jc+2] (red / blue trace)
     double tmid, tnx, twend;              // time of node jc+1; the same, but +inf in the last interval (or without a table): the time at which the window
                                           // advances; end of the two cached intervals (+inf without a table)
     bool fastm;                           // fast_model(m), fixed per trajectory
@@ -974,15 +974,17 @@ struct Lane1 {
         if (j != jc) {
             const double* q0 = tab + (size_t)j * stride;
             const double* q1 = q0 + (size_t)m.n_nodes * stride;
-            if (j == jc + 1) { sr0 = sr1; nr1 = nr2; sb0 = sb1; nb1 = nb2; }
+            const int last = m.n_nodes - 1;
+            if (j == jc + 1) { sr0 = sr1; nr1 = nr2; nr2 = nr3; sb0 = sb1; nb1 = nb2; nb2 = nb3; }   // nr3 / nb3 were requested one advance ago
             else {
                 const double a0 = q0[0], b0 = q1[0];
-                nr1 = q0[stride]; nb1 = q1[stride];
+                const int o2 = (j + 2 < last ? 2 : last - j) * stride;
+                nr1 = q0[stride]; nb1 = q1[stride]; nr2 = q0[o2]; nb2 = q1[o2];
                 sr0 = (nr1 - a0) * m.inv_dtn; sb0 = (nb1 - b0) * m.inv_dtn;
             }
-            const int o2 = (j + 2 < m.n_nodes ? 2 : 1) * stride;
-            nr2 = q0[o2]; nb2 = q1[o2];   // prefetch: the node value is first needed at the next advance
             sr1 = (nr2 - nr1) * m.inv_dtn; sb1 = (nb2 - nb1) * m.inv_dtn;   // (zero slope past the last node)
+            const int o3 = (j + 3 < last ? 3 : last - j) * stride;
+            nr3 = q0[o3]; nb3 = q1[o3];   // prefetch: first needed at the next advance, so nothing waits for this load
             jc = j;
         }
         tmid = (j + 1) * m.dtn;
@@ -1145,7 +1147,7 @@ struct Lane1 {
             b3[q][0] = GP ? 0.0 : a[7 * kstride]; b3[q][1] = GP ? 0.0 : a[8 * kstride];
         }
         const double ta = anchor_t0();
-        double worst = 0.0;
+        double worst[2] = {0.0, 0.0};   // one accumulator per beam: two short chains instead of one long one
 #pragma unroll
         for (int n = 0; n < 5; ++n) {
             const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
@@ -1164,8 +1166,8 @@ struct Lane1 {
                     di = fma(tau, fma(tau, fma(tau, b3[q][1], b2[q][1]), b1[q][1]), ph[q] - pa[q]);
                 }
                 const double d2 = di * di;
-                if (GP) worst += d2;   // |Re δ| is bounded once per anchor (refresh_anchor); Σ di² >= max di² is the per-step guard
-                else worst = fma(400.0 * dr, dr, worst + d2);
+                if (GP) worst[q] += d2;   // |Re δ| is bounded once per anchor (refresh_anchor); Σ di² >= max di² is the per-step guard
+                else worst[q] = fma(400.0 * dr, dr, worst[q] + d2);
                 if (GP) {
                     ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
                     cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
@@ -1201,7 +1203,7 @@ struct Lane1 {
             for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
         }
         // Gaussian pair: every |di| < 6e-3 (di⁶/720 < 7e-17), |dr| < 3e-4 (dr⁴/24 < 4e-16); else |di| < 0.1 (di¹⁰/3.6e6 < 3e-17), |dr| < 5e-3 (dr⁷/5040 < 2e-20)
-        return worst < (GP ? 3.6e-5 : 1e-2);
+        return worst[0] + worst[1] < (GP ? 3.6e-5 : 1e-2);
     }
 
     // Coefficients of the five distinct stage times of one step (c2..c5 and t+h; stage 7 and the next stage 1 share the
@@ -1264,7 +1266,7 @@ struct Lane1 {
             if (m.doppler_z_legacy) { Dd = m.aDz * vz; dd = m.bDz * vz; }
             dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
         }
-        tab = table; stride = tstride; jc = -5; nr1 = nr2 = sr0 = sr1 = nb1 = nb2 = sb0 = sb1 = 0.0; tmid = 0.0; tnx = table ? -1e300 : 1e300; twend = 1e300;
+        tab = table; stride = tstride; jc = -5; nr1 = nr2 = nr3 = sr0 = sr1 = nb1 = nb2 = nb3 = sb0 = sb1 = 0.0; tmid = 0.0; tnx = table ? -1e300 : 1e300; twend = 1e300;
         // initial state
         y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
         y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
@@ -1438,11 +1440,11 @@ struct Lane1 {
 #pragma unroll
             for (int i = 3; i < NS; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
             double EEst2 = s * (hh * hh * (1.0 / 25.0));
-            if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; return; }
-            if (EEst2 <= 1.0) {
+            if (EEst2 <= 1.0) {   // one decision on the common path; NaN and overflow fail it and are sorted out on the rare side
                 const double prop = hh * ctrl.accept(EEst2);
                 dt = clipped ? fmax(dt, prop) : prop;
             } else {
+                if (!(EEst2 <= 1e300)) { status = CA_ERR_NONFINITE; return; }
                 accept = false;
                 dt = hh * ctrl.reject(EEst2);
                 n_rej++;
