@@ -40,9 +40,6 @@ constexpr int kMaxModes = 17;  // flat-top orders up to 32
 #ifndef CA_NORM_SHORT
 #define CA_NORM_SHORT 2
 #endif
-#ifndef CA_PREMUL_ST
-#define CA_PREMUL_ST 1
-#endif
 struct U4 { uint32_t x, y, z, w; };
 
 CA_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -872,9 +869,20 @@ struct StepCtrl {
     CA_HD void reset() { l2q_old = -13.287712f; }   // log2(1e-4)
     static CA_HD float lg2(float x) {
 #if defined(__CUDA_ARCH__)
-        return __log2f(x);
+        float r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // EEst² below 1e-38 flushes to log2(0) = -inf, which the clamps saturate like any tiny value
+        return r;
 #else
         return log2f(x);
+#endif
+    }
+    static CA_HD float ex2(float x) {   // |x| <= 3.33 here: no denormal range to handle
+#if defined(__CUDA_ARCH__)
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+#else
+        return exp2f(x);
 #endif
     }
     // returns the factor dt/h
@@ -884,12 +892,22 @@ struct StepCtrl {
         float l2q = fmaf(0.17f, l2E, fmaf(-0.04f, l2q_old, 0.15200309f));             // - log2(0.9)
         l2q = fmaxf(-3.3219281f, fminf(2.3219281f, l2q));                             // q in [0.1, 5]
         l2q_old = fmaxf(l2E, -13.287712f);
-        return (double)exp2f(-l2q);
+        return (double)ex2(-l2q);
     }
     CA_HD double reject(double EEst2) const {
         const float l2E = 0.5f * lg2((float)EEst2);
         const float l2q = fminf(2.3219281f, fmaf(0.17f, l2E, 0.15200309f));
-        return (double)exp2f(-l2q);
+        return (double)ex2(-l2q);
+    }
+    // Both outcomes from one log2, selected by `acc`, with no branch between the error norm and the new dt (the caller decides
+    // `acc` in double while the conversion and the two MUFU operations are already in flight).
+    CA_HD double decide(double EEst2, bool acc) {
+        const float l2E = 0.5f * lg2((float)EEst2);
+        const float base = fmaf(0.17f, l2E, 0.15200309f);
+        const float qa = fmaxf(-3.3219281f, fminf(2.3219281f, fmaf(-0.04f, l2q_old, base)));
+        const float qr = fminf(2.3219281f, base);
+        l2q_old = acc ? fmaxf(l2E, -13.287712f) : l2q_old;
+        return (double)ex2(-(acc ? qa : qr));
     }
 };
 
@@ -923,7 +941,7 @@ struct Lane1 {
     StepCtrl ctrl;
     double y[NS], un[NS];
     double P[2], Pn[2], SD[2];             // ρ00, ρll quadratures; SD = Σ_j d_j (ρpp, ρrr)(stage j) of the last accepted step (dense output)
-    long long iters;
+    unsigned iters_left;                  // attempts left before CA_ERR_MAXITERS (maxiters clamped to 2^32-1)
     int n_rhs, n_acc, n_rej, n_exact;     // n_exact: steps whose coefficients took the exact (generic / guard-failed) path
     int status;
 
@@ -932,6 +950,8 @@ struct Lane1 {
     CA_HD void set_anchor_window(double a, double b) { anc_t0 = a; anc_t1 = b; }
     CA_HD double anchor_t0() const { return anc_t0; }
     CA_HD double anchor_t1() const { return anc_t1; }
+    // a failed trajectory parks at tcommit = +inf, so that the step loop's only test is tcommit < T
+    CA_HD void fail(int code) { status = code; tcommit = 1e300; }
     CA_HD double* kptr(int j) const {     // j = 1..7
         const int slot = (j == 1) ? p : ((j == 2 || j == 7) ? 1 - p : j - 1);
         return kb + (size_t)slot * NS * kstride;
@@ -1286,7 +1306,7 @@ struct Lane1 {
             y[19] = m.rho0[5 + 18]; y[20] = -m.rho0[5 + 19];
         }
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
-        t = t0; tcommit = t0; h = 0.0; iters = 0; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
+        t = t0; tcommit = t0; h = 0.0; iters_left = oo.maxiters > 0xffffffffLL ? 0xffffffffu : (unsigned)oo.maxiters; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
         ctrl.reset();
         double k1[NS];
         Coef cf0;
@@ -1355,7 +1375,7 @@ struct Lane1 {
             h = 0.0;
             p ^= 1;
         }
-        if (++iters > oo.maxiters) { status = CA_ERR_MAXITERS; return; }
+        if (iters_left-- == 0u) { fail(CA_ERR_MAXITERS); return; }
         double hh = fmin(dt, oo.dtmax);
         bool clipped = false;
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
@@ -1369,7 +1389,7 @@ struct Lane1 {
                SDr = MC.rd[1] * y[1];
 #pragma unroll
         for (int s = 2; s <= 6; ++s) {   // fully unrolled: tableau weights become constant-bank operands, slots immediates
-#if CA_PREMUL_ST
+            // y + Σ_j (h a_sj) k_j with the weights scaled once per stage: s-1 multiplications instead of NS
 #pragma unroll
             for (int i = 0; i < NS; ++i) us[i] = y[i];
 #pragma unroll
@@ -1379,19 +1399,6 @@ struct Lane1 {
 #pragma unroll
                 for (int i = 0; i < NS; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
             }
-#else
-#pragma unroll
-            for (int i = 0; i < NS; ++i) us[i] = 0.0;
-#pragma unroll
-            for (int j = 1; j < s; ++j) {
-                const double w = MC.ra[s][j];
-                const double* kp = kptr(j);
-#pragma unroll
-                for (int i = 0; i < NS; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < NS; ++i) us[i] = fma(hh, us[i], y[i]);
-#endif
             {
                 const double* o = cb + (size_t)(s - 2) * 6 * kstride;
                 cf.Ar = o[0]; cf.Ai = o[kstride]; cf.Br = o[2 * kstride]; cf.Bi = o[3 * kstride]; cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride];
@@ -1440,19 +1447,19 @@ struct Lane1 {
 #pragma unroll
             for (int i = 3; i < NS; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
             double EEst2 = s * (hh * hh * (1.0 / 25.0));
-            if (EEst2 <= 1.0) {   // one decision on the common path; NaN and overflow fail it and are sorted out on the rare side
-                const double prop = hh * ctrl.accept(EEst2);
-                dt = clipped ? fmax(dt, prop) : prop;
-            } else {
-                if (!(EEst2 <= 1e300)) { status = CA_ERR_NONFINITE; return; }
+            const bool acc = EEst2 <= 1.0;                 // NaN and overflow fail it and are sorted out on the rare side
+            const double prop = hh * ctrl.decide(EEst2, acc);
+            const bool keep = acc && clipped && dt > prop;   // a step clipped at tstop does not shrink the running step size
+            dt = keep ? dt : prop;
+            if (!acc) {
+                if (!(EEst2 <= 1e300)) { fail(CA_ERR_NONFINITE); return; }
                 accept = false;
-                dt = hh * ctrl.reject(EEst2);
                 n_rej++;
-                if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; return; }
+                if (dt < 1e-14 * fmax(1.0, fabs(t))) { fail(CA_ERR_NONFINITE); return; }
             }
         } else {
             dt = oo.dt0;
-            if (!(fabs(un[0] + un[1] + un[2]) < 1e300)) { status = CA_ERR_NONFINITE; return; }   // fixed step beyond the stability limit
+            if (!(fabs(un[0] + un[1] + un[2]) < 1e300)) { fail(CA_ERR_NONFINITE); return; }   // fixed step beyond the stability limit
         }
         if (accept) {
             n_acc++;

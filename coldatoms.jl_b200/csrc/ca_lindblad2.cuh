@@ -486,13 +486,13 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                     sacc += (sde * sde) * (isc * isc);   // err of ρ_ll,ll = -Σ err of the other diagonal entries
                 }
                 const double EEst2 = sacc * (1.0 / 625.0);
-                if (!(EEst2 == EEst2) || EEst2 > 1e300) { status = CA_ERR_NONFINITE; break; }
-                if (EEst2 <= 1.0) {
-                    const double prop = hh * ctrl.accept(EEst2);
-                    dt = clipped ? fmax(dt, prop) : prop;
-                } else {
+                const bool acc = EEst2 <= 1.0;                 // NaN and overflow fail it and are sorted out on the rare side
+                const double prop = hh * ctrl.decide(EEst2, acc);
+                const bool keep = acc && clipped && dt > prop;   // a step clipped at tstop does not shrink the running step size
+                dt = keep ? dt : prop;
+                if (!acc) {
+                    if (!(EEst2 <= 1e300)) { status = CA_ERR_NONFINITE; break; }
                     accept = false;
-                    dt = hh * ctrl.reject(EEst2);
                     n_rej++;
                     if (dt < 1e-14 * fmax(1.0, fabs(t))) { status = CA_ERR_NONFINITE; break; }
                 }
