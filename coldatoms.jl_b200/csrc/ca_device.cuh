@@ -1011,6 +1011,28 @@ struct Lane1 {
         tnx = (j >= m.n_nodes - 2) ? 1e300 : tmid;
         twend = (j >= m.n_nodes - 2) ? 1e300 : tmid + m.dtn;
     }
+    // Sequential advance by one node, written with selects so that it is PREDICATED, not branched: the lanes of a warp cross node
+    // boundaries at different steps (their step sizes differ), and as a branch this block ran, mostly empty, in every fifth step.
+    CA_HD void advance_window_if(const DevModel& m, bool adv) {
+        const int last = m.n_nodes - 1;
+        const int jn = jc + 1;
+        const double s1r = (nr3 - nr2) * m.inv_dtn, s1b = (nb3 - nb2) * m.inv_dtn;   // slope of the interval that becomes the right one
+        sr0 = adv ? sr1 : sr0; sb0 = adv ? sb1 : sb0;
+        sr1 = adv ? s1r : sr1; sb1 = adv ? s1b : sb1;
+        nr1 = adv ? nr2 : nr1; nb1 = adv ? nb2 : nb1;
+        nr2 = adv ? nr3 : nr2; nb2 = adv ? nb3 : nb2;
+        if (adv) {   // the only memory operation: the next prefetch (nothing waits for it before the next advance)
+            const double* q0 = tab + (size_t)jn * stride;
+            const int o3 = (jn + 3 < last ? 3 : last - jn) * stride;
+            nr3 = q0[o3]; nb3 = q0[(size_t)m.n_nodes * stride + o3];
+        }
+        const bool tail = jn >= m.n_nodes - 2;
+        const double tm = tmid + m.dtn;   // (re-synchronised to (jc+1) dtn whenever window_at runs)
+        tnx = adv ? (tail ? 1e300 : tm) : tnx;
+        twend = adv ? (tail ? 1e300 : tm + m.dtn) : twend;
+        tmid = adv ? tm : tmid;
+        jc = adv ? jn : jc;
+    }
     // Both cached intervals are anchored at their common node jc+1: φ(t) = φ_{jc+1} + (t - t_{jc+1}) · slope(left | right interval).
     // Branch-free: without a table the node values and slopes stay zero (init), so the result is 0 for any finite tt.
     CA_HD void phases_lin(const DevModel& m, double tt, double& pr, double& pb) const {  // needs t_jc <= tt < twend
@@ -1235,6 +1257,7 @@ struct Lane1 {
             // ONE decision on the common path: no re-anchoring requested, the anchor model still covers the step, the step lies inside the
             // two cached noise intervals (time only moves forward, so only the upper ends are checked; a fresh trajectory starts with
             // tnx = -inf and an empty anchor window and therefore takes the careful path below)
+            if (tab) advance_window_if(m, !(tt0 < tnx) && tt0 < twend);   // the common sequential advance (never in the last interval: tnx = +inf)
             bool ok = !refresh && win_ok && tn <= anchor_t1() && tt0 < tnx && tn < twend;
             if (!ok) {
                 ok = true;
@@ -1286,7 +1309,7 @@ struct Lane1 {
             if (m.doppler_z_legacy) { Dd = m.aDz * vz; dd = m.bDz * vz; }
             dpc = m.Delta0 - m.dsign * Dd; drc = m.delta0 - m.dsign * dd;
         }
-        tab = table; stride = tstride; jc = -5; nr1 = nr2 = nr3 = sr0 = sr1 = nb1 = nb2 = nb3 = sb0 = sb1 = 0.0; tmid = 0.0; tnx = table ? -1e300 : 1e300; twend = 1e300;
+        tab = table; stride = tstride; jc = -5; nr1 = nr2 = nr3 = sr0 = sr1 = nb1 = nb2 = nb3 = sb0 = sb1 = 0.0; tmid = 0.0; tnx = table ? -1e300 : 1e300; twend = tnx;   // with a table: an empty window, so the first step loads it (window_at)
         // initial state
         y[0] = m.rho0[1]; y[1] = m.rho0[2]; y[2] = m.rho0[3];
         y[3] = m.rho0[5 + 8]; y[4] = m.rho0[5 + 9];      // (1,r)
