@@ -930,17 +930,16 @@ struct Lane1 {
     double nr1, nr2, nr3, sr0, sr1, nb1, nb2, nb3, sb0, sb1;  // node values jc+1, jc+2 and the PREFETCHED jc+3, slopes of the intervals [jc, jc+1] and [jc+1, jc+2] (red / blue trace)
     double tmid, tnx, twend;              // time of node jc+1; the same, but +inf in the last interval (or without a table): the time at which the window
                                           // advances; end of the two cached intervals (+inf without a table)
-    bool fastm;                           // fast_model(m), fixed per trajectory
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
     double* ab;                           // per beam q: ab[(q*9 + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a) | b3 re,im; ab[18] = t_a, ab[19] = end of validity
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
     bool win_ok;                          // the anchor's quadratic model of ln B passed its guard
-    double t, h, dt, tcommit;
+    double t, h, dt;                      // committed time, size of the last accepted step (0: none yet), proposed next step size
     StepCtrl ctrl;
-    double y[NS], un[NS];
-    double P[2], Pn[2], SD[2];             // ρ00, ρll quadratures; SD = Σ_j d_j (ρpp, ρrr)(stage j) of the last accepted step (dense output)
+    double y[NS];                         // committed state (the end of the last accepted step)
+    double P[2], SB[2], SD[2];            // ρ00, ρll quadratures; SB / SD = Σ_j b_j / d_j (ρpp, ρrr)(stage j) of the last accepted step (dense output)
     unsigned iters_left;                  // attempts left before CA_ERR_MAXITERS (maxiters clamped to 2^32-1)
     int n_rhs, n_acc, n_rej, n_exact;     // n_exact: steps whose coefficients took the exact (generic / guard-failed) path
     int status;
@@ -950,8 +949,8 @@ struct Lane1 {
     CA_HD void set_anchor_window(double a, double b) { anc_t0 = a; anc_t1 = b; }
     CA_HD double anchor_t0() const { return anc_t0; }
     CA_HD double anchor_t1() const { return anc_t1; }
-    // a failed trajectory parks at tcommit = +inf, so that the step loop's only test is tcommit < T
-    CA_HD void fail(int code) { status = code; tcommit = 1e300; }
+    // a failed trajectory parks at t = +inf, so that the step loop's only test is t < T
+    CA_HD void fail(int code) { status = code; t = 1e300; }
     CA_HD double* kptr(int j) const {     // j = 1..7
         const int slot = (j == 1) ? p : ((j == 2 || j == 7) ? 1 - p : j - 1);
         return kb + (size_t)slot * NS * kstride;
@@ -1252,27 +1251,26 @@ struct Lane1 {
     // last) into the shared-memory buffer cb.  `refresh`: warp-uniform request to re-anchor now.
     CA_HD void stage_coefficients(const DevModel& m, double tt0, double hh, double tn, bool refresh) {
         bool done = false;
-        if (fastm) {
-            const bool gp = (BEAMS == 1 || BEAMS == 3) ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
-            // ONE decision on the common path: no re-anchoring requested, the anchor model still covers the step, the step lies inside the
-            // two cached noise intervals (time only moves forward, so only the upper ends are checked; a fresh trajectory starts with
-            // tnx = -inf and an empty anchor window and therefore takes the careful path below)
-            if (tab) advance_window_if(m, !(tt0 < tnx) && tt0 < twend);   // the common sequential advance (never in the last interval: tnx = +inf)
-            bool ok = !refresh && win_ok && tn <= anchor_t1() && tt0 < tnx && tn < twend;
-            if (!ok) {
-                ok = true;
-                if (tab) {
-                    if (!(tt0 < tnx) || tt0 < tmid - m.dtn) window_at(m, tt0);
-                    ok = tn < twend;
-                }
-                if (refresh || !(tn <= anchor_t1()) || tt0 < anchor_t0()) {   // two steps of headroom over the re-anchoring cadence
-                    if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
-                    else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
-                }
-                ok = ok && win_ok;
+        const bool gp = (BEAMS == 1 || BEAMS == 3) ? true : (BEAMS == 2 ? false : gauss_pair(m));   // uniform over the launch
+        if (tab) advance_window_if(m, !(tt0 < tnx) && tt0 < twend);   // the common sequential advance (never in the last interval: tnx = +inf)
+        // ONE decision on the common path: no re-anchoring requested, the anchor model still covers the step (win_ok is only ever set by
+        // an anchor refresh, i.e. it implies fast_model), the step lies inside the two cached noise intervals (time only moves forward,
+        // so only the upper ends are checked; a fresh trajectory starts with an empty window and an empty anchor range and therefore
+        // takes the careful path below)
+        bool ok = !refresh && win_ok && tn <= anchor_t1() && tt0 < tnx && tn < twend;
+        if (!ok && fast_model(m)) {
+            ok = true;
+            if (tab) {
+                if (!(tt0 < tnx) || tt0 < tmid - m.dtn) window_at(m, tt0);
+                ok = tn < twend;
             }
-            if (ok) done = gp ? eval_anchored<true>(m, tt0, hh, tn) : eval_anchored<false>(m, tt0, hh, tn);
+            if (refresh || !(tn <= anchor_t1()) || tt0 < anchor_t0()) {   // two steps of headroom over the re-anchoring cadence
+                if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
+                else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
+            }
+            ok = ok && win_ok;
         }
+        if (ok) done = gp ? eval_anchored<true>(m, tt0, hh, tn) : eval_anchored<false>(m, tt0, hh, tn);
         if (!done) {   // generic / guard-failed: exact evaluation stage by stage (one rolled copy of the code)
             ++n_exact;
 #pragma unroll 1
@@ -1299,7 +1297,7 @@ struct Lane1 {
 
     CA_HD void init(const DevModel& m, const Rates& g, const OdeOpts& oo, const double* smp, const double* table, int tstride,
                     double t0, double* kbase, int kstr, double* cbase, double* abase) {
-        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false; fastm = fast_model(m);
+        kb = kbase; kstride = kstr; p = 0; cb = cbase; ab = abase; win_ok = false;
         if (ab) set_anchor_window(1e300, -1e300);
         if (m.atom_motion) { x0 = smp[0]; y0 = smp[1]; z0 = smp[2]; vx = smp[3]; vy = smp[4]; vz = smp[5]; }
         else { x0 = y0 = z0 = vx = vy = vz = 0.0; }
@@ -1329,7 +1327,7 @@ struct Lane1 {
             y[19] = m.rho0[5 + 18]; y[20] = -m.rho0[5 + 19];
         }
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
-        t = t0; tcommit = t0; h = 0.0; iters_left = oo.maxiters > 0xffffffffLL ? 0xffffffffu : (unsigned)oo.maxiters; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
+        t = t0; h = 0.0; iters_left = oo.maxiters > 0xffffffffLL ? 0xffffffffu : (unsigned)oo.maxiters; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
         ctrl.reset();
         double k1[NS];
         Coef cf0;
@@ -1342,9 +1340,7 @@ struct Lane1 {
         }
         const double g1[2] = {g.G0 * y[2], g.Gl * y[2] + g.Gr * y[1]};
         n_rhs = 1;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) un[i] = y[i];
-        Pn[0] = P[0]; Pn[1] = P[1];
+        SB[0] = SB[1] = SD[0] = SD[1] = 0.0;
         dt = oo.dt0;
         if (dt <= 0.0) {  // OrdinaryDiffEq ode_determine_initdt (Hairer hinit), norm over all 25 matrix entries
             double d0 = 0.0, d1 = 0.0;
@@ -1388,18 +1384,12 @@ struct Lane1 {
         }
     }
 
-    // Commit the pending accepted step (FSAL) and attempt one new step towards `tstop`.
+    // Attempt one step towards `tstop`.  An accepted step is committed at once on the straight-line path (y <- y_new, t <- t+h, k1 <- k7 by
+    // a toggle of the slot index); a rejection, the rare case, leaves early.  The state at the START of the last accepted step, which only
+    // the dense output needs, is not kept: state_at() re-forms it from the stage derivatives that are still in shared memory.
     CA_HD void attempt(const DevModel& m, const Rates& g, const OdeOpts& oo, double tstop, bool refresh = false) {
-        if (h != 0.0) {  // commit: y <- un, k1 <- k7 (slot toggle), t <- t+h
-#pragma unroll
-            for (int i = 0; i < NS; ++i) y[i] = un[i];
-            P[0] = Pn[0]; P[1] = Pn[1];
-            t = tcommit;
-            h = 0.0;
-            p ^= 1;
-        }
         if (iters_left-- == 0u) { fail(CA_ERR_MAXITERS); return; }
-        double hh = fmin(dt, oo.dtmax);
+        double hh = dt < oo.dtmax ? dt : oo.dtmax;   // (dt is finite here: a NaN norm has already failed the trajectory)
         bool clipped = false;
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
         const double tn = clipped ? tstop : t + hh;
@@ -1437,7 +1427,7 @@ struct Lane1 {
             for (int i = 0; i < NS; ++i) ks[i * kstride] = ko[i];
         }
         // y_new and the error combination share one pass over k1,k3..k6 (ko still holds k6)
-        double er[NS];
+        double er[NS], un[NS], Pn[2];
 #pragma unroll
         for (int i = 0; i < NS; ++i) { un[i] = MC.rb[6] * ko[i]; er[i] = MC.re[6] * ko[i]; }
 #pragma unroll
@@ -1462,7 +1452,6 @@ struct Lane1 {
         SEp = fma(MC.re[7], un[2], SEp); SEr = fma(MC.re[7], un[1], SEr); SDp = fma(MC.rd[7], un[2], SDp); SDr = fma(MC.rd[7], un[1], SDr);
         Pn[0] = fma(hh * g.G0, SBp, P[0]); Pn[1] = fma(hh, fma(g.Gl, SBp, g.Gr * SBr), P[1]);
         n_rhs += 6;
-        bool accept = true;
         if (oo.adaptive) {
             double s = nrm_real(g.G0 * SEp, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(fma(g.Gl, SEp, g.Gr * SEr), P[1], Pn[1], oo.atol, oo.rtol);
 #pragma unroll
@@ -1474,49 +1463,57 @@ struct Lane1 {
             const double prop = hh * ctrl.decide(EEst2, acc);
             const bool keep = acc && clipped && dt > prop;   // a step clipped at tstop does not shrink the running step size
             dt = keep ? dt : prop;
-            if (!acc) {
+            if (!acc) {   // rejected (rare): nothing is committed, the next attempt restarts from the same y, k1 with the smaller dt
                 if (!(EEst2 <= 1e300)) { fail(CA_ERR_NONFINITE); return; }
-                accept = false;
                 n_rej++;
-                if (dt < 1e-14 * fmax(1.0, fabs(t))) { fail(CA_ERR_NONFINITE); return; }
+                if (dt < 1e-14 * fmax(1.0, fabs(t))) fail(CA_ERR_NONFINITE);
+                return;
             }
         } else {
             dt = oo.dt0;
             if (!(fabs(un[0] + un[1] + un[2]) < 1e300)) { fail(CA_ERR_NONFINITE); return; }   // fixed step beyond the stability limit
         }
-        if (accept) {
-            n_acc++;
-            h = hh; tcommit = tn;
-            SD[0] = SDp; SD[1] = SDr;
-        }
+        // accepted: commit on the straight-line path
+        n_acc++;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) y[i] = un[i];
+        P[0] = Pn[0]; P[1] = Pn[1];
+        t = tn; h = hh; p ^= 1;
+        SB[0] = SBp; SB[1] = SBr; SD[0] = SDp; SD[1] = SDr;
     }
 
-    // State at time T inside the last accepted step [t, t+h] (Hairer contd5), Hermitian-packed ρ into out[0..24].
+    // State at time T inside the last accepted step [t-h, t] (Hairer contd5), Hermitian-packed ρ into out[0..24].  The increment
+    // r2 = y(t) - y(t-h) = h Σ_j b_j k_j is re-formed from the stage derivatives (k1 of that step now sits in the slot kptr(2) names, its
+    // k7 is the current k1), and the state at the start of the step is y - r2.
     CA_HD void state_at(const DevModel& m, double T, double* out) const {
         double s[NS], p0, p1;
-        if (h == 0.0 || T >= tcommit) {
+        if (h == 0.0 || T >= t) {
 #pragma unroll
-            for (int i = 0; i < NS; ++i) s[i] = un[i];
-            p0 = Pn[0]; p1 = Pn[1];
+            for (int i = 0; i < NS; ++i) s[i] = y[i];
+            p0 = P[0]; p1 = P[1];
         } else {
-            double th = (T - t) / h, th1 = 1.0 - th;
-            const double *k1 = kptr(1), *k3 = kptr(3), *k4 = kptr(4), *k5 = kptr(5), *k6 = kptr(6), *k7 = kptr(7);
+            double th = (T - (t - h)) / h, th1 = 1.0 - th;
+            const double *k1 = kptr(2), *k3 = kptr(3), *k4 = kptr(4), *k5 = kptr(5), *k6 = kptr(6), *k7 = kptr(1);
+            double yo1 = 0.0, yo2 = 0.0;
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 const int o = i * kstride;
-                double r2 = un[i] - y[i];
+                const double r2 = h * (MC.rb[1] * k1[o] + MC.rb[3] * k3[o] + MC.rb[4] * k4[o] + MC.rb[5] * k5[o] + MC.rb[6] * k6[o]);
+                const double yo = y[i] - r2;
+                if (i == 1) yo1 = yo;
+                if (i == 2) yo2 = yo;
                 double r3 = h * k1[o] - r2;
                 double r4 = r2 - h * k7[o] - r3;
                 double r5 = h * (MC.rd[1] * k1[o] + MC.rd[3] * k3[o] + MC.rd[4] * k4[o] + MC.rd[5] * k5[o] + MC.rd[6] * k6[o] + MC.rd[7] * k7[o]);
-                s[i] = y[i] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+                s[i] = yo + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
             }
             {
-                // stage-1 / stage-7 derivatives and the d-weighted sums of the quadratures from ρpp, ρrr at the step ends and SD
-                const double g10 = m.G0 * y[2], g11 = m.Gl * y[2] + m.Gr * y[1], g70 = m.G0 * un[2], g71 = m.Gl * un[2] + m.Gr * un[1];
-                double r2 = Pn[0] - P[0], r3 = h * g10 - r2, r4 = r2 - h * g70 - r3, r5 = h * (m.G0 * SD[0]);
-                p0 = P[0] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
-                r2 = Pn[1] - P[1]; r3 = h * g11 - r2; r4 = r2 - h * g71 - r3; r5 = h * (m.Gl * SD[0] + m.Gr * SD[1]);
-                p1 = P[1] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+                // stage-1 / stage-7 derivatives of the quadratures from ρpp, ρrr at the step ends; increments and d-sums from SB, SD
+                const double g10 = m.G0 * yo2, g11 = m.Gl * yo2 + m.Gr * yo1, g70 = m.G0 * y[2], g71 = m.Gl * y[2] + m.Gr * y[1];
+                double r2 = h * (m.G0 * SB[0]), r3 = h * g10 - r2, r4 = r2 - h * g70 - r3, r5 = h * (m.G0 * SD[0]);
+                p0 = (P[0] - r2) + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+                r2 = h * (m.Gl * SB[0] + m.Gr * SB[1]); r3 = h * g11 - r2; r4 = r2 - h * g71 - r3; r5 = h * (m.Gl * SD[0] + m.Gr * SD[1]);
+                p1 = (P[1] - r2) + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
             }
         }
 #pragma unroll

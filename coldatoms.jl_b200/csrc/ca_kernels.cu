@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
         // ---- K3: integrate
         Lane1<NS, BEAMS> L;
         L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS == 9 ? sab + threadIdx.x : nullptr);
-        if (!valid) L.tcommit = 1e300;
+        if (!valid) L.t = 1e300;
         const double tend = tsp[P.nt - 1];
         unsigned n_att = 0;
         double* acc_pt = P.accum + (size_t)pt * P.nt * kNV;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             const double T = tsp[j];
             const double tstop = P.ode.dense ? tend : T;
             while (true) {
-                const bool need = L.tcommit < T;   // invalid and failed lanes are parked at tcommit = +inf
+                const bool need = L.t < T;   // invalid and failed lanes are parked at t = +inf
                 if (!__any_sync(0xffffffffu, need)) break;
                 if (need) L.attempt(m, rt, P.ode, tstop, (n_att & (kAnchorEvery - 1)) == 0);   // all lanes re-anchor their beam model together
                 ++n_att;

@@ -26,7 +26,7 @@ static int run_lane(const DevModel& m, const OdeOpts& oo, const double* tspan, i
     for (int j = 0; j < nt; ++j) {
         const double T = tspan[j];
         const double tstop = oo.dense ? tend : T;
-        while (L.status == 0 && L.tcommit < T) { L.attempt(m, rt, oo, tstop, (n_att & (kAnchorEvery - 1)) == 0); ++n_att; }
+        while (L.status == 0 && L.t < T) { L.attempt(m, rt, oo, tstop, (n_att & (kAnchorEvery - 1)) == 0); ++n_att; }
         if (L.status) return L.status;
         double v[kNV];
         L.state_at(m, T, v);
