@@ -211,3 +211,18 @@ def test_sweep_over_beam_classes(pkg, oracle, ctx, r1cfg):
             o, o2, _ = oracle.rydberg1_run(m, [0.0, tends[k]], psis[k], n_pp, traj_offset=k * n_pp, seed=13)
             assert np.abs(srho[k] - o[-1]).max() < TOL_ADAPTIVE, k
             assert np.abs(srho2[k] - o2[-1]).max() < TOL_ADAPTIVE, k
+
+
+def test_rejected_steps_parity(pkg, oracle, ctx, r1cfg):
+    """A too large initial step (ode dt = 0.05) forces every trajectory through a series of rejections before the controller
+    settles: the accept/reject sequence and the solution must still be the oracle's."""
+    cfg = r1cfg.copy()
+    n = 70
+    kw = _inputs(oracle, cfg, n, seed=9)
+    model = pkg.model_from_config(cfg)
+    ode = pkg._abi.ode_opts(dt=0.05)
+    rho, rho2, st = ctx.rydberg1_run(model, cfg.tspan, cfg.ψ0, n, ode=ode, **kw)
+    o, o2, ost = oracle.rydberg1_run(model, cfg.tspan, cfg.ψ0, n, ode=ode, **kw)
+    assert ost["n_reject"] >= 3 * n
+    assert (st["n_rhs"], st["n_accept"], st["n_reject"]) == (ost["n_rhs"], ost["n_accept"], ost["n_reject"])
+    assert np.abs(rho - o).max() < 1e-9 and np.abs(rho2 - o2).max() < 1e-9

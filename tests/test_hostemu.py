@@ -250,3 +250,20 @@ def test_thermal_average_functionals_device_source_vs_reference_loops(pkg, oracl
     assert he.he_thermal_terms(1, C.byref(m2), P(s1), P(s2), C.c_longlong(400), P(out)) == 0
     ref = oracle.rm6_terms(s1, s2, cz.atom_centers)
     assert np.abs(out[:, 0] / ref - 1).max() < 1e-14 and not out[:, 1].any()
+
+
+def test_lane_rejected_steps_restore_the_state(pkg, oracle, he, r1cfg):
+    """A too large initial step forces rejections: the lane advances y in place and re-forms the old state from the stored stage
+    derivatives on a rejection, so the retried steps must reproduce the oracle's accept/reject sequence and its solution."""
+    cfg = r1cfg
+    m = pkg.config.model_from_config(cfg)
+    rng = np.random.default_rng(5)
+    sample, _ = oracle.sample_atoms(cfg.trap_params, cfg.atom_params, 1, seed=3)
+    pr, pb = rng.uniform(0, 2 * np.pi, len(cfg.f)), rng.uniform(0, 2 * np.pi, len(cfg.f))
+    for psi in (pkg.ket_1, (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2)):
+        ode = pkg._abi.ode_opts(dt=0.05)
+        r1, r2, st = he_traj(he, m, cfg.tspan, psi, sample[0], pr, pb, cfg.f, cfg.red_laser_phase_amplitudes, cfg.blue_laser_phase_amplitudes, ode)
+        o1, o2, ost = oracle.rydberg1_run(m, cfg.tspan, psi, 1, samples=sample, phases_red=pr[None], phases_blue=pb[None], f=cfg.f,
+                                          amp_red=cfg.red_laser_phase_amplitudes, amp_blue=cfg.blue_laser_phase_amplitudes, ode=ode)
+        assert ost["n_reject"] >= 3 and st == [ost["n_rhs"], ost["n_accept"], ost["n_reject"]]
+        assert np.abs(r1 - o1).max() < 1e-9 and np.abs(r2 - o2).max() < 1e-9
