@@ -1239,7 +1239,7 @@ struct Lane1 {
                 if (m.doppler_z_legacy) { const double Vzt = vz * cz - z0 * m.wz * sz; Dd = m.aDz * Vzt; dd = m.bDz * Vzt; }
                 cb[(n * 6 + 4) * kstride] = m.Delta0 - m.dsign * Dd; cb[(n * 6 + 5) * kstride] = m.delta0 - m.dsign * dd;
             }
-        } else {
+        } else if (!(BEAMS == 1 || BEAMS == 2)) {   // (the free-flight variants read dpc / drc directly)
 #pragma unroll
             for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
         }
@@ -1414,7 +1414,9 @@ struct Lane1 {
             }
             {
                 const double* o = cb + (size_t)(s - 2) * 6 * kstride;
-                cf.Ar = o[0]; cf.Ai = o[kstride]; cf.Br = o[2 * kstride]; cf.Bi = o[3 * kstride]; cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride];
+                cf.Ar = o[0]; cf.Ai = o[kstride]; cf.Br = o[2 * kstride]; cf.Bi = o[3 * kstride];
+                if (BEAMS == 1 || BEAMS == 2) { cf.dp = dpc; cf.dr = drc; }   // free flight: the detunings are constants of the trajectory
+                else { cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride]; }
             }
             lindblad_rhs<NS>(cf, g, us, ko);
             {
