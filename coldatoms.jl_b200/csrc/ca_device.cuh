@@ -440,6 +440,11 @@ CA_HD void gauss_batch(const DevBeam& br, const DevBeam& bb, const double* x, co
 // truncation < 4e-16).  Nothing accumulates:
 // every value hangs off an exactly evaluated anchor; a lane whose step leaves [t_a, t_a + 2H] re-anchors on the spot.
 constexpr int kAnchorEvery = 32;   // attempts between warp-wide re-anchorings (power of two)
+#ifndef CA_ANCHOR_EVERY_GENERIC
+#define CA_ANCHOR_EVERY_GENERIC 64
+#endif
+constexpr int kAnchorEveryGeneric = CA_ANCHOR_EVERY_GENERIC;   // the same for the flat-top / uniform beam class (BEAMS = 2): no phase noise there, and the
+                                                               // refresh is big code that evicts the step loop from the instruction cache (32: -16 %, 128: guard failures)
 struct BeamGeom { double s, iq, g; };
 CA_HD BeamGeom beam_geom(const DevBeam& b, double rp, double z) {
     const double xr = rp * b.cs - z * b.sn, zr = rp * b.sn + z * b.cs;
@@ -921,6 +926,7 @@ struct StepCtrl {
 template <int NS, int BEAMS = 0>   // BEAMS: 0 decide at run time (all coefficient paths compiled), 1 Gaussian pair + free flight only,
                                      // 2 other beam kinds (free flight), 3 Gaussian pair + trap oscillation
 struct Lane1 {
+    static constexpr int kEvery = BEAMS == 2 ? kAnchorEveryGeneric : kAnchorEvery;   // attempts between re-anchorings of this variant
     // trajectory
     double x0, y0, z0, vx, vy, vz, vzq;  // vzq: velocity used for "Vz" (vy when the B1 quirk is on)
     double dpc, drc;                      // constant detunings (free motion) incl. Δ0, δ0
@@ -1265,8 +1271,8 @@ struct Lane1 {
                 ok = tn < twend;
             }
             if (refresh || !(tn <= anchor_t1()) || tt0 < anchor_t0()) {   // two steps of headroom over the re-anchoring cadence
-                if (gp) refresh_anchor(m, tt0, (0.5 * kAnchorEvery + 1.0) * hh);
-                else refresh_anchor_generic(m, tt0, ((kAnchorEvery + 2.0) / 3.0) * hh);
+                if (gp) refresh_anchor(m, tt0, (0.5 * kEvery + 1.0) * hh);
+                else refresh_anchor_generic(m, tt0, ((kEvery + 2.0) / 3.0) * hh);
             }
             ok = ok && win_ok;
         }

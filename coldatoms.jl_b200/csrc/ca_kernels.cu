@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             while (true) {
                 const bool need = L.t < T;   // invalid and failed lanes are parked at t = +inf
                 if (!__any_sync(0xffffffffu, need)) break;
-                if (need) L.attempt(m, rt, P.ode, tstop, (n_att & (kAnchorEvery - 1)) == 0);   // all lanes re-anchor their beam model together
+                if (need) L.attempt(m, rt, P.ode, tstop, (n_att & (Lane1<NS, BEAMS>::kEvery - 1)) == 0);   // all lanes re-anchor their beam model together
                 ++n_att;
             }
             double v[kNV];
@@ -515,9 +515,10 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
             n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
             n_free += dm[p].free_motion != 0;
         }
-#ifdef CA_FAST_BUILD   // developer builds (profiles/dev_fast.sh): only the R1 variant is compiled
-        if (ns == 9 && !sweep && n_gp == n_points && n_free == n_points) rc = launch_lindblad1<9, false, 1>(c, P, grid);
-        else { set_error("CA_FAST_BUILD: only the Gaussian-pair free-flight ket_1 variant is compiled"); rc = CA_ERR_UNSUPPORTED; }
+#ifdef CA_FAST_BUILD   // developer builds (profiles/dev_fast.sh): only the R1 variant (CA_FAST_BUILD=2: only the flat-top R2 variant) is compiled
+        constexpr int kFastBeams = (CA_FAST_BUILD + 0) == 2 ? 2 : 1;
+        if (ns == 9 && !sweep && n_free == n_points && n_gp == (kFastBeams == 1 ? n_points : 0)) rc = launch_lindblad1<9, false, kFastBeams>(c, P, grid);
+        else { set_error("CA_FAST_BUILD: only one free-flight ket_1 variant is compiled"); rc = CA_ERR_UNSUPPORTED; }
 #else
         if (ns == 9) {
             if (n_gp == n_points && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 1>(c, P, grid) : launch_lindblad1<9, false, 1>(c, P, grid);

@@ -5,6 +5,6 @@ set -e
 R=/root/repo
 mkdir -p $R/variants
 cd $R/coldatoms.jl_b200/csrc
-/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v -DCA_FAST_BUILD ${CA_DEFS} \
+/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v -DCA_FAST_BUILD=${CA_FAST:-1} ${CA_DEFS} \
     -shared -o $R/variants/${1:-libfast}.so ca_kernels.cu ca_lindblad2.cu ca_model.cpp 2> $R/variants/${1:-libfast}.log
-grep -A2 "k_lindblad1ILi9ELb0ELi1" $R/variants/${1:-libfast}.log | grep -v Compiling | paste - - | sed 's/ptxas info    : //g; s/Function properties for //'
+grep -A2 "k_lindblad1ILi9ELb0ELi${CA_FAST:-1}" $R/variants/${1:-libfast}.log | grep -v Compiling | paste - - | sed 's/ptxas info    : //g; s/Function properties for //'
