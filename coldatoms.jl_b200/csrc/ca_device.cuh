@@ -1064,7 +1064,7 @@ struct Lane1 {
     }
 
     CA_HD bool fast_model(const DevModel& m) const {   // anchored coefficients are available
-        if (!(NS == 9 && ab != nullptr && m.xi == 0.0 && m.dtn > 0.0)) return false;
+        if (!(NS <= 15 && ab != nullptr && m.xi == 0.0 && m.dtn > 0.0)) return false;   // (NS = 21 is register-bound: the anchored code costs it more in spills than it saves)
         if (m.free_motion) return true;                       // any beam kind in free flight
         return (BEAMS == 0 || BEAMS == 3) && gauss_pair(m);   // trap oscillation: Gaussian pairs only
     }

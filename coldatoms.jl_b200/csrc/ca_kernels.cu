@@ -37,7 +37,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // K1+K2+K3: fused one-atom ensemble kernel
 // ----------------------------------------------------------------------------------------------------
 template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? 96 : 128); }
-template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS == 9 ? 20 : 0); }   // k slots + stage coefficients + anchors
+template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS <= 15 ? 20 : 0); }   // k slots + stage coefficients + anchors (NS <= 15)
 constexpr int kNoiseChunk = 64;
 
 struct R1Params {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sk = reinterpret_cast<double*>(smem_raw);                                   // [6][NS][T] stage derivatives
     double* scb = sk + 6 * NS * T;                                                      // [5][6][T] stage coefficients
-    double* sab = scb + 30 * T;                                                         // [2][2][5][T] beam anchors (NS = 9)
+    double* sab = scb + 30 * T;                                                         // [2][2][5][T] beam anchors (NS <= 15)
     DevModel* sm_models = reinterpret_cast<DevModel*>(sk + smem_doubles_per_thread<NS>() * T);  // [warps] (sweeps only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * (T / 32) + warp;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
         }
         // ---- K3: integrate
         Lane1<NS, BEAMS> L;
-        L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS == 9 ? sab + threadIdx.x : nullptr);
+        L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS <= 15 ? sab + threadIdx.x : nullptr);
         if (!valid) L.t = 1e300;
         const double tend = tsp[P.nt - 1];
         unsigned n_att = 0;

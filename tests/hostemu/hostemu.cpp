@@ -20,7 +20,7 @@ static int run_lane(const DevModel& m, const OdeOpts& oo, const double* tspan, i
     rt.G0 = m.G0; rt.G1 = m.G1; rt.Gl = m.Gl; rt.Gr = m.Gr; rt.Gp = m.G0 + m.G1 + m.Gl; rt.gp2 = 0.5 * rt.Gp; rt.gr2 = 0.5 * m.Gr;
     Lane1<NS> L;
     double kstore[6 * NS], cstore[30], astore[20];
-    L.init(m, rt, oo, smp, tab, 1, tspan[0], kstore, 1, cstore, NS == 9 ? astore : nullptr);
+    L.init(m, rt, oo, smp, tab, 1, tspan[0], kstore, 1, cstore, NS <= 15 ? astore : nullptr);
     const double tend = tspan[nt - 1];
     unsigned n_att = 0;
     for (int j = 0; j < nt; ++j) {
