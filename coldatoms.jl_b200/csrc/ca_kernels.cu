@@ -525,7 +525,10 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
             else if (n_gp == 0 && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 2>(c, P, grid) : launch_lindblad1<9, false, 2>(c, P, grid);
             else if (n_gp == n_points && n_free == 0) rc = sweep ? launch_lindblad1<9, true, 3>(c, P, grid) : launch_lindblad1<9, false, 3>(c, P, grid);
             else rc = sweep ? launch_lindblad1<9, true, 0>(c, P, grid) : launch_lindblad1<9, false, 0>(c, P, grid);
-        } else if (ns == 15) rc = sweep ? launch_lindblad1<15, true, 0>(c, P, grid) : launch_lindblad1<15, false, 0>(c, P, grid);
+        } else if (ns == 15) {
+            if (n_gp == n_points && n_free == n_points) rc = sweep ? launch_lindblad1<15, true, 1>(c, P, grid) : launch_lindblad1<15, false, 1>(c, P, grid);
+            else rc = sweep ? launch_lindblad1<15, true, 0>(c, P, grid) : launch_lindblad1<15, false, 0>(c, P, grid);
+        }
         else rc = sweep ? launch_lindblad1<21, true, 0>(c, P, grid) : launch_lindblad1<21, false, 0>(c, P, grid);
 #endif
         if (rc) return rc;
