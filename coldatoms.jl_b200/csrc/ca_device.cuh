@@ -153,6 +153,16 @@ CA_HD double rcp_norm(double x) {
     return rcp_d(x);
 #endif
 }
+// odd series Σ_{k=0..9} c_k u^{2k+1}: atanh-type (c_k = 1/(2k+1)) and atan-type (alternating), for |u| < 0.12 (u^21/21 < 3e-21)
+CA_HD double odd_series(double u, bool alternating) {
+    const double z = alternating ? -(u * u) : u * u;
+    double p = 1.0 / 19.0;
+    p = fma(p, z, 1.0 / 17.0); p = fma(p, z, 1.0 / 15.0); p = fma(p, z, 1.0 / 13.0); p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0); p = fma(p, z, 1.0 / 7.0); p = fma(p, z, 1.0 / 5.0); p = fma(p, z, 1.0 / 3.0);
+    return fma(u * z, p, u);
+}
+CA_HD double log1p_small(double x) { return 2.0 * odd_series(x * rcp_d(2.0 + x), false); }   // ln(1+x) = 2 atanh(x / (2 + x)),  |x| < 0.25
+CA_HD double atan_small(double t) { return odd_series(t, true); }                             // |t| < 0.12
 CA_HD double sqrt_d(double x);
 CA_HD double sqrt_norm(double x) {
 #if defined(__CUDA_ARCH__) && CA_NORM_SHORT
@@ -1109,7 +1119,9 @@ struct Lane1 {
                 } else {   // ln(c_i / c_0) = ln|r| + i arg r  (the flat-top fields carry e^{-ikz}: the phase moves by mrad over the window)
                     const double rr = (re * c0r + im * c0i) * inv0, ri = (im * c0r - re * c0i) * inv0, wr = rr - 1.0;
                     win_ok = win_ok && (wr * wr + ri * ri < 0.01);
-                    const double lr = 0.5 * log1p(fma(wr, 2.0 + wr, ri * ri)), li = atan2(ri, rr);
+                    // ln|r| and arg r for |r - 1| < 0.1 (guarded above) by short odd series (truncation < 1e-19): the library log1p / atan2
+                    // are several hundred instructions of rarely executed code that the refresh would pull through the instruction cache
+                    const double lr = 0.5 * log1p_small(fma(wr, 2.0 + wr, ri * ri)), li = atan_small(ri * rcp_d(rr));
                     if (i == 1) { l[0][0] = lr; l[0][1] = li; } else if (i == 2) { l[1][0] = lr; l[1][1] = li; } else { l[2][0] = lr; l[2][1] = li; }
                 }
             }
