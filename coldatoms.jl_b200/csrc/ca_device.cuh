@@ -306,8 +306,8 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
         // flat-top HG / LG (arbitrary_beams.jl:50-81): E = Ω (w0/w) e^{-i phase0} Σ c HG HG e^{-i(i+j+1)at}
         double s = z * b.inv_z0;
         double q = 1.0 + s * s;
-        double iq = 1.0 / q;
-        double rq = sqrt(iq);                // w0/w
+        double iq = rcp_d(q);                // (in-house rcp / sqrt / exp / sincos throughout: the library versions drag their slow paths
+        double rq = sqrt_d(iq);              //  through the instruction cache at every anchor refresh)   w0/w
         double iw2 = b.inv_w0sq * iq;        // 1/w^2
         double r2 = x * x + y * y;
         double phase0 = b.k * z + s * r2 * iw2;  // k z + (k/2) z r²/(z²+zr²) = k z + s r²/w²
@@ -322,7 +322,7 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
                 double u = ax == 0 ? x : y * b.sqz_inv;   // HG(y, w*sqz, j)
                 int nmax = ax == 0 ? b.nx : b.ny;
                 const double* cf = ax == 0 ? b.cx : b.cy;
-                double xi = sqrt(2.0 * iw2) * u;          // sqrt(2) u / w
+                double xi = sqrt_d(2.0 * iw2) * u;        // sqrt(2) u / w
                 double h0 = 1.0, h1 = 2.0 * xi;           // H_0, H_1
                 double pr = 1.0, pi = 0.0;                // g2^a
                 double ar = cf[0], ai = 0.0;
@@ -334,7 +334,7 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
                     double t = pr * g2r - pi * g2i; pi = pr * g2i + pi * g2r; pr = t;
                     ar += cf[a] * h2 * pr; ai += cf[a] * h2 * pi;
                 }
-                double ex = exp(-u * u * iw2);
+                double ex = exp_d(-u * u * iw2);
                 sums[ax][0] = ar * ex; sums[ax][1] = ai * ex;
             }
             Sr = sums[0][0] * sums[1][0] - sums[0][1] * sums[1][1];
@@ -348,16 +348,16 @@ CA_HD void beam_half_omega(const DevBeam& b, double x, double y, double z, doubl
                 double lp = l1;  // L_p
                 double t = pr * g1r - pi * g1i; pi = pr * g1i + pi * g1r; pr = t;
                 ar += b.cx[p] * lp * pr; ai += b.cx[p] * lp * pi;
-                double l2 = ((2.0 * p + 1.0 - u) * l1 - p * l0) / (p + 1.0);
+                double l2 = ((2.0 * p + 1.0 - u) * l1 - p * l0) * rcp_d(p + 1.0);
                 l0 = l1; l1 = l2;
             }
-            double ex = exp(-r2 * iw2);
+            double ex = exp_d(-r2 * iw2);
             Sr = ar * ex; Si = ai * ex;
         }
         // E/2 = hO rq g1 S e^{i(phi - phase0)}
         double tr = g1r * Sr - g1i * Si, ti = g1r * Si + g1i * Sr;
         double sn, cs;
-        sincos_d(phi - phase0, &sn, &cs);
+        sincos_fast(phi - phase0, &sn, &cs);
         double f = b.hO * rq;
         *re = f * (tr * cs - ti * sn);
         *im = f * (tr * sn + ti * cs);
