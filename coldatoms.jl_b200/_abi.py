@@ -62,6 +62,7 @@ class ca_stats(C.Structure):
         ("n_sample_attempts", C.c_int64),
         ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("noise_ms", C.c_double),
         ("n_launches", C.c_int32), ("status", C.c_int32),
+        ("n_exact_steps", C.c_int64),
     ]
 
     def as_dict(self):

@@ -21,6 +21,9 @@ _lock = threading.Lock()
 # every symbol include/coldatoms_b200.h declares
 EXPORTS = [
     "ca_version", "ca_last_error", "ca_init", "ca_finalize", "ca_set_stream", "ca_reset_stream", "ca_synchronize",
+    "ca_collect_stats", "ca_stats_to_device",
+    "ca_init_multi", "ca_finalize_multi", "ca_multi_size", "ca_multi_context", "ca_rydberg1_run_multi", "ca_rydberg2_run_multi",
+    "ca_rydberg1_sweep_multi", "ca_release_recapture_multi",
     "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg1_sweep", "ca_release_recapture",
     "ca_sample_atoms", "ca_sample_atoms_metropolis", "ca_phase_noise", "ca_eval_beam", "ca_thermal_average",
 ]
@@ -44,6 +47,7 @@ def load():
             L = C.CDLL(LIB_PATH)
             L.ca_last_error.restype = C.c_char_p
             L.ca_version.restype = C.c_int
+            L.ca_multi_context.restype = C.c_void_p
             _lib = L
     return _lib
 
@@ -101,6 +105,19 @@ class Context:
 
     def synchronize(self):
         _check(load().ca_synchronize(self._h))
+
+    def collect_stats(self, check=True):
+        """Deferred ca_stats of the most recent ensemble call (synchronises).  A CA_OUT_DEVICE call cannot report a trajectory that
+        hit maxiters / went non-finite in its return value: this does, raising ColdAtomsError like the synchronous call would."""
+        st = _abi.ca_stats()
+        rc = load().ca_collect_stats(self._h, C.byref(st))
+        if check:
+            _check(rc)
+        return st.as_dict()
+
+    def stats_to_device(self, dev_ptr):
+        """Enqueue the export of the last call's counters as 8 doubles at device pointer `dev_ptr` (they add across shards)."""
+        _check(load().ca_stats_to_device(self._h, C.cast(C.c_void_p(dev_ptr), dp)))
 
     def measure_fp64_peak(self):
         tf, mhz = C.c_double(), C.c_double()
@@ -189,16 +206,20 @@ class Context:
 
     # -- release and recapture ---------------------------------------------------------------------------
     def release_recapture(self, trap, atom, tspan, n, traj_offset=0, n_total=0, eps=1e-3, seed=_abi.DEFAULT_SEED, samples=None,
-                          out_flags=0, want_indicators=False):
+                          out_flags=0, want_indicators=False, dev_out=None):
         trap, atom, tspan = _arr(trap, (3,)), _arr(atom, (2,)), _arr(tspan)
         samples = _arr(samples, (-1, 6)) if samples is not None else None
         nt = len(tspan)
-        probs = np.zeros(nt)
         ind = np.zeros((n, nt), dtype=np.uint8) if want_indicators else None
+        if out_flags & _abi.CA_OUT_DEVICE:
+            probs, pp = None, C.cast(C.c_void_p(dev_out), dp)
+        else:
+            probs = np.zeros(nt)
+            pp = _p(probs)
         st = _abi.ca_stats()
         _check(load().ca_release_recapture(self._h, _p(trap), _p(atom), _p(tspan), C.c_int32(nt), C.c_int64(n), C.c_int64(traj_offset),
                                            C.c_int64(n_total), C.c_double(eps), C.c_uint64(seed), _p(samples), C.c_int32(out_flags),
-                                           _p(probs), None if ind is None else ind.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st)))
+                                           pp, None if ind is None else ind.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st)))
         return probs, ind, st.as_dict()
 
     # -- samplers ----------------------------------------------------------------------------------------
@@ -242,6 +263,102 @@ class Context:
         out = np.zeros((len(xyz), 2))
         _check(load().ca_eval_beam(self._h, C.byref(beam), _p(xyz), C.c_int64(len(xyz)), _p(out)))
         return out[:, 0] + 1j * out[:, 1]
+
+
+class MultiContext:
+    """ca_multi: several GPUs driven from this one process (ca_init_multi: one context per device + one NCCL clique).  The ensemble
+    methods mirror Context's; trajectories are sharded by contiguous global-index ranges inside the library and combined with one
+    ncclAllReduce, so the results equal the single-GPU ones up to summation order."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices is None:
+            _check(load().ca_init_multi(None, C.c_int32(0), C.byref(self._h)))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(load().ca_init_multi(arr, C.c_int32(len(devices)), C.byref(self._h)))
+        self.size = int(load().ca_multi_size(self._h))
+
+    def close(self):
+        if self._h:
+            load().ca_finalize_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rydberg1_run(self, model, tspan, psi0, n_traj, traj_offset=0, n_total=0, seed=_abi.DEFAULT_SEED, samples=None,
+                     phases_red=None, phases_blue=None, f=None, amp_red=None, amp_blue=None, ode=None, out_flags=0):
+        tspan = _arr(tspan)
+        nt = len(tspan)
+        samples = _arr(samples, (-1, 6)) if samples is not None else None
+        f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
+        nf = 0 if f is None else len(f)
+        phases_red = _arr(phases_red, (-1, nf)) if phases_red is not None else None
+        phases_blue = _arr(phases_blue, (-1, nf)) if phases_blue is not None else None
+        st = _abi.ca_stats()
+        ode = ode if ode is not None else _abi.ode_opts()
+        rho = np.zeros((nt, 5, 5), dtype=np.complex128)
+        rho2 = np.zeros((nt, 5, 5), dtype=np.complex128)
+        _check(load().ca_rydberg1_run_multi(self._h, C.byref(model), _p(tspan), C.c_int32(nt), _p(_psi(psi0, 5)), C.c_int64(n_traj),
+                                            C.c_int64(traj_offset), C.c_int64(n_total), C.c_uint64(seed), _p(samples), _p(phases_red),
+                                            _p(phases_blue), _p(f), _p(amp_red), _p(amp_blue), C.c_int32(nf), C.byref(ode),
+                                            C.c_int32(out_flags), rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), C.byref(st)))
+        return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
+
+    def rydberg2_run(self, model, tspan, psi0, n_traj, traj_offset=0, n_total=0, seed=_abi.DEFAULT_SEED, samples1=None,
+                     samples2=None, phases4=None, f=None, amp_red=None, amp_blue=None, ode=None, out_flags=0):
+        tspan = _arr(tspan)
+        nt = len(tspan)
+        samples1 = _arr(samples1, (-1, 6)) if samples1 is not None else None
+        samples2 = _arr(samples2, (-1, 6)) if samples2 is not None else None
+        f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
+        nf = 0 if f is None else len(f)
+        ph_arr, keep = None, []
+        if phases4 is not None:
+            keep = [_arr(p, (-1, nf)) for p in phases4]
+            ph_arr = (dp * 4)(*[_p(p) for p in keep])
+        st = _abi.ca_stats()
+        ode = ode if ode is not None else _abi.ode_opts()
+        rho = np.zeros((nt, 25, 25), dtype=np.complex128)
+        rho2 = np.zeros((nt, 25, 25), dtype=np.complex128)
+        _check(load().ca_rydberg2_run_multi(self._h, C.byref(model), _p(tspan), C.c_int32(nt), _p(_psi(psi0, 25)), C.c_int64(n_traj),
+                                            C.c_int64(traj_offset), C.c_int64(n_total), C.c_uint64(seed), _p(samples1), _p(samples2),
+                                            ph_arr, _p(f), _p(amp_red), _p(amp_blue), C.c_int32(nf), C.byref(ode), C.c_int32(out_flags),
+                                            rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), C.byref(st)))
+        return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
+
+    def rydberg1_sweep(self, models, psi0s, t_end, n_traj_per_point, traj_offset=0, n_total=0, seed=_abi.DEFAULT_SEED, f=None,
+                       amp_red=None, amp_blue=None, ode=None, out_flags=0):
+        n_points = len(models)
+        marr = (_abi.ca_model * n_points)(*models)
+        psi = np.ascontiguousarray(np.asarray(psi0s, dtype=np.complex128).reshape(n_points, 5)).view(np.float64)
+        t_end = _arr(t_end, (n_points,))
+        f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
+        nf = 0 if f is None else len(f)
+        rho = np.zeros((n_points, 5, 5), dtype=np.complex128)
+        rho2 = np.zeros((n_points, 5, 5), dtype=np.complex128)
+        st = _abi.ca_stats()
+        ode = ode if ode is not None else _abi.ode_opts()
+        _check(load().ca_rydberg1_sweep_multi(self._h, marr, _p(psi), _p(t_end), C.c_int32(n_points), C.c_int64(n_traj_per_point),
+                                              C.c_int64(traj_offset), C.c_int64(n_total), C.c_uint64(seed), _p(f), _p(amp_red),
+                                              _p(amp_blue), C.c_int32(nf), C.byref(ode), C.c_int32(out_flags), rho.ctypes.data_as(dp),
+                                              rho2.ctypes.data_as(dp), C.byref(st)))
+        return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
+
+    def release_recapture(self, trap, atom, tspan, n, traj_offset=0, n_total=0, eps=1e-3, seed=_abi.DEFAULT_SEED, samples=None, out_flags=0):
+        trap, atom, tspan = _arr(trap, (3,)), _arr(atom, (2,)), _arr(tspan)
+        samples = _arr(samples, (-1, 6)) if samples is not None else None
+        nt = len(tspan)
+        probs = np.zeros(nt)
+        st = _abi.ca_stats()
+        _check(load().ca_release_recapture_multi(self._h, _p(trap), _p(atom), _p(tspan), C.c_int32(nt), C.c_int64(n), C.c_int64(traj_offset),
+                                                 C.c_int64(n_total), C.c_double(eps), C.c_uint64(seed), _p(samples), C.c_int32(out_flags),
+                                                 _p(probs), C.byref(st)))
+        return probs, None, st.as_dict()
 
 
 _default_ctx = {}

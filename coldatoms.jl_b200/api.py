@@ -79,18 +79,33 @@ def _shard(n, distributed):
 
 
 def _allreduce_mean(ctx, run, nt, d, n_total):
-    """Run with device-resident un-normalised sums, all-reduce them over NCCL, normalise."""
+    """Run with device-resident un-normalised sums, all-reduce them over NCCL, normalise.
+
+    The 8 shard-additive counters of the call (ca_stats_to_device: RHS / step counts and the two failure flags) ride at the tail of
+    the SAME buffer, so one all-reduce carries the sums and the status: a trajectory that hit maxiters or went non-finite on ANY rank
+    raises on EVERY rank, exactly like the single-GPU call does (such a trajectory is left out of the sums)."""
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", ctx.device)
-    buf = torch.zeros((2, nt, d, d, 2), dtype=torch.float64, device=dev)
+    n_out = 2 * nt * d * d * 2
+    flat = torch.zeros(n_out + 8, dtype=torch.float64, device=dev)
+    buf = flat[:n_out].view(2, nt, d, d, 2)
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     try:
         st = run(_abi.CA_OUT_SUMS | _abi.CA_OUT_DEVICE, (buf[0].data_ptr(), buf[1].data_ptr()))
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        out = (buf / float(n_total)).cpu().numpy()
+        ctx.stats_to_device(flat[n_out:].data_ptr())
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        host = flat.cpu().numpy()
     finally:
         ctx.reset_stream()
+    cnt = host[n_out:]
+    st = dict(st, n_traj=int(cnt[7]), n_rhs=int(cnt[0]), n_accept=int(cnt[1]), n_reject=int(cnt[2]), n_sample_attempts=int(cnt[3]),
+              n_exact_steps=int(cnt[6]))
+    if cnt[5] > 0:
+        raise _lib.ColdAtomsError(_abi.CA_ERR_NONFINITE, "a trajectory produced a non-finite state or the step size underflowed (on some rank)")
+    if cnt[4] > 0:
+        raise _lib.ColdAtomsError(_abi.CA_ERR_MAXITERS, "a trajectory hit maxiters (on some rank)")
+    out = host[:n_out].reshape(2, nt, d, d, 2) / float(n_total)
     cm = out[..., 0] + 1j * out[..., 1]
     return cm[0].transpose(0, 2, 1).copy(), cm[1].transpose(0, 2, 1).copy(), st
 
@@ -188,12 +203,14 @@ def simulation(cfg: RydbergConfig, temperature_calibrate=False, seed=None, devic
     Extra keywords (not in the reference): `seed`, `device`, `distributed`, host-supplied `samples[N,6]` /
     `phases_red|blue[N,Nf]` (the parity protocol of SURVEY §8c), `compat`, `rho2_mode`.
     """
-    cfg_t = calibrate_two_photon(cfg, seed=seed, device=device) if temperature_calibrate else cfg
+    sd = _next_seed(seed)
+    # the calibration draws its own thermal ensemble (rydberg_model.jl:289 vs :206-212): a sub-seed derived from the call's seed, so
+    # that it is not the first 1000 atoms of the simulated ensemble
+    cfg_t = calibrate_two_photon(cfg, seed=(sd ^ 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF, device=device) if temperature_calibrate else cfg
     model = model_from_config(cfg_t, compat=compat, rho2_mode=rho2_mode)
     ctx = _lib.default_context(device)
     n = int(cfg_t.n_samples)
     lo, cnt, world = _shard(n, distributed)
-    sd = _next_seed(seed)
     kw = dict(traj_offset=lo, n_total=n, seed=sd,
               samples=None if samples is None else np.asarray(samples)[lo:lo + cnt],
               phases_red=None if phases_red is None else np.asarray(phases_red)[lo:lo + cnt],
@@ -201,7 +218,7 @@ def simulation(cfg: RydbergConfig, temperature_calibrate=False, seed=None, devic
               f=cfg_t.f if cfg_t.laser_noise else None,
               amp_red=cfg_t.red_laser_phase_amplitudes if cfg_t.laser_noise else None,
               amp_blue=cfg_t.blue_laser_phase_amplitudes if cfg_t.laser_noise else None, ode=_ode(ode_kwargs))
-    if world == 1:
+    if not distributed:
         ρ, ρ2, st = ctx.rydberg1_run(model, cfg_t.tspan, cfg_t.ψ0, cnt, **kw)
     else:
         ρ, ρ2, st = _allreduce_mean(
@@ -265,7 +282,7 @@ def simulation_czlp(cfg: CZLPConfig, seed=None, device=None, distributed=False, 
               f=cfg.f if cfg.laser_noise else None,
               amp_red=cfg.red_laser_phase_amplitudes if cfg.laser_noise else None,
               amp_blue=cfg.blue_laser_phase_amplitudes if cfg.laser_noise else None, ode=_ode(ode_kwargs))
-    if world == 1:
+    if not distributed:
         ρ, ρ2, st = ctx.rydberg2_run(model, cfg.tspan, cfg.ψ0, cnt, **kw)
     else:
         ρ, ρ2, st = _allreduce_mean(
@@ -305,26 +322,51 @@ def release_recapture(tspan, trap_params, atom_params, N, freq=10, skip=1000, ep
     lo, cnt, world = _shard(n, distributed)
     sd = _next_seed(seed)
     if not harmonic:
-        if world != 1:
-            raise _lib.ColdAtomsError(_abi.CA_ERR_UNSUPPORTED, "release_recapture(harmonic=false) is single-process")
-        smp, acc = ctx.sample_atoms_metropolis(trap_params, atom_params, n, freq=freq, skip=skip, harmonic=False, seed=sd)
-        probs, _, st = ctx.release_recapture(trap_params, atom_params, tspan, n, eps=eps, seed=sd, samples=smp)
+        # Metropolis branch: every rank runs its own set of independent chains for its share of the N atoms (the multi-chain sampler is
+        # already a decomposition of the reference's single chain; ranks differ by the Philox key) and the counts are all-reduced
+        rk = 0
+        if distributed:
+            import torch.distributed as dist
+            rk = dist.get_rank()
+        smp, acc = ctx.sample_atoms_metropolis(trap_params, atom_params, cnt, freq=freq, skip=skip, harmonic=False,
+                                               seed=(sd + 0x632BE59BD9B4E019 * rk) & 0xFFFFFFFFFFFFFFFF)
+        if not distributed:
+            probs, _, st = ctx.release_recapture(trap_params, atom_params, tspan, n, eps=eps, seed=sd, samples=smp)
+            _last_stats.clear()
+            _last_stats.update(st)
+            return probs, acc
+        probs, st = _allreduce_counts(ctx, lambda fl, dev: ctx.release_recapture(trap_params, atom_params, tspan, cnt, n_total=n, eps=eps, seed=sd,
+                                                                                 samples=smp, out_flags=fl, dev_out=dev)[2], len(tspan), n, extra=acc * cnt)
         _last_stats.clear()
         _last_stats.update(st)
-        return probs, acc
-    if world == 1:
+        return probs[:-1], float(probs[-1])   # acceptance rate: mean over the ranks' chains, weighted by their sample counts
+    if not distributed:
         probs, _, st = ctx.release_recapture(trap_params, atom_params, tspan, cnt, traj_offset=lo, n_total=n, eps=eps, seed=sd)
     else:
-        import torch
-        import torch.distributed as dist
-        counts, _, st = ctx.release_recapture(trap_params, atom_params, tspan, cnt, traj_offset=lo, n_total=n, eps=eps, seed=sd,
-                                              out_flags=_abi.CA_OUT_SUMS)
-        t = torch.from_numpy(counts).to(torch.device("cuda", ctx.device))
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        probs = t.cpu().numpy() / n
+        probs, st = _allreduce_counts(ctx, lambda fl, dev: ctx.release_recapture(trap_params, atom_params, tspan, cnt, traj_offset=lo, n_total=n,
+                                                                                 eps=eps, seed=sd, out_flags=fl, dev_out=dev)[2], len(tspan), n)
+        probs = probs[:-1]
     _last_stats.clear()
     _last_stats.update(st)
     return probs, 1.0
+
+
+def _allreduce_counts(ctx, run, nt, n_total, extra=0.0):
+    """Recapture counts stay on the device (CA_OUT_SUMS | CA_OUT_DEVICE), one NCCL all-reduce, then the division by N
+    (`recapture ./ N`, basic_experiments.jl:80).  `extra` rides along as an additional shard-additive slot."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", ctx.device)
+    buf = torch.zeros(nt + 1, dtype=torch.float64, device=dev)
+    buf[nt] = float(extra)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        st = run(_abi.CA_OUT_SUMS | _abi.CA_OUT_DEVICE, buf.data_ptr())
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        out = buf.cpu().numpy() / float(n_total)
+    finally:
+        ctx.reset_stream()
+    return out, st
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -2,9 +2,7 @@
 // the samplers and release-recapture.  The two-atom kernel lives in ca_lindblad2.cu.
 //
 // Kernels (SURVEY §8a "Kernel <-> reference mapping"):
-//   k_lindblad1<NS,SWEEP,BEAMS>  K1+K2+K3 fused: Philox atom sampler, phase-noise table generation and the DP5
-//                          Lindblad integrator, one trajectory per thread, state in registers; observables
-//                          reduced by warp shuffles and accumulated with fp64 RED atomics.
+//   k_lindblad1<NS,SWEEP,BEAMS>  K1+K2+K3 fused (ca_lindblad1.cuh; one translation unit per variant: ca_l1_inst.cu)
 //   k_finalize             K6: packed sums -> full column-major complex matrices, scaled by 1/N.
 //   k_release_recapture    K5.
 //   k_sample_atoms, k_phase_noise, k_eval_beam   exposed samplers / beam code for tests and helpers.
@@ -20,175 +18,19 @@
 #include <vector>
 
 #include "ca_host.h"
-#include "ca_device.cuh"
+#include "ca_lindblad1.cuh"
 
 namespace ca {
 
-// ----------------------------------------------------------------------------------------------------
-// device helpers
-// ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// ----------------------------------------------------------------------------------------------------
-// K1+K2+K3: fused one-atom ensemble kernel
-// ----------------------------------------------------------------------------------------------------
-template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? 96 : 128); }
-template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS <= 15 ? 20 : 0); }   // k slots + stage coefficients + anchors (NS <= 15)
-constexpr int kNoiseChunk = 64;
-
-struct R1Params {
-    DevModel model;            // single-point runs: lives in the constant bank with the other params
-    const DevModel* models;    // sweeps: one per point
-    const double* tspans;      // [n_points][nt]
-    const double* samples;     // NULL or [n_points*n_per_point][6]
-    const double* phases_red;  // NULL or [.][nf]
-    const double* phases_blue;
-    const NoiseK* nk_red;      // [n_points][nf] per-frequency recurrence constants (dtn depends on the point's t_end)
-    const NoiseK* nk_blue;
-    double* scratch;           // per-warp phase-noise tables [2][n_nodes_max][32] + coarse staging [n_coarse_max][32]
-    double* accum;             // [n_points][nt][kNV]
-    unsigned long long* counters;  // n_rhs, n_accept, n_reject, n_attempts, status(max |err|)
-    OdeOpts ode;
-    long long n_per_point, traj_offset, groups_per_point, n_groups;
-    unsigned long long seed;
-    int n_points, nt, nf, n_nodes_max, n_coarse_max;
-};
-
-template <int NS>
-__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 1 : (NS == 15 ? 2 : 1); }
-
-template <int NS, bool SWEEP, int BEAMS>
-__global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
-    constexpr int T = threads_for<NS>();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sk = reinterpret_cast<double*>(smem_raw);                                   // [6][NS][T] stage derivatives
-    double* scb = sk + 6 * NS * T;                                                      // [5][6][T] stage coefficients
-    double* sab = scb + 30 * T;                                                         // [2][2][5][T] beam anchors (NS <= 15)
-    DevModel* sm_models = reinterpret_cast<DevModel*>(sk + smem_doubles_per_thread<NS>() * T);  // [warps] (sweeps only)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wg = (long long)blockIdx.x * (T / 32) + warp;
-    const long long W = (long long)gridDim.x * (T / 32);
-    long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0, tot_exact = 0;
-    long long cyc_noise = 0, cyc_all = -clock64();
-    int worst = 0;
-    // All warps of a CTA walk the group list in lock-step (one barrier per 32-trajectory group): measured, the warps
-    // otherwise drift apart over a long ensemble and the instruction cache (the step is ~36 KB of code) thrashes:
-    // 85.8 -> 96.8 ms per wave between 3 and 27 waves.
-    const long long n_iter = (P.n_groups + W - 1) / W;
-    for (long long it = 0; it < n_iter; ++it) {
-        const long long g = wg + it * W;
-        __syncthreads();
-        if (g >= P.n_groups) continue;
-        const int pt = (int)(g / P.groups_per_point);
-        const long long il = (g - (long long)pt * P.groups_per_point) * 32 + lane;
-        const bool valid = il < P.n_per_point;
-        const long long li = (long long)pt * P.n_per_point + il;  // index into host-supplied arrays
-        const uint64_t gi = (uint64_t)(P.traj_offset + li);
-        if (SWEEP) {
-            __syncwarp();
-            const int nw = (int)(sizeof(DevModel) / sizeof(double));
-            const double* src = reinterpret_cast<const double*>(P.models + pt);
-            double* dst = reinterpret_cast<double*>(&sm_models[warp]);
-            for (int q = lane; q < nw; q += 32) dst[q] = src[q];
-            __syncwarp();
-        }
-        const DevModel* mp;
-        if constexpr (SWEEP) mp = &sm_models[warp]; else mp = &P.model;
-        const DevModel& m = *mp;
-        Rates rt;
-        rt.G0 = m.G0; rt.G1 = m.G1; rt.Gl = m.Gl; rt.Gr = m.Gr; rt.Gp = m.G0 + m.G1 + m.Gl; rt.gp2 = 0.5 * rt.Gp; rt.gr2 = 0.5 * m.Gr;
-        const double* tsp = P.tspans + (size_t)pt * P.nt;
-        // ---- K1: atom sample
-        double smp[6] = {0, 0, 0, 0, 0, 0};
-        if (valid && m.atom_motion) {
-            if (P.samples) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) smp[q] = P.samples[li * 6 + q];
-            } else {
-                SamplerConsts sc;
-#pragma unroll
-                for (int q = 0; q < 6; ++q) sc.sig[q] = m.sig[q];
-                sc.U0 = m.U0; sc.w0 = m.w0; sc.z0 = m.z0; sc.mfac = m.mfac; sc.ecut = m.ecut;
-                int att = sample_atom_literal(sc, P.seed, gi, 0u, smp);
-                if (att < 0) worst = max(worst, -CA_ERR_NONFINITE); else tot_att += att;
-            }
-        }
-        // ---- K2: phase-noise tables for this warp's 32 trajectories
-        double* tab = nullptr;
-        if (m.laser_noise && P.nf > 0) {
-            cyc_noise -= clock64();
-            tab = P.scratch + (size_t)wg * (2 * P.n_nodes_max + P.n_coarse_max) * 32 + lane;
-            if (valid) {
-                double* tmp = tab + (size_t)2 * P.n_nodes_max * 32;
-                gen_noise_trace_c<kNoiseChunk>(P.nk_red + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn, m.noise_coarse,
-                                               P.phases_red ? P.phases_red + li * P.nf : nullptr, P.seed, gi, 2u, tab, 32, tmp, 32);
-                gen_noise_trace_c<kNoiseChunk>(P.nk_blue + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn, m.noise_coarse,
-                                               P.phases_blue ? P.phases_blue + li * P.nf : nullptr, P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32, tmp, 32);
-            }
-            __syncwarp();
-            cyc_noise += clock64();
-        }
-        // ---- K3: integrate
-        Lane1<NS, BEAMS> L;
-        L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS <= 15 ? sab + threadIdx.x : nullptr);
-        if (!valid) L.t = 1e300;
-        const double tend = tsp[P.nt - 1];
-        unsigned n_att = 0;
-        double* acc_pt = P.accum + (size_t)pt * P.nt * kNV;
-        for (int j = 0; j < P.nt; ++j) {
-            const double T = tsp[j];
-            const double tstop = P.ode.dense ? tend : T;
-            while (true) {
-                const bool need = L.t < T;   // invalid and failed lanes are parked at t = +inf
-                if (!__any_sync(0xffffffffu, need)) break;
-                if (need) L.attempt(m, rt, P.ode, tstop, (n_att & (Lane1<NS, BEAMS>::kEvery - 1)) == 0);   // all lanes re-anchor their beam model together
-                ++n_att;
-            }
-            double v[kNV];
-            L.state_at(m, T, v);
-            second_moment<(NS > 9)>(v, m.rho2_mode, v + 25);
-            const bool ok = valid && L.status == 0;
-            double mine0 = 0.0, mine1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < kNV; ++q) {
-                double s = warp_sum(ok ? v[q] : 0.0);
-                if (q < 32) { if (lane == q) mine0 = s; }
-                else { if (lane == q - 32) mine1 = s; }
-            }
-            atomicAdd(acc_pt + (size_t)j * kNV + lane, mine0);
-            if (lane < kNV - 32) atomicAdd(acc_pt + (size_t)j * kNV + 32 + lane, mine1);
-        }
-        if (valid) { tot_rhs += L.n_rhs; tot_acc += L.n_acc; tot_rej += L.n_rej; tot_exact += L.n_exact; if (L.status) worst = max(worst, -L.status); }
-    }
-    // ---- statistics
-    tot_rhs = (long long)warp_sum((double)tot_rhs); tot_acc = (long long)warp_sum((double)tot_acc);
-    tot_rej = (long long)warp_sum((double)tot_rej); tot_att = (long long)warp_sum((double)tot_att);
-    tot_exact = (long long)warp_sum((double)tot_exact);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-    if (lane == 0) {
-        atomicAdd(P.counters + 0, (unsigned long long)tot_rhs);
-        atomicAdd(P.counters + 1, (unsigned long long)tot_acc);
-        atomicAdd(P.counters + 2, (unsigned long long)tot_rej);
-        atomicAdd(P.counters + 3, (unsigned long long)tot_att);
-        if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
-        atomicAdd(P.counters + 5, (unsigned long long)cyc_noise);               // warp-cycles in phase-noise generation
-        atomicAdd(P.counters + 6, (unsigned long long)(cyc_all + clock64()));   // warp-cycles in the whole kernel
-        atomicAdd(P.counters + 7, (unsigned long long)tot_exact);               // steps on the exact coefficient path
-    }
-}
-
-// K6: packed Hermitian sums -> column-major complex d x d matrices scaled by `scale`.
-__global__ void k_finalize5(const double* __restrict__ accum, long long n_mats, double scale, double* __restrict__ rho, double* __restrict__ rho2) {
+// K6: packed Hermitian sums -> column-major complex d x d matrices scaled by `scale`.  Output matrix i is accumulator matrix
+// i*stride + first (sweeps keep only the last time point of every grid point: stride = nt, first = nt - 1).
+__global__ void k_finalize5(const double* __restrict__ accum, long long n_mats, long long stride, long long first, double scale,
+                            double* __restrict__ rho, double* __restrict__ rho2) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_mats * 2) return;
     const long long mat = i >> 1;
     const int which = (int)(i & 1);
-    const double* p = accum + mat * kNV + which * 25;
+    const double* p = accum + (mat * stride + first) * kNV + which * 25;
     double* o = (which ? rho2 : rho) + mat * 50;
     const int off[5][5] = {{-1, 0, 1, 2, 3}, {-1, -1, 4, 5, 6}, {-1, -1, -1, 7, 8}, {-1, -1, -1, -1, 9}, {-1, -1, -1, -1, -1}};
     for (int b = 0; b < 5; ++b)
@@ -199,6 +41,11 @@ __global__ void k_finalize5(const double* __restrict__ accum, long long n_mats, 
             else { re = p[5 + 2 * off[b][a]]; im = -p[6 + 2 * off[b][a]]; }
             o[2 * (a + 5 * b)] = re * scale; o[2 * (a + 5 * b) + 1] = im * scale;
         }
+}
+
+__global__ void k_counts_to_double(const unsigned long long* __restrict__ counts, int nt, double scale, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nt) out[j] = (double)counts[j] * scale;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -377,6 +224,11 @@ struct ca_ctx {
     std::map<int, ca::DevBuf> extra;  // buffers of other translation units (ca_lindblad2.cu), by id
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    // most recent ensemble call (ca_collect_stats / ca_stats_to_device): its 8 device counters, size and launch count
+    unsigned long long* last_counters = nullptr;
+    long long last_n = 0;
+    int last_launches = 0;
+    int last_kind = 0;   // 1: one-atom (counters[5..7] = noise cycles, total cycles, exact-coefficient steps), 2: two-atom
 };
 
 namespace ca {
@@ -407,13 +259,45 @@ void* ctx_buf(ca_ctx* c, int which, size_t bytes) {
     return b.p;
 }
 
-template <int NS, bool SWEEP, int BEAMS>
-static int launch_lindblad1(ca_ctx* c, const R1Params& P, int grid) {
-    constexpr int T = threads_for<NS>();
-    const size_t smem = sizeof(double) * smem_doubles_per_thread<NS>() * T + (SWEEP ? sizeof(DevModel) * (T / 32) : 0);
-    CA_CUDA(cudaFuncSetAttribute(k_lindblad1<NS, SWEEP, BEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_lindblad1<NS, SWEEP, BEAMS><<<grid, T, smem, c->stream>>>(P);
-    CA_CUDA(cudaGetLastError());
+void ctx_set_last(ca_ctx* c, unsigned long long* counters, long long n, int launches, int kind) {
+    c->last_counters = counters; c->last_n = n; c->last_launches = launches; c->last_kind = kind;
+}
+
+// counters -> 8 doubles that add across shards (ca_stats_to_device)
+__global__ void k_export_counters(const unsigned long long* __restrict__ cnt, long long n, int kind, double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i >= 8) return;
+    double v;
+    if (i < 4) v = (double)cnt[i];
+    else if (i == 4) v = cnt[4] == (unsigned long long)(-CA_ERR_MAXITERS) ? 1.0 : 0.0;
+    else if (i == 5) v = cnt[4] == (unsigned long long)(-CA_ERR_NONFINITE) ? 1.0 : 0.0;
+    else if (i == 6) v = kind == 1 ? (double)cnt[7] : 0.0;
+    else v = (double)n;
+    out[i] = v;
+}
+
+// Synchronise, read the counters of the most recent ensemble call and report them (the tail of every synchronous call; the whole of
+// ca_collect_stats after a CA_OUT_DEVICE call).
+int collect_last(ca_ctx* c, ca_stats* stats) {
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (!c->last_counters) { set_error("no ensemble call has run on this context"); return CA_ERR_ARG; }
+    unsigned long long hc[8];
+    CA_CUDA(cudaMemcpyAsync(hc, c->last_counters, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+    CA_CUDA(cudaStreamSynchronize(c->stream));
+    const int status = hc[4] ? -(int)hc[4] : 0;
+    if (stats) {
+        stats->n_traj = c->last_n; stats->n_rhs = (int64_t)hc[0]; stats->n_accept = (int64_t)hc[1]; stats->n_reject = (int64_t)hc[2];
+        stats->n_sample_attempts = (int64_t)hc[3]; stats->n_launches = c->last_launches; stats->status = status;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); stats->kernel_ms = ms;
+        if (c->last_kind == 1) {
+            stats->noise_ms = hc[6] ? ms * (double)hc[5] / (double)hc[6] : 0.0;  // share of warp-cycles spent generating noise tables
+            stats->n_exact_steps = (int64_t)hc[7];
+        }
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); stats->total_ms = ms;
+    }
+    if (status == CA_ERR_MAXITERS) { set_error("a trajectory hit maxiters (it is left out of the sums)"); return status; }
+    if (status) { set_error("a trajectory produced a non-finite state or the step size underflowed (it is left out of the sums)"); return status; }
     return CA_OK;
 }
 
@@ -515,23 +399,17 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
             n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
             n_free += dm[p].free_motion != 0;
         }
-#ifdef CA_FAST_BUILD   // developer builds (profiles/dev_fast.sh): only the R1 variant (CA_FAST_BUILD=2: only the flat-top R2 variant) is compiled
-        constexpr int kFastBeams = (CA_FAST_BUILD + 0) == 2 ? 2 : 1;
-        if (ns == 9 && !sweep && n_free == n_points && n_gp == (kFastBeams == 1 ? n_points : 0)) rc = launch_lindblad1<9, false, kFastBeams>(c, P, grid);
-        else { set_error("CA_FAST_BUILD: only one free-flight ket_1 variant is compiled"); rc = CA_ERR_UNSUPPORTED; }
-#else
+        cudaError_t le;
         if (ns == 9) {
-            if (n_gp == n_points && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 1>(c, P, grid) : launch_lindblad1<9, false, 1>(c, P, grid);
-            else if (n_gp == 0 && n_free == n_points) rc = sweep ? launch_lindblad1<9, true, 2>(c, P, grid) : launch_lindblad1<9, false, 2>(c, P, grid);
-            else if (n_gp == n_points && n_free == 0) rc = sweep ? launch_lindblad1<9, true, 3>(c, P, grid) : launch_lindblad1<9, false, 3>(c, P, grid);
-            else rc = sweep ? launch_lindblad1<9, true, 0>(c, P, grid) : launch_lindblad1<9, false, 0>(c, P, grid);
+            if (n_gp == n_points && n_free == n_points) le = launch_l1_9_1(sweep, c->stream, P, grid);
+            else if (n_gp == 0 && n_free == n_points) le = launch_l1_9_2(sweep, c->stream, P, grid);
+            else if (n_gp == n_points && n_free == 0) le = launch_l1_9_3(sweep, c->stream, P, grid);
+            else le = launch_l1_9_0(sweep, c->stream, P, grid);
         } else if (ns == 15) {
-            if (n_gp == n_points && n_free == n_points) rc = sweep ? launch_lindblad1<15, true, 1>(c, P, grid) : launch_lindblad1<15, false, 1>(c, P, grid);
-            else rc = sweep ? launch_lindblad1<15, true, 0>(c, P, grid) : launch_lindblad1<15, false, 0>(c, P, grid);
-        }
-        else rc = sweep ? launch_lindblad1<21, true, 0>(c, P, grid) : launch_lindblad1<21, false, 0>(c, P, grid);
-#endif
-        if (rc) return rc;
+            if (n_gp == n_points && n_free == n_points) le = launch_l1_15_1(sweep, c->stream, P, grid);
+            else le = launch_l1_15_0(sweep, c->stream, P, grid);
+        } else le = launch_l1_21_0(sweep, c->stream, P, grid);
+        if (le != cudaSuccess) { set_error(std::string("k_lindblad1 launch: ") + cudaGetErrorString(le)); return CA_ERR_CUDA; }
         ++launches;
     }
     CA_CUDA(cudaEventRecord(c->ev[2], c->stream));
@@ -541,60 +419,27 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     double *d_rho, *d_rho2;
     if (out_flags & CA_OUT_DEVICE) { d_rho = rho; d_rho2 = rho2; }
     else {
-        if ((rc = c->out.ensure(sizeof(double) * 100 * n_mats))) return rc;
-        d_rho = (double*)c->out.p; d_rho2 = d_rho + 50 * n_mats;
+        if ((rc = c->out.ensure(sizeof(double) * 100 * out_mats))) return rc;
+        d_rho = (double*)c->out.p; d_rho2 = d_rho + 50 * out_mats;
     }
-    if (last_only && !(out_flags & CA_OUT_DEVICE)) {
-        k_finalize5<<<(unsigned)((n_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)n_mats, div, d_rho, d_rho2);
-    } else if (last_only) {
-        // device output of a sweep: finalize into scratch then gather the last time point of each point
-        if ((rc = c->out.ensure(sizeof(double) * 100 * n_mats))) return rc;
-        double* t1 = (double*)c->out.p;
-        k_finalize5<<<(unsigned)((n_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)n_mats, div, t1, t1 + 50 * n_mats);
-        for (int p = 0; p < n_points; ++p) {
-            CA_CUDA(cudaMemcpyAsync(d_rho + 50 * (size_t)p, t1 + 50 * ((size_t)p * nt + nt - 1), 400, cudaMemcpyDeviceToDevice, c->stream));
-            CA_CUDA(cudaMemcpyAsync(d_rho2 + 50 * (size_t)p, t1 + 50 * n_mats + 50 * ((size_t)p * nt + nt - 1), 400, cudaMemcpyDeviceToDevice, c->stream));
-        }
-    } else {
-        k_finalize5<<<(unsigned)((n_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)n_mats, div, d_rho, d_rho2);
-    }
+    k_finalize5<<<(unsigned)((out_mats * 2 + 127) / 128), 128, 0, c->stream>>>(P.accum, (long long)out_mats, last_only ? nt : 1, last_only ? nt - 1 : 0,
+                                                                             div, d_rho, d_rho2);
     CA_CUDA(cudaGetLastError());
     ++launches;
     CA_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    if (out_flags & CA_OUT_DEVICE) {
+    ctx_set_last(c, P.counters, n_all, launches, 1);
+    if (out_flags & CA_OUT_DEVICE) {   // asynchronous: the device-side status is read later (ca_collect_stats / ca_stats_to_device)
         if (stats) { std::memset(stats, 0, sizeof *stats); stats->n_traj = n_all; stats->n_launches = launches; }
         return CA_OK;
     }
-    if ((rc = ensure_pinned(c, sizeof(double) * 100 * n_mats + 64))) return rc;
+    if ((rc = ensure_pinned(c, sizeof(double) * 100 * out_mats + 64))) return rc;
     double* hp = (double*)c->pinned;
-    CA_CUDA(cudaMemcpyAsync(hp, d_rho, sizeof(double) * 100 * n_mats, cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long* hc = (unsigned long long*)(hp + 100 * n_mats);
-    CA_CUDA(cudaMemcpyAsync(hc, c->counters.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CA_CUDA(cudaStreamSynchronize(c->stream));
-    if (last_only) {
-        for (int p = 0; p < n_points; ++p) {
-            std::memcpy(rho + 50 * (size_t)p, hp + 50 * ((size_t)p * nt + nt - 1), 400);
-            std::memcpy(rho2 + 50 * (size_t)p, hp + 50 * n_mats + 50 * ((size_t)p * nt + nt - 1), 400);
-        }
-    } else {
-        std::memcpy(rho, hp, sizeof(double) * 50 * n_mats);
-        std::memcpy(rho2, hp + 50 * n_mats, sizeof(double) * 50 * n_mats);
-    }
-    (void)out_mats;
-    int status = hc[4] ? -(int)hc[4] : 0;
-    if (std::getenv("CA_DEBUG_STATS")) std::fprintf(stderr, "k_lindblad1: steps %llu, exact-coefficient steps %llu\n", hc[1] + hc[2], hc[7]);
-    if (stats) {
-        std::memset(stats, 0, sizeof *stats);
-        stats->n_traj = n_all; stats->n_rhs = (int64_t)hc[0]; stats->n_accept = (int64_t)hc[1]; stats->n_reject = (int64_t)hc[2];
-        stats->n_sample_attempts = (int64_t)hc[3]; stats->n_launches = launches; stats->status = status;
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); stats->kernel_ms = ms;
-        stats->noise_ms = hc[6] ? ms * (double)hc[5] / (double)hc[6] : 0.0;  // share of warp-cycles spent generating noise tables
-        cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); stats->total_ms = ms;
-    }
-    if (status == CA_ERR_MAXITERS) { set_error("a trajectory hit maxiters"); return status; }
-    if (status) { set_error("a trajectory produced a non-finite state or the step size underflowed"); return status; }
-    return CA_OK;
+    CA_CUDA(cudaMemcpyAsync(hp, d_rho, sizeof(double) * 100 * out_mats, cudaMemcpyDeviceToHost, c->stream));
+    rc = collect_last(c, stats);   // synchronises
+    if (rc == CA_ERR_CUDA || rc == CA_ERR_ARG) return rc;
+    std::memcpy(rho, hp, sizeof(double) * 50 * out_mats);
+    std::memcpy(rho2, hp + 50 * out_mats, sizeof(double) * 50 * out_mats);
+    return rc;
 }
 
 }  // namespace ca
@@ -666,6 +511,21 @@ int ca_synchronize(ca_ctx* c) {
     return CA_OK;
 }
 
+int ca_collect_stats(ca_ctx* c, ca_stats* stats) {
+    if (!c) { set_error("null context"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    return collect_last(c, stats);
+}
+
+int ca_stats_to_device(ca_ctx* c, double* dev_out8) {
+    if (!c || !dev_out8) { set_error("bad argument"); return CA_ERR_ARG; }
+    if (!c->last_counters) { set_error("no ensemble call has run on this context"); return CA_ERR_ARG; }
+    CA_CUDA(cudaSetDevice(c->device));
+    k_export_counters<<<1, 32, 0, c->stream>>>(c->last_counters, c->last_n, c->last_kind, dev_out8);
+    CA_CUDA(cudaGetLastError());
+    return CA_OK;
+}
+
 int ca_measure_fp64_peak(ca_ctx* c, double* tflops, double* sm_mhz_est) {
     if (!c || !tflops) { set_error("bad argument"); return CA_ERR_ARG; }
     CA_CUDA(cudaSetDevice(c->device));
@@ -711,7 +571,7 @@ int ca_release_recapture(ca_ctx* c, const double* trap, const double* atom, cons
                          int64_t traj_offset, int64_t n_total, double eps, uint64_t seed, const double* samples, int32_t out_flags,
                          double* probs, uint8_t* indicators, ca_stats* stats) {
     if (!c || !trap || !atom || !tspan || nt < 1 || n < 0 || !probs) { set_error("bad argument"); return CA_ERR_ARG; }
-    if (out_flags & CA_OUT_DEVICE) { set_error("CA_OUT_DEVICE is not supported by ca_release_recapture"); return CA_ERR_UNSUPPORTED; }
+    if ((out_flags & CA_OUT_DEVICE) && indicators) { set_error("CA_OUT_DEVICE: indicators must be NULL"); return CA_ERR_ARG; }
     CA_CUDA(cudaSetDevice(c->device));
     ca_model m;
     std::memset(&m, 0, sizeof m);
@@ -740,6 +600,14 @@ int ca_release_recapture(ca_ctx* c, const double* trap, const double* atom, cons
         CA_CUDA(cudaGetLastError());
     }
     CA_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if (out_flags & CA_OUT_DEVICE) {   // counts (or means) as doubles straight into the caller's device buffer; no synchronisation
+        const double sc_ = (out_flags & CA_OUT_SUMS) ? 1.0 : 1.0 / (double)(n_total > 0 ? n_total : n);
+        k_counts_to_double<<<(nt + 127) / 128, 128, 0, c->stream>>>(d_counts, nt, sc_, probs);
+        CA_CUDA(cudaGetLastError());
+        CA_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->n_traj = n; stats->n_launches = (n > 0 ? 1 : 0) + 1; }
+        return CA_OK;
+    }
     if ((rc = ensure_pinned(c, sizeof(unsigned long long) * ((size_t)nt + 8)))) return rc;
     CA_CUDA(cudaMemcpyAsync(c->pinned, d_counts, sizeof(unsigned long long) * ((size_t)nt + 8), cudaMemcpyDeviceToHost, c->stream));
     if (d_ind) CA_CUDA(cudaMemcpyAsync(indicators, d_ind, (size_t)n * nt, cudaMemcpyDeviceToHost, c->stream));

@@ -20,6 +20,8 @@ int ctx_sm_count(ca_ctx* c);
 int ctx_device(ca_ctx* c);
 void* ctx_buf(ca_ctx* c, int which, size_t bytes);  // grow-only device buffers owned by the context
 cudaEvent_t ctx_event(ca_ctx* c, int i);
+void ctx_set_last(ca_ctx* c, unsigned long long* counters, long long n, int launches, int kind);
+int collect_last(ca_ctx* c, ca_stats* stats);
 
 #ifndef CA_WARPS2
 #define CA_WARPS2 8
@@ -361,25 +363,12 @@ extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* t
         ++launches;
     }
     CA_CUDA2(cudaEventRecord(e3, s));
-    if (out_flags & CA_OUT_DEVICE) {
+    ctx_set_last(c, P.counters, n_traj, launches, 2);
+    if (out_flags & CA_OUT_DEVICE) {   // asynchronous: the device-side status is read later (ca_collect_stats / ca_stats_to_device)
         if (stats) { std::memset(stats, 0, sizeof *stats); stats->n_traj = n_traj; stats->n_launches = launches; }
         return CA_OK;
     }
-    unsigned long long hc[8];
     CA_CUDA2(cudaMemcpyAsync(rho, d_rho, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, s));
     CA_CUDA2(cudaMemcpyAsync(rho2, d_rho2, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, s));
-    CA_CUDA2(cudaMemcpyAsync(hc, P.counters, 64, cudaMemcpyDeviceToHost, s));
-    CA_CUDA2(cudaStreamSynchronize(s));
-    const int status = hc[4] ? -(int)hc[4] : 0;
-    if (stats) {
-        std::memset(stats, 0, sizeof *stats);
-        stats->n_traj = n_traj; stats->n_rhs = (int64_t)hc[0]; stats->n_accept = (int64_t)hc[1]; stats->n_reject = (int64_t)hc[2];
-        stats->n_sample_attempts = (int64_t)hc[3]; stats->n_launches = launches; stats->status = status;
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e1, e2); stats->kernel_ms = ms;
-        cudaEventElapsedTime(&ms, e0, e3); stats->total_ms = ms;
-    }
-    if (status == CA_ERR_MAXITERS) { set_error("a trajectory hit maxiters"); return status; }
-    if (status) { set_error("a trajectory produced a non-finite state or the step size underflowed"); return status; }
-    return CA_OK;
+    return collect_last(c, stats);   // synchronises; reports a trajectory that hit maxiters / went non-finite
 }

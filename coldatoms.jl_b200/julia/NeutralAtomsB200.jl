@@ -57,7 +57,8 @@ mutable struct CaStats
     n_traj::Int64; n_rhs::Int64; n_accept::Int64; n_reject::Int64; n_sample_attempts::Int64
     kernel_ms::Float64; total_ms::Float64; noise_ms::Float64
     n_launches::Int32; status::Int32
-    CaStats() = new(0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
+    n_exact_steps::Int64
+    CaStats() = new(0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0, 0)
 end
 
 const BEAM_GAUSS, BEAM_HG, BEAM_LG, BEAM_UNIFORM = Int32(0), Int32(1), Int32(2), Int32(3)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CA_VERSION 100 /* 0.1.0 */
+#define CA_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define CA_OK 0
@@ -47,6 +47,7 @@ extern "C" {
 #define CA_ERR_NONFINITE (-5) /* a trajectory produced a non-finite state or dt underflow */
 #define CA_ERR_UNSUPPORTED (-6)
 #define CA_ERR_NOMEM (-7)
+#define CA_ERR_NCCL (-8)      /* NCCL missing (libnccl.so.2 could not be loaded) or a NCCL call failed */
 
 /* beam kinds: Ω dispatch of src/rydberg_model.jl:51-74 and Ω_red/Ω_blue of src/rydberg_model_arb_bms.jl:1-13 */
 #define CA_BEAM_GAUSS 0      /* 5-param TEM00 in the θ-rotated frame: Ω0*A*A_phase (utilities.jl:27-48) */
@@ -136,6 +137,8 @@ typedef struct ca_stats {
     double noise_ms;    /* device time of the phase-noise table kernel */
     int32_t n_launches; /* kernels launched by this call */
     int32_t status;     /* 0 ok, or the CA_ERR_* observed on device */
+    int64_t n_exact_steps; /* one-atom path: attempted steps whose Hamiltonian coefficients took the exact evaluation instead
+                              of the anchored model (guard failed / generic variant); 0 on the other paths */
 } ca_stats;
 
 int ca_version(void);
@@ -149,6 +152,19 @@ int ca_finalize(ca_ctx* ctx);
 int ca_set_stream(ca_ctx* ctx, void* cuda_stream);
 int ca_reset_stream(ca_ctx* ctx);
 int ca_synchronize(ca_ctx* ctx);
+/*
+ * Deferred statistics of the most recent ensemble call on this context (ca_rydberg1_run / _sweep / ca_rydberg2_run).
+ * A CA_OUT_DEVICE call returns without synchronising, so its device-side status (a trajectory that hit maxiters or went
+ * non-finite is LEFT OUT of the sums) cannot be part of its return value:
+ *   ca_collect_stats     synchronises the context stream, fills *stats and returns the status the synchronous call would
+ *                        have returned (CA_OK / CA_ERR_MAXITERS / CA_ERR_NONFINITE);
+ *   ca_stats_to_device   enqueues (no synchronisation) the conversion of the counters into 8 doubles at dev_out8 (device
+ *                        pointer): n_rhs, n_accept, n_reject, n_sample_attempts, #(status == MAXITERS) in {0,1},
+ *                        #(status == NONFINITE) in {0,1}, n_exact_steps, n_traj.  All eight ADD across shards, so a
+ *                        multi-GPU caller appends them to the buffer it all-reduces and every rank sees the same status.
+ */
+int ca_collect_stats(ca_ctx* ctx, ca_stats* stats);
+int ca_stats_to_device(ca_ctx* ctx, double* dev_out8);
 /* Measured FP64 FMA throughput of the device in TFLOP/s (2 flop per DFMA); roofline denominator. */
 int ca_measure_fp64_peak(ca_ctx* ctx, double* tflops, double* sm_mhz_est);
 
@@ -198,7 +214,8 @@ int ca_rydberg1_sweep(ca_ctx* ctx, const ca_model* models, const double* psi0s, 
 /*
  * Release and recapture (basic_experiments.jl:25-81).  trap = (U0,w0,z0), atom = (m,T).
  * samples NULL -> Philox harmonic sampler (sampler eps stays 1e-2: basic_experiments.jl:73).
- * probs[nt]: mean indicator (CA_OUT_MEAN) or counts as doubles (CA_OUT_SUMS).
+ * probs[nt]: mean indicator (CA_OUT_MEAN) or counts as doubles (CA_OUT_SUMS); with CA_OUT_DEVICE a device pointer, written on
+ * the context stream without synchronising (indicators must be NULL then; stats carry no sampler count).
  * indicators: NULL or n x nt bytes (host) for bit-exact parity.
  */
 int ca_release_recapture(ca_ctx* ctx, const double* trap, const double* atom, const double* tspan,
@@ -247,6 +264,45 @@ int ca_eval_beam(ca_ctx* ctx, const ca_beam* beam, const double* xyz /* n x 3 ho
 int ca_thermal_average(ca_ctx* ctx, int32_t kind, const ca_model* model, int64_t n, int64_t traj_offset,
                        uint64_t seed, double eps, const double* samples1, const double* samples2,
                        double* sums_out /* 2 host */, int64_t* attempts_out);
+
+/*
+ * ---- several GPUs in ONE process (the dead simulation_mpi of src/rydberg_model.jl:309-383 meant to MPI.Reduce the
+ * same payload) -----------------------------------------------------------------------------------------------------------
+ * ca_init_multi creates one context per listed device (devices == NULL: 0..ndev-1; ndev <= 0: every visible device) and, for
+ * ndev > 1, one NCCL clique (ncclCommInitAll; libnccl.so.2 is loaded with dlopen on first use, so single-GPU users never need it).
+ * The *_multi ensemble calls take exactly the arguments of their single-GPU counterparts (host output only: CA_OUT_MEAN or
+ * CA_OUT_SUMS).  Device g integrates the contiguous slice [g*n/G, (g+1)*n/G) of the trajectory index space -- the Philox streams
+ * are keyed by the GLOBAL index, so the ensemble is the one a single GPU would draw --, every device leaves its un-normalised
+ * sums in its own HBM, and ONE ncclAllReduce(sum, fp64) per call combines [sum rho | sum rho*rho | 8 counters] over NVLink.
+ * The counters carry the device-side status: a trajectory that hit maxiters / went non-finite on ANY device fails the call.
+ * ca_rydberg1_sweep_multi shards by grid point instead and needs no collective (results are gathered on the host).
+ */
+typedef struct ca_multi ca_multi;
+int ca_init_multi(const int* devices, int32_t ndev, ca_multi** out);
+int ca_finalize_multi(ca_multi* m);
+int ca_multi_size(const ca_multi* m);            /* number of devices */
+ca_ctx* ca_multi_context(ca_multi* m, int32_t i); /* the i-th single-GPU context (owned by m) */
+int ca_rydberg1_run_multi(ca_multi* m, const ca_model* model, const double* tspan, int32_t nt,
+                          const double* psi0, int64_t n_traj, int64_t traj_offset, int64_t n_total,
+                          uint64_t seed, const double* samples, const double* phases_red,
+                          const double* phases_blue, const double* f, const double* amp_red,
+                          const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags,
+                          double* rho, double* rho2, ca_stats* stats);
+int ca_rydberg2_run_multi(ca_multi* m, const ca_model* model, const double* tspan, int32_t nt,
+                          const double* psi0, int64_t n_traj, int64_t traj_offset, int64_t n_total,
+                          uint64_t seed, const double* samples1, const double* samples2,
+                          const double* const* phases4, const double* f, const double* amp_red,
+                          const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags,
+                          double* rho, double* rho2, ca_stats* stats);
+int ca_rydberg1_sweep_multi(ca_multi* m, const ca_model* models, const double* psi0s, const double* t_end,
+                            int32_t n_points, int64_t n_traj_per_point, int64_t traj_offset, int64_t n_total,
+                            uint64_t seed, const double* f, const double* amp_red, const double* amp_blue,
+                            int32_t nf, const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2,
+                            ca_stats* stats);
+int ca_release_recapture_multi(ca_multi* m, const double* trap, const double* atom, const double* tspan,
+                               int32_t nt, int64_t n, int64_t traj_offset, int64_t n_total, double eps,
+                               uint64_t seed, const double* samples, int32_t out_flags, double* probs,
+                               ca_stats* stats);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = pkg._lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ca_version() == 100
+    assert lib.ca_version() == 200
 
 
 def test_no_cpu_fallback(pkg):
@@ -47,7 +47,7 @@ def test_struct_layouts_match_header(pkg):
     abi = pkg._abi
     assert C.sizeof(abi.ca_beam) == 6 * 8 + 5 * 4 + 4  # 72 with tail padding
     assert C.sizeof(abi.ca_ode_opts) == 48
-    assert C.sizeof(abi.ca_stats) == 5 * 8 + 3 * 8 + 8
+    assert C.sizeof(abi.ca_stats) == 5 * 8 + 3 * 8 + 8 + 8
     assert C.sizeof(abi.ca_model) == 5 * 8 + 2 * 72 + 6 * 8 + 12 * 4 + 6 * 8 + 16
 
 
