@@ -271,7 +271,7 @@ __global__ void k_export_counters(const unsigned long long* __restrict__ cnt, lo
     if (i < 4) v = (double)cnt[i];
     else if (i == 4) v = cnt[4] == (unsigned long long)(-CA_ERR_MAXITERS) ? 1.0 : 0.0;
     else if (i == 5) v = cnt[4] == (unsigned long long)(-CA_ERR_NONFINITE) ? 1.0 : 0.0;
-    else if (i == 6) v = kind == 1 ? (double)cnt[7] : 0.0;
+    else if (i == 6) v = (double)cnt[kind == 1 ? 7 : 5];
     else v = (double)n;
     out[i] = v;
 }
@@ -293,7 +293,7 @@ int collect_last(ca_ctx* c, ca_stats* stats) {
         if (c->last_kind == 1) {
             stats->noise_ms = hc[6] ? ms * (double)hc[5] / (double)hc[6] : 0.0;  // share of warp-cycles spent generating noise tables
             stats->n_exact_steps = (int64_t)hc[7];
-        }
+        } else stats->n_exact_steps = (int64_t)hc[5];
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); stats->total_ms = ms;
     }
     if (status == CA_ERR_MAXITERS) { set_error("a trajectory hit maxiters (it is left out of the sums)"); return status; }

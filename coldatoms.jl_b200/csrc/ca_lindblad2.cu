@@ -54,6 +54,7 @@ struct DevWarp {
     double *xm, *xp, *kb;
     Coef2* coef;
     double* smp;
+    double* anc;   // per-lane anchor slots anc[slot * 32]
 #ifdef CA_TIMERS
     long long tm[4] = {0, 0, 0, 0}, tl = 0;   // cycles: 0 noise+sampling, 1 coefficients, 2 stage-7 RHS, 3 everything else
     __device__ __forceinline__ void tick(int i) { const long long c = clock64(); tm[i] += c - tl; tl = c; }
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
     W.lane = lane; W.xm = base; W.xp = base + kXN; W.kb = base + 2 * kXN + lane;
     W.coef = reinterpret_cast<Coef2*>(base + 2 * kXN + kKB * kS2 * 32);
     W.smp = base + 2 * kXN + kKB * kS2 * 32 + kStages2 * 16;
+    W.anc = W.smp + 12 + lane;
 #ifdef CA_TIMERS
     W.tl = clock64();
 #endif
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
 #pragma unroll
     for (int s = 0; s < kS2; ++s) rho0[s] = P.rho0m[lane * kS2 + s];
     const long long wg = (long long)blockIdx.x * kWarps2 + wi, Wn = (long long)gridDim.x * kWarps2;
-    long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0;
+    long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0, tot_exact = 0;
     int worst = 0;
     double* acc_w = P.accum + (size_t)wg * P.nt * 2 * kAccSlots * 32 + lane;
     double* tab_w = (m.laser_noise && P.nf > 0) ? P.scratch + (size_t)wg * 4 * m.n_nodes : nullptr;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         CA_TICK(W, 0);
         Stats2 st;
         integrate2(W, L, m, P.ode, P.tspan, P.nt, tab_w, rho0, P.tr0, acc_w, st);
-        tot_rhs += st.n_rhs; tot_acc += st.n_acc; tot_rej += st.n_rej;
+        tot_rhs += st.n_rhs; tot_acc += st.n_acc; tot_rej += st.n_rej; tot_exact += st.n_exact;
         if (st.status) worst = max(worst, -st.status);
         unsigned long long nx = 0;
         if (lane == 0) nx = atomicAdd(P.counters + 7, 1ull);
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         __syncwarp();
     }
     tot_att = (long long)W.sum((double)tot_att);
+    tot_exact = (long long)W.sum((double)tot_exact);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
     if (lane == 0) {
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
         atomicAdd(P.counters + 2, (unsigned long long)tot_rej);
         atomicAdd(P.counters + 3, (unsigned long long)tot_att);
         if (worst) atomicMax(P.counters + 4, (unsigned long long)worst);
+        atomicAdd(P.counters + 5, (unsigned long long)tot_exact);   // (lane, step) beam evaluations that took the exact path
 #ifdef CA_TIMERS
         if (wg == 0 || wg == 777) printf("timers (warp %lld, cycles): noise %lld coef %lld rhs7 %lld other %lld | rhs %lld steps %lld\n", wg, W.tm[0], W.tm[1], W.tm[2], W.tm[3], tot_rhs, tot_acc + tot_rej);
 #endif

@@ -25,6 +25,18 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         model = pkg.blue_intens_model([86.9091835, 70.0], [1000.0, 1.1, pkg.w0_to_z0(1.1, 0.852, 1.3)], [Ω, 100.0, pkg.w0_to_z0(100.0, 0.795)], blue,
                                       [Δ0, pkg.δ_twophoton(Ω, Ω, Δ0)], [Γ / 4, 3 * Γ / 4])
         run = lambda: ctx.rydberg1_run(model, tspan, pkg.ket_1, n, seed=7)   # noqa: E731
+    elif os.environ.get("AB_WORKLOAD") == "z1":   # two-atom CZ (BASELINE config 4); AB_TEND shortens the window
+        _, cz = pkg.get_default_configs()
+        cz.laser_noise = True
+        m2 = pkg.model_from_config(cz, two_atom=True)
+        ts = np.array([0.0, float(os.environ.get("AB_TEND", cz.tspan[-1]))])
+        run = lambda: ctx.rydberg2_run(m2, ts, cz.ψ0, n, seed=7, f=cz.f, amp_red=cz.red_laser_phase_amplitudes,   # noqa: E731
+                                       amp_blue=cz.blue_laser_phase_amplitudes, ode=pkg._abi.ode_opts(maxiters=10 ** 7))
+    elif os.environ.get("AB_WORKLOAD") == "ns15":   # R1 with a superposition initial state (fidelity callers)
+        model = pkg.model_from_config(cfg)
+        psi = (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2)
+        run = lambda: ctx.rydberg1_run(model, cfg.tspan, psi, n, seed=7, f=cfg.f, amp_red=cfg.red_laser_phase_amplitudes,   # noqa: E731
+                                       amp_blue=cfg.blue_laser_phase_amplitudes)
     else:
         model = pkg.model_from_config(cfg)
         run = lambda: ctx.rydberg1_run(model, cfg.tspan, cfg.ψ0, n, seed=7, f=cfg.f, amp_red=cfg.red_laser_phase_amplitudes,   # noqa: E731
@@ -33,7 +45,8 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         rho, rho2, st = run()
         best = st["kernel_ms"] if best is None else min(best, st["kernel_ms"])
     np.save(sys.argv[3], rho)
-    print("kernel_ms %.2f traj/s %.0f rhs/traj %.1f rej %d" % (best, n / best * 1e3, st["n_rhs"] / n, st["n_reject"]), flush=True)
+    print("kernel_ms %.2f traj/s %.0f rhs/traj %.1f rhs/s %.3g rej %d exact %d" % (best, n / best * 1e3, st["n_rhs"] / n, st["n_rhs"] / best * 1e3, st["n_reject"],
+                                                                                 st.get("n_exact_steps", 0)), flush=True)
     sys.exit(0)
 
 n = int(sys.argv[1])

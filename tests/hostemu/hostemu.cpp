@@ -48,6 +48,7 @@ struct HostWarp {
     double *xm, *xp, *kb;
     Coef2* coef;
     double* smp;
+    double* anc;
     HostShared* sh;
     void sync() { pthread_barrier_wait(&sh->bar); }
     double sum(double v) {
@@ -130,6 +131,7 @@ int he_rydberg2_traj(const ca_model* model, const double* tspan, int nt, const d
         w.lane = l; w.xm = base; w.xp = base + kXN; w.kb = base + 2 * kXN + l;
         w.coef = reinterpret_cast<Coef2*>(base + 2 * kXN + kKB * kS2 * 32);
         w.smp = base + 2 * kXN + kKB * kS2 * 32 + kStages2 * 16;
+        w.anc = w.smp + 12 + l;
         w.sh = &sh;
         la[l].m = &m; la[l].oo = &oo; la[l].tspan = tspan; la[l].nt = nt; la[l].tab = tp; la[l].rho0 = rho0m + l * kS2; la[l].tr0 = tr0;
         la[l].acc = acc.data() + l;
@@ -149,6 +151,8 @@ int he_rydberg2_traj(const ca_model* model, const double* tspan, int nt, const d
                     scatter_entry(l, s, a[s * 32 + l], a[ts * 32 + tl], (which ? rho2 : rho) + (size_t)j * 1250);
                 }
     stats[0] = la[0].st.n_rhs; stats[1] = la[0].st.n_acc; stats[2] = la[0].st.n_rej;
+    stats[3] = 0;
+    for (int l = 0; l < 32; ++l) stats[3] += la[l].st.n_exact;
     return la[0].st.status;
 }
 

@@ -141,7 +141,7 @@ def he_traj2(he, model, tspan, psi0, s1, s2, ph4, f, ar, ab, ode, seed=1, gi=0):
     tspan = np.ascontiguousarray(tspan, float)
     nt = len(tspan)
     rho, rho2 = np.zeros((nt, 25, 25), complex), np.zeros((nt, 25, 25), complex)
-    st = (C.c_longlong * 3)()
+    st = (C.c_longlong * 4)()
     psi = np.ascontiguousarray(np.asarray(psi0, complex)).view(float)
     arrs = [None if a is None else np.ascontiguousarray(a, float) for a in (s1, s2, f, ar, ab)]
     keep = None if ph4 is None else [np.ascontiguousarray(p, float) for p in ph4]
@@ -149,7 +149,8 @@ def he_traj2(he, model, tspan, psi0, s1, s2, ph4, f, ar, ab, ode, seed=1, gi=0):
     nf = 0 if f is None else len(f)
     rc = he.he_rydberg2_traj(C.byref(model), P(tspan), nt, P(psi), P(arrs[0]), P(arrs[1]), ph, P(arrs[2]), P(arrs[3]), P(arrs[4]), nf,
                              C.byref(ode), C.c_ulonglong(seed), C.c_ulonglong(gi), rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), st)
-    return rc, rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), list(st)
+    he_traj2.n_exact = st[3]   # (lane, step) beam evaluations on the exact path
+    return rc, rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), list(st)[:3]
 
 
 @pytest.fixture(scope="module")
