@@ -157,21 +157,28 @@ class Context:
         return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
 
     def rydberg1_sweep(self, models, psi0s, t_end, n_traj_per_point, traj_offset=0, n_total=0, seed=_abi.DEFAULT_SEED, f=None,
-                       amp_red=None, amp_blue=None, ode=None, out_flags=0):
+                       amp_red=None, amp_blue=None, ode=None, out_flags=0, dev_out=None):
+        """`models`: a list of ca_model, or an already marshalled ctypes array of them (a caller that repeats a sweep marshals once)."""
         n_points = len(models)
-        marr = (_abi.ca_model * n_points)(*models)
+        marr = models if isinstance(models, C.Array) else (_abi.ca_model * n_points)(*models)
         psi = np.ascontiguousarray(np.asarray(psi0s, dtype=np.complex128).reshape(n_points, 5)).view(np.float64)
         t_end = _arr(t_end, (n_points,))
         f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
         nf = 0 if f is None else len(f)
-        rho = np.zeros((n_points, 5, 5), dtype=np.complex128)
-        rho2 = np.zeros((n_points, 5, 5), dtype=np.complex128)
+        if out_flags & _abi.CA_OUT_DEVICE:
+            rho = rho2 = None
+            prho, prho2 = C.cast(C.c_void_p(dev_out[0]), dp), C.cast(C.c_void_p(dev_out[1]), dp)
+        else:
+            rho = np.zeros((n_points, 5, 5), dtype=np.complex128)
+            rho2 = np.zeros((n_points, 5, 5), dtype=np.complex128)
+            prho, prho2 = rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp)
         st = _abi.ca_stats()
         ode = ode if ode is not None else _abi.ode_opts()
         _check(load().ca_rydberg1_sweep(self._h, marr, _p(psi), _p(t_end), C.c_int32(n_points), C.c_int64(n_traj_per_point),
                                         C.c_int64(traj_offset), C.c_int64(n_total), C.c_uint64(seed), _p(f), _p(amp_red), _p(amp_blue),
-                                        C.c_int32(nf), C.byref(ode), C.c_int32(out_flags), rho.ctypes.data_as(dp),
-                                        rho2.ctypes.data_as(dp), C.byref(st)))
+                                        C.c_int32(nf), C.byref(ode), C.c_int32(out_flags), prho, prho2, C.byref(st)))
+        if rho is None:
+            return None, None, st.as_dict()
         return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
 
     # -- two-atom ensemble -------------------------------------------------------------------------------

@@ -171,12 +171,14 @@ __global__ void k_sum_partials(const double* __restrict__ partials, int nb, doub
     }
 }
 
-// FP64 FMA-chain microbenchmark: 8 independent chains per thread.
+// FP64 FMA-chain microbenchmark (roofline denominator): 8 independent chains per thread, 8 warps per SM (two per scheduler keep the
+// half-rate FP64 pipe saturated: DFMA latency 8.4 cycles, issue interval 2 -- profiles/micro/lat.cu; more warps only add
+// scheduling noise), long unrolled bodies so that the loop overhead is < 1 %.
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < 32; ++r) {
             x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
             x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
         }
@@ -531,7 +533,7 @@ int ca_measure_fp64_peak(ca_ctx* c, double* tflops, double* sm_mhz_est) {
     CA_CUDA(cudaSetDevice(c->device));
     int rc = c->misc.ensure(64);
     if (rc) return rc;
-    const int iters = 4096, blocks = c->sm_count * 8, threads = 256;
+    const int iters = 2048, blocks = c->sm_count, threads = 256;   // one 8-warp CTA per SM
     float best = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {
         CA_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -542,7 +544,7 @@ int ca_measure_fp64_peak(ca_ctx* c, double* tflops, double* sm_mhz_est) {
         CA_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
         if (rep > 0 && ms < best) best = ms;
     }
-    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    const double flops = 2.0 * 8.0 * 32.0 * iters * (double)blocks * threads;
     *tflops = flops / (best * 1e-3) / 1e12;
     if (sm_mhz_est) *sm_mhz_est = (*tflops * 1e12) / (2.0 * 64.0 * c->sm_count) / 1e6;  // 64 DFMA/clk/SM
     return CA_OK;

@@ -447,7 +447,10 @@ static void coefficients(lind_sys* S, double t, cplx* c) {
     }
 }
 
+static void lind_rhs_dense(lind_sys* S, double t, const cplx* rho, cplx* out);
+static int g_dense_emulation = 0;
 static void lind_rhs(lind_sys* S, double t, const cplx* rho, cplx* out) {
+    if (g_dense_emulation) { lind_rhs_dense(S, t, rho, out); return; }
     int d = S->d, n = d * d;
     cplx c[MAXH];
     coefficients(S, t, c);
@@ -471,6 +474,51 @@ static void lind_rhs(lind_sys* S, double t, const cplx* rho, cplx* out) {
                 out[o->r[e1] + d * o->r[e2]] += o->v[e1] * conj(o->v[e2]) * rho[o->c[e1] + d * o->c[e2]];
     }
     for (int j = 0; j < d; ++j) for (int i = 0; i < d; ++i) out[i + d * j] -= 0.5 * (S->gam[i] + S->gam[j]) * rho[i + d * j];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * "dense emulation" of the reference's own arithmetic (timing only): the operators the
+ * reference builds with `ket ⊗ dagger(ket)` are DENSE d x d matrices and QuantumOptics' dmaster_h! applies them with dense
+ * `mul!` calls -- per RHS two per term of the TimeDependentSum (6 / 13 terms) and five per jump operator (4 / 8 jumps):
+ * 32 products of 5x5 (one atom) or 66 products of 25x25 complex matrices (two atoms).  Same numbers as lind_rhs up to rounding.
+ * ---------------------------------------------------------------------------------------------- */
+void co_set_dense_emulation(int on) { g_dense_emulation = on; }
+
+static void sp_to_dense(const spop* o, int d, cplx* M) {
+    for (int i = 0; i < d * d; ++i) M[i] = 0.0;
+    for (int e = 0; e < o->n; ++e) M[o->r[e] + d * o->c[e]] += o->v[e];
+}
+/* C = alpha A B + beta C, all d x d column-major (the generic mul! the dense Operators dispatch to) */
+static void dense_mul(int d, cplx alpha, const cplx* A, const cplx* B, cplx beta, cplx* C) {
+    for (int j = 0; j < d; ++j)
+        for (int i = 0; i < d; ++i) {
+            cplx acc = 0.0;
+            for (int k = 0; k < d; ++k) acc += A[i + d * k] * B[k + d * j];
+            C[i + d * j] = alpha * acc + (beta == 0.0 ? 0.0 : beta * C[i + d * j]);
+        }
+}
+static void lind_rhs_dense(lind_sys* S, double t, const cplx* rho, cplx* out) {
+    const int d = S->d, n = d * d;
+    cplx c[MAXH];
+    coefficients(S, t, c);
+    S->n_rhs++;
+    cplx *Hd = (cplx*)malloc(sizeof(cplx) * n * 3), *Jd = Hd + n, *tmp = Hd + 2 * n;
+    for (int i = 0; i < n; ++i) out[i] = 0.0;
+    for (int k = 0; k < S->nH; ++k) {   /* LazySum: every term applied on its own, from the left and from the right */
+        sp_to_dense(&S->Hop[k], d, Hd);
+        dense_mul(d, -1.0 * I * c[k], Hd, rho, 1.0, out);
+        dense_mul(d, 1.0 * I * c[k], rho, Hd, 1.0, out);
+    }
+    for (int j = 0; j < S->nJ; ++j) {   /* dmaster_h!: J ρ J† - ½ J†J ρ - ½ ρ J†J as five products */
+        sp_to_dense(&S->J[j], d, Jd);
+        for (int a = 0; a < d; ++a) for (int b = 0; b < d; ++b) Hd[a + d * b] = conj(Jd[b + d * a]);   /* J† */
+        dense_mul(d, 1.0, Jd, rho, 0.0, tmp);
+        dense_mul(d, 1.0, tmp, Hd, 1.0, out);
+        dense_mul(d, -0.5, Hd, tmp, 1.0, out);
+        dense_mul(d, 1.0, rho, Hd, 0.0, tmp);
+        dense_mul(d, -0.5, tmp, Jd, 1.0, out);
+    }
+    free(Hd);
 }
 
 static void build_operators(lind_sys* S, const ca_model* m, int natoms) {

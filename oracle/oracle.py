@@ -67,6 +67,11 @@ def _psi(psi0):
     return v.view(np.float64)
 
 
+def set_dense_emulation(on):
+    """Switch the RHS to the reference's own dense `mul!` arithmetic (32 products of 5x5 / 66 of 25x25 per RHS): timing baseline only."""
+    lib().co_set_dense_emulation(C.c_int(1 if on else 0))
+
+
 def num_threads():
     return int(lib().co_num_threads())
 
