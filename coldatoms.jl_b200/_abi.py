@@ -17,6 +17,8 @@ CA_COMPAT_DEFAULT = CA_COMPAT_VZ_FROM_VY
 CA_RHO2_MATSQ, CA_RHO2_ABS2 = 0, 1
 CA_OUT_MEAN, CA_OUT_SUMS, CA_OUT_DEVICE = 0, 1, 2
 CA_AVG_TWOPHOTON, CA_AVG_RM6 = 0, 1
+CA_2A_PER_ATOM_LASERS, CA_2A_CONST_VRR, CA_2A_SHIFT_AFTER_MOTION, CA_2A_DIRECT = 1, 2, 4, 8
+CA_ERR_NCCL = -8
 
 # Philox stream ids (shared by the device sampler and the oracle)
 STREAM_ATOM1, STREAM_ATOM2, STREAM_RED1, STREAM_BLUE1, STREAM_RED2, STREAM_BLUE2 = range(6)
@@ -46,6 +48,9 @@ class ca_model(C.Structure):
         ("compat", C.c_int32), ("rho2_mode", C.c_int32), ("n_noise_nodes", C.c_int32), ("_pad", C.c_int32),
         ("center1", C.c_double * 3), ("center2", C.c_double * 3),
         ("c6", C.c_double), ("xi", C.c_double),
+        ("two_atom_flags", C.c_int32), ("_pad2", C.c_int32),
+        ("red2", ca_beam), ("blue2", ca_beam),
+        ("Delta0_2", C.c_double), ("delta0_2", C.c_double), ("V_rr", C.c_double), ("seg2_phase", C.c_double),
     ]
 
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "ca_collect_stats", "ca_stats_to_device",
     "ca_init_multi", "ca_finalize_multi", "ca_multi_size", "ca_multi_context", "ca_rydberg1_run_multi", "ca_rydberg2_run_multi",
     "ca_rydberg1_sweep_multi", "ca_release_recapture_multi",
-    "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg1_sweep", "ca_release_recapture",
+    "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg2_run_ex", "ca_rydberg1_sweep", "ca_release_recapture",
     "ca_sample_atoms", "ca_sample_atoms_metropolis", "ca_phase_noise", "ca_eval_beam", "ca_thermal_average",
 ]
 
@@ -209,6 +209,32 @@ class Context:
                                       C.byref(st)))
         if rho is None:
             return None, None, st.as_dict()
+        return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
+
+    def rydberg2_run_ex(self, model, tspan, psi0=None, rho0=None, n_traj=1, nt_seg1=0, traj_offset=0, n_total=0, seed=_abi.DEFAULT_SEED,
+                        samples1=None, samples2=None, phases4=None, f=None, amp_red=None, amp_blue=None, ode=None, out_flags=0):
+        """ca_rydberg2_run_ex: general initial state (`rho0[25, 25]` as numpy [row, col], or `psi0`), optional two time segments
+        (`tspan[:nt_seg1]`, `tspan[nt_seg1:]`), legacy two-atom flags in the model."""
+        tspan = _arr(tspan)
+        nt = len(tspan)
+        samples1 = _arr(samples1, (-1, 6)) if samples1 is not None else None
+        samples2 = _arr(samples2, (-1, 6)) if samples2 is not None else None
+        f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
+        nf = 0 if f is None else len(f)
+        ph_arr, keep = None, []
+        if phases4 is not None:
+            keep = [_arr(p, (-1, nf)) for p in phases4]
+            ph_arr = (dp * 4)(*[_p(p) for p in keep])
+        r0 = None if rho0 is None else np.ascontiguousarray(np.asarray(rho0, dtype=np.complex128).reshape(25, 25).T).view(np.float64)
+        p0 = None if psi0 is None else _psi(psi0, 25)
+        st = _abi.ca_stats()
+        ode = ode if ode is not None else _abi.ode_opts()
+        rho = np.zeros((nt, 25, 25), dtype=np.complex128)
+        rho2 = np.zeros((nt, 25, 25), dtype=np.complex128)
+        _check(load().ca_rydberg2_run_ex(self._h, C.byref(model), _p(tspan), C.c_int32(nt), C.c_int32(nt_seg1), _p(p0), _p(r0),
+                                         C.c_int64(n_traj), C.c_int64(traj_offset), C.c_int64(n_total), C.c_uint64(seed), _p(samples1),
+                                         _p(samples2), ph_arr, _p(f), _p(amp_red), _p(amp_blue), C.c_int32(nf), C.byref(ode),
+                                         C.c_int32(out_flags), rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), C.byref(st)))
         return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
 
     # -- release and recapture ---------------------------------------------------------------------------

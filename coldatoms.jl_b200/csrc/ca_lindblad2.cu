@@ -12,42 +12,16 @@
 
 #include "ca_host.h"
 #include "ca_lindblad2.cuh"
+#include "ca_r2params.cuh"
 
 namespace ca {
 
-cudaStream_t ctx_stream(ca_ctx* c);
-int ctx_sm_count(ca_ctx* c);
-int ctx_device(ca_ctx* c);
-void* ctx_buf(ca_ctx* c, int which, size_t bytes);  // grow-only device buffers owned by the context
-cudaEvent_t ctx_event(ca_ctx* c, int i);
-void ctx_set_last(ca_ctx* c, unsigned long long* counters, long long n, int launches, int kind);
-int collect_last(ca_ctx* c, ca_stats* stats);
 
 #ifndef CA_WARPS2
 #define CA_WARPS2 8
 #endif
 constexpr int kWarps2 = CA_WARPS2;   // warps (trajectories) per CTA, one CTA per SM
 
-struct R2Params {
-    DevModel model;
-    const double* rho0m;     // [32][kS2] initial state in the per-lane real layout
-    double tr0;              // trace of ρ0
-    const double* tspan;
-    const double* samples1;  // NULL or [n][6] (before the centre shift)
-    const double* samples2;
-    const double* phases[4]; // NULL or [n][nf]: red1, blue1, red2, blue2
-    const double* f;
-    const double* amp_red;
-    const double* amp_blue;
-    double* scratch;         // per warp: [4][n_nodes] phase-noise tables
-    double* accum;           // per warp: [nt][2 (ρ, ρ²)][kAccSlots][32]
-    unsigned long long* counters;
-    const unsigned* order;   // NULL or [n_traj]: trajectory indices, most expensive first (k_order2_*)
-    OdeOpts ode;
-    long long n_traj, traj_offset;
-    unsigned long long seed;
-    int nt, nf;
-};
 
 struct DevWarp {
     int lane;
@@ -118,38 +92,7 @@ __global__ void __launch_bounds__(kWarps2 * 32, 1) k_lindblad2(const __grid_cons
             for (int q = 0; q < 3; ++q) s6[q] += m.center[lane][q];
             for (int q = 0; q < 6; ++q) W.smp[6 * lane + q] = m.atom_motion ? s6[q] : 0.0;
         }
-        // ---- phase-noise tables: lane = chunk of 32 nodes, all four traces (cz_model.jl:41-46)
-        if (tab_w) {
-            for (int q = 0; q < 4; ++q) {
-                const double* ph = P.phases[q] ? P.phases[q] + tr * P.nf : nullptr;
-                for (int c0 = lane * 32; c0 < m.n_nodes; c0 += 32 * 32) {
-                    double acc[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-                    const double t0 = c0 * m.dtn;
-                    const double* amp = (q & 1) ? P.amp_blue : P.amp_red;
-                    double ph_next = 0.0;
-                    for (int k = 0; k < P.nf; ++k) {
-                        double phk;
-                        if (ph) phk = ph[k];
-                        else if (k & 1) phk = ph_next;
-                        else { U4 r4 = philox(P.seed, gi, (uint32_t)(k >> 1), (uint32_t)(2 + q)); phk = kTwoPi * u53(r4.x, r4.y); ph_next = kTwoPi * u53(r4.z, r4.w); }
-                        const double om = kTwoPi * P.f[k];
-                        double s0, c0v, sh, ch;
-                        sincos(om * t0 + phk, &s0, &c0v);
-                        sincos(0.5 * om * m.dtn, &sh, &ch);
-                        const double a = amp[k], sig = -4.0 * sh * sh;
-                        double c = a * c0v, dlt = -2.0 * a * (s0 * ch + c0v * sh) * sh;
-                        acc[0] += c;
-#pragma unroll
-                        for (int j = 1; j < 32; ++j) { c += dlt; dlt += sig * c; acc[j] += c; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < m.n_nodes) tab_w[(size_t)q * m.n_nodes + c0 + j] = acc[j];
-                }
-            }
-        }
+        if (tab_w) gen_noise_tables2(P, m, tr, gi, lane, tab_w);
         __syncwarp();
         __threadfence_block();
         CA_TICK(W, 0);
@@ -265,13 +208,12 @@ static constexpr size_t kSmem2 = sizeof(double) * (size_t)kWarps2 * kWarpDoubles
         if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return CA_ERR_CUDA; } \
     } while (0)
 
-extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* tspan, int32_t nt, const double* psi0, int64_t n_traj,
-                               int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2,
-                               const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int32_t nf,
-                               const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats) {
-    if (!c || !model || !tspan || nt < 1 || !psi0 || n_traj < 0 || !rho || !rho2) { set_error("bad argument"); return CA_ERR_ARG; }
-    for (int j = 1; j < nt; ++j)
-        if (!(tspan[j] > tspan[j - 1])) { set_error("tspan must be strictly increasing"); return CA_ERR_ARG; }
+
+// The blocked kernel (k_lindblad2): simulation_czlp with psi0 inside the {0,1,r,p}^2 block.
+static int run_r2_blocked(ca_ctx* c, const ca_model* model, const double* tspan, int32_t nt, const double* psi0, int64_t n_traj,
+                          int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2,
+                          const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int32_t nf,
+                          const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats) {
     CA_CUDA2(cudaSetDevice(ctx_device(c)));
     cudaStream_t s = ctx_stream(c);
     R2Params P;
@@ -287,7 +229,7 @@ extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* t
     fill_ode(ode, tspan[0], tspan[nt - 1], &P.ode);
     if (!P.ode.adaptive && !(P.ode.dt0 > 0)) { set_error("adaptive=false needs dt > 0"); return CA_ERR_ARG; }
     double h_rho0[32 * kS2];
-    if (!rho0_lanes(psi0, h_rho0, &P.tr0)) { set_error("two-atom kernel: ψ0 with |l> components is not supported on the GPU path"); return CA_ERR_UNSUPPORTED; }
+    if (!rho0_lanes(psi0, h_rho0, &P.tr0)) { set_error("internal: blocked two-atom kernel called with |l> components"); return CA_ERR_ARG; }
     cudaEvent_t e0 = ctx_event(c, 0), e1 = ctx_event(c, 1), e2 = ctx_event(c, 2), e3 = ctx_event(c, 3);
     CA_CUDA2(cudaEventRecord(e0, s));
     // device buffers (ids 20..): struct, tspan, samples x2, phases x4, f/amps, scratch, accum, counters, out
@@ -375,4 +317,33 @@ extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* t
     CA_CUDA2(cudaMemcpyAsync(rho, d_rho, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, s));
     CA_CUDA2(cudaMemcpyAsync(rho2, d_rho2, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, s));
     return collect_last(c, stats);   // synchronises; reports a trajectory that hit maxiters / went non-finite
+}
+
+extern "C" int ca_rydberg2_run_ex(ca_ctx* c, const ca_model* model, const double* tspan, int32_t nt, int32_t nt_seg1, const double* psi0,
+                                  const double* rho0, int64_t n_traj, int64_t traj_offset, int64_t n_total, uint64_t seed,
+                                  const double* samples1, const double* samples2, const double* const* phases4, const double* f,
+                                  const double* amp_red, const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags,
+                                  double* rho, double* rho2, ca_stats* stats) {
+    if (!c || !model || !tspan || nt < 1 || (!psi0 && !rho0) || n_traj < 0 || !rho || !rho2 || nt_seg1 < 0 || nt_seg1 >= nt + (nt_seg1 == 0)) {
+        set_error("bad argument"); return CA_ERR_ARG;
+    }
+    for (int j = 1; j < nt; ++j)
+        if (j != nt_seg1 && !(tspan[j] > tspan[j - 1])) { set_error("tspan must be strictly increasing (within each time segment)"); return CA_ERR_ARG; }
+    bool blocked = !rho0 && nt_seg1 == 0 && model->two_atom_flags == 0;
+    if (blocked)
+        for (int i = 0; i < 25; ++i)
+            if ((i % 5 == 4 || i / 5 == 4) && (psi0[2 * i] != 0.0 || psi0[2 * i + 1] != 0.0)) blocked = false;   // |l> components: SURVEY App. A6 fall-back
+    if (blocked)
+        return run_r2_blocked(c, model, tspan, nt, psi0, n_traj, traj_offset, n_total, seed, samples1, samples2, phases4, f, amp_red, amp_blue, nf,
+                              ode, out_flags, rho, rho2, stats);
+    return run_r2_full(c, model, tspan, nt, nt_seg1, psi0, rho0, n_traj, traj_offset, n_total, seed, samples1, samples2, phases4, f, amp_red,
+                       amp_blue, nf, ode, out_flags, rho, rho2, stats);
+}
+
+extern "C" int ca_rydberg2_run(ca_ctx* c, const ca_model* model, const double* tspan, int32_t nt, const double* psi0, int64_t n_traj,
+                               int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2,
+                               const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int32_t nf,
+                               const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats) {
+    return ca_rydberg2_run_ex(c, model, tspan, nt, 0, psi0, nullptr, n_traj, traj_offset, n_total, seed, samples1, samples2, phases4, f, amp_red,
+                              amp_blue, nf, ode, out_flags, rho, rho2, stats);
 }

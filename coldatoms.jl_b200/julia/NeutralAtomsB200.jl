@@ -48,6 +48,9 @@ struct CaModel
     compat::Int32; rho2_mode::Int32; n_noise_nodes::Int32; _pad::Int32
     center1::NTuple{3,Float64}; center2::NTuple{3,Float64}
     c6::Float64; xi::Float64
+    two_atom_flags::Int32; _pad2::Int32
+    red2::CaBeam; blue2::CaBeam
+    Delta0_2::Float64; delta0_2::Float64; V_rr::Float64; seg2_phase::Float64
 end
 struct CaOde
     reltol::Float64; abstol::Float64; dt::Float64; dtmax::Float64

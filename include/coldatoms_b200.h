@@ -8,6 +8,8 @@
  *   ca_rydberg1_run      <- simulation                src/rydberg_model.jl:194-265  (lines 206-264)
  *                           simulation_blue_intens    src/rydberg_model_arb_bms.jl:15-86
  *   ca_rydberg2_run      <- simulation_czlp           src/cz_model.jl:107-171       (lines 111-170)
+ *   ca_rydberg2_run_ex   <- two_atom_simulation       src/two_atom_model.jl:89-190  (legacy parameterisation, model->two_atom_flags)
+ *                           direct_CZ_simulation      src/two_atom_model.jl:192-319 (two segments, rho0 input, direct coupling)
  *   ca_release_recapture <- release_recapture         src/basic_experiments.jl:72-81
  *   ca_sample_atoms      <- samples_generate (harmonic=true branch) src/atom_sampler.jl:84-96
  *   ca_sample_atoms_metropolis <- samples_generate (harmonic=false branch) src/atom_sampler.jl:97-120
@@ -112,7 +114,26 @@ typedef struct ca_model {
     double center1[3], center2[3];
     double c6;
     double xi; /* red phase jump at t >= tspan[end]/2 (cz_model.jl:130,137) */
+    /* legacy two-atom parameterisations (src/two_atom_model.jl:89-190 two_atom_simulation, :192-319 direct_CZ_simulation); all
+     * zero = the cz_model.jl behaviour above */
+    int32_t two_atom_flags; /* CA_2A_* bits */
+    int32_t _pad2;
+    ca_beam red2, blue2;    /* atom 2's beams for Ω (CA_2A_PER_ATOM_LASERS); the Doppler shifts of BOTH atoms use red/blue, as the
+                               reference passes red/blue_laser_params_first to Δ and δ of atom 2 (two_atom_model.jl:158-159) */
+    double Delta0_2, delta0_2; /* detuning_params_second (CA_2A_PER_ATOM_LASERS) */
+    double V_rr;            /* constant blockade shift replacing c6/R^6 (CA_2A_CONST_VRR; two_atom_model.jl:165,283) */
+    double seg2_phase;      /* direct CZ: the couplings of the SECOND time segment carry exp(i*seg2_phase) (two_atom_model.jl:287-299) */
 } ca_model;
+
+/* two_atom_flags */
+#define CA_2A_PER_ATOM_LASERS 1   /* atom 2 uses red2/blue2 and Delta0_2/delta0_2 */
+#define CA_2A_CONST_VRR 2         /* V = V_rr instead of c6/(1e-18 + R^6) */
+#define CA_2A_SHIFT_AFTER_MOTION 4 /* the centres are beam-frame offsets added AFTER the motion R(t) (legacy X1(t)-X0, dist+X2(t)-X0,
+                                      two_atom_model.jl:160-166), not shifts of the initial positions (cz_model.jl:124-125) */
+#define CA_2A_DIRECT 8            /* direct one-photon coupling |1><r| with the BLUE beam's Ω(x,y,z)/2 and H_rr = +Delta0 (no Doppler shift,
+                                      no intermediate level: direct_CZ_simulation, two_atom_model.jl:262-299); the red beam is unused.
+                                      The reference's first-segment Hamiltonian couples σgr and σrg with the SAME coefficient (not
+                                      conjugated, :270-274): non-Hermitian for a complex Ω; the Hermitian form is implemented. */
 
 /* ode_kwargs subset (forwarded verbatim to OrdinaryDiffEq by the reference, rydberg_model.jl:255) */
 typedef struct ca_ode_opts {
@@ -198,6 +219,24 @@ int ca_rydberg2_run(ca_ctx* ctx, const ca_model* model, const double* tspan, int
                     const double* const* phases4, const double* f, const double* amp_red,
                     const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags,
                     double* rho, double* rho2, ca_stats* stats);
+
+/*
+ * General two-atom entry: everything ca_rydberg2_run does, plus
+ *   rho0     NULL, or 625 complex128 (column-major 25x25) initial density matrix replacing |psi0><psi0| (direct_CZ_simulation starts
+ *            from a density matrix, two_atom_model.jl:192,226); psi0 may then be NULL;
+ *   nt_seg1  0, or the number of leading tspan points that form a FIRST time segment: tspan[0..nt_seg1) and tspan[nt_seg1..nt) are
+ *            then two consecutive solves (each a fresh DP5 solve on its own time axis, the second starting from the per-trajectory
+ *            final state of the first: two_atom_model.jl:304-305); outputs are concatenated (nt matrices).
+ * Initial states with |l> components, rho0, two segments and any two_atom_flags run on the full 25x25 kernel (k_lindblad2_full);
+ * the cz_model.jl case with psi0 inside the {0,1,r,p}^2 block runs on the blocked kernel (k_lindblad2).  ca_rydberg2_run is
+ * ca_rydberg2_run_ex with rho0 = NULL, nt_seg1 = 0.
+ */
+int ca_rydberg2_run_ex(ca_ctx* ctx, const ca_model* model, const double* tspan, int32_t nt, int32_t nt_seg1,
+                       const double* psi0, const double* rho0, int64_t n_traj, int64_t traj_offset, int64_t n_total,
+                       uint64_t seed, const double* samples1, const double* samples2,
+                       const double* const* phases4, const double* f, const double* amp_red,
+                       const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags,
+                       double* rho, double* rho2, ca_stats* stats);
 
 /*
  * Batched one-atom sweep: n_points parameter points in one launch (fidelity.jl:78-88 loops; BASELINE

@@ -388,7 +388,7 @@ enum { L0 = 0, L1 = 1, LR = 2, LP = 3, LL = 4 };
 /* ------------------------------------------------------------------------------------------------
  * Lindblad right-hand side in QuantumOptics' dmaster_h! form.
  * ---------------------------------------------------------------------------------------------- */
-#define MAXH 13
+#define MAXH 17
 #define MAXJ 8
 typedef struct {
     int d;
@@ -404,18 +404,29 @@ typedef struct {
     int n_nodes; double dtn;
     double tau;                        /* CZ phase-jump time */
     int64_t n_rhs;
+    double shift[2][3];                /* CA_2A_SHIFT_AFTER_MOTION: beam-frame offsets added after R(t) (two_atom_model.jl:160-166) */
+    int segment;                       /* 0 / 1: time segment of direct_CZ_simulation (two_atom_model.jl:304-305) */
 } lind_sys;
 
 static void coefficients(lind_sys* S, double t, cplx* c) {
     const ca_model* m = S->m;
     int fr = m->free_motion;
+    const int fl = S->natoms == 2 ? m->two_atom_flags : 0;
+    for (int k = 0; k < MAXH; ++k) c[k] = 0.0;
     for (int a = 0; a < S->natoms; ++a) {
         const double* s = S->s[a];
+        /* legacy two_atom_simulation: atom 2 has its own beams and detunings (two_atom_model.jl:168-173) */
+        const ca_beam* red = (a == 1 && (fl & CA_2A_PER_ATOM_LASERS)) ? &m->red2 : &m->red;
+        const ca_beam* blue = (a == 1 && (fl & CA_2A_PER_ATOM_LASERS)) ? &m->blue2 : &m->blue;
+        const double Delta0 = (a == 1 && (fl & CA_2A_PER_ATOM_LASERS)) ? m->Delta0_2 : m->Delta0;
+        const double delta0 = (a == 1 && (fl & CA_2A_PER_ATOM_LASERS)) ? m->delta0_2 : m->delta0;
         /* get_atom_trajectories: src/rydberg_model.jl:28-43 (note Vz built from vy: line 41) */
         double X = traj_R(t, s[0], s[3], S->wr, fr), Y = traj_R(t, s[1], s[4], S->wr, fr), Z = traj_R(t, s[2], s[5], S->wz, fr);
+        if (fl & CA_2A_SHIFT_AFTER_MOTION) { X += S->shift[a][0]; Y += S->shift[a][1]; Z += S->shift[a][2]; }
         double Vx = traj_V(t, s[0], s[3], S->wr, fr);
         double vz_src = (m->compat & CA_COMPAT_VZ_FROM_VY) ? s[4] : s[5];
         double Vz = traj_V(t, s[2], vz_src, S->wz, fr);
+        /* the Doppler shifts of BOTH atoms are built from the first atom's laser parameters (two_atom_model.jl:158-159, :168-169) */
         double kr = 2.0 * m->red.z0 / (m->red.w0 * m->red.w0);
         double kb = 2.0 * m->blue.z0 / (m->blue.w0 * m->blue.w0);
         double Dd, dd;
@@ -430,20 +441,32 @@ static void coefficients(lind_sys* S, double t, cplx* c) {
         double ph_r = interp_lin(S->phi_tab[2 * a], S->n_nodes, S->dtn, t);
         double ph_b = interp_lin(S->phi_tab[2 * a + 1], S->n_nodes, S->dtn, t);
         if (S->natoms == 2) ph_r += (t < S->tau) ? 0.0 : m->xi; /* cz_model.jl:136-137 */
-        cplx Or = cexp(1.0 * I * ph_r) * Omega_field(X, Y, Z, &m->red);   /* rydberg_model.jl:175 */
-        cplx Ob = cexp(1.0 * I * ph_b) * Omega_field(X, Y, Z, &m->blue);  /* :176 */
         cplx* ca = c + 6 * a;
-        if (m->detuning_sign == CA_SIGN_RYDBERG1) { ca[0] = -Dd - m->Delta0; ca[1] = -dd - m->delta0; }   /* :180-181 */
-        else { ca[0] = Dd - m->Delta0; ca[1] = dd - m->delta0; }                                        /* cz_model.jl:55-56 */
+        if (fl & CA_2A_DIRECT) {   /* direct_CZ_simulation: Δ0 on nr, Ω(blue beam)/2 on σ1r / σr1, phase factor in segment 2 (:262-299) */
+            cplx Od = cexp(1.0 * I * (ph_b + (S->segment ? m->seg2_phase : 0.0))) * Omega_field(X, Y, Z, blue);
+            ca[1] = Delta0;
+            c[13 + 2 * a] = Od / 2.0; c[14 + 2 * a] = conj(Od) / 2.0;
+            continue;
+        }
+        cplx Or = cexp(1.0 * I * ph_r) * Omega_field(X, Y, Z, red);   /* rydberg_model.jl:175 */
+        cplx Ob = cexp(1.0 * I * ph_b) * Omega_field(X, Y, Z, blue);  /* :176 */
+        if (m->detuning_sign == CA_SIGN_RYDBERG1) { ca[0] = -Dd - Delta0; ca[1] = -dd - delta0; }   /* :180-181 */
+        else { ca[0] = Dd - Delta0; ca[1] = dd - delta0; }                                        /* cz_model.jl:55-56 */
         ca[2] = Or / 2.0; ca[3] = conj(Or) / 2.0; ca[4] = Ob / 2.0; ca[5] = conj(Ob) / 2.0;             /* :182-185 */
     }
     if (S->natoms == 2) { /* get_V: cz_model.jl:12-17 */
-        int fr2 = fr;
-        double dx = traj_R(t, S->s[0][0], S->s[0][3], S->wr, fr2) - traj_R(t, S->s[1][0], S->s[1][3], S->wr, fr2);
-        double dy = traj_R(t, S->s[0][1], S->s[0][4], S->wr, fr2) - traj_R(t, S->s[1][1], S->s[1][4], S->wr, fr2);
-        double dz = traj_R(t, S->s[0][2], S->s[0][5], S->wz, fr2) - traj_R(t, S->s[1][2], S->s[1][5], S->wz, fr2);
-        double r2 = dx * dx + dy * dy + dz * dz;
-        c[12] = m->c6 / (1e-18 + r2 * r2 * r2);
+        if (fl & CA_2A_CONST_VRR) c[12] = m->V_rr;   /* t -> V_rr: two_atom_model.jl:165 */
+        else {
+            double p[2][3];
+            for (int a = 0; a < 2; ++a) {
+                p[a][0] = traj_R(t, S->s[a][0], S->s[a][3], S->wr, fr); p[a][1] = traj_R(t, S->s[a][1], S->s[a][4], S->wr, fr);
+                p[a][2] = traj_R(t, S->s[a][2], S->s[a][5], S->wz, fr);
+                if (fl & CA_2A_SHIFT_AFTER_MOTION) for (int k = 0; k < 3; ++k) p[a][k] += S->shift[a][k];
+            }
+            double dx = p[0][0] - p[1][0], dy = p[0][1] - p[1][1], dz = p[0][2] - p[1][2];
+            double r2 = dx * dx + dy * dy + dz * dz;
+            c[12] = m->c6 / (1e-18 + r2 * r2 * r2);
+        }
     }
 }
 
@@ -538,9 +561,13 @@ static void build_operators(lind_sys* S, const ca_model* m, int natoms) {
         for (int k = 0; k < 6; ++k) S->Hop[k] = ops[k];
         for (int k = 0; k < 4; ++k) S->J[k] = js[k];
     } else { /* cz_model.jl:31 and :2-9 */
-        S->d = 25; S->nH = 13; S->nJ = 8;
+        S->d = 25; S->nH = 17; S->nJ = 8;
         for (int k = 0; k < 6; ++k) { sp_kron_left(&S->Hop[k], &ops[k]); sp_kron_right(&S->Hop[6 + k], &ops[k]); }
         sp_clear(&S->Hop[12]); sp_add(&S->Hop[12], LR + 5 * LR, LR + 5 * LR, 1.0);
+        /* direct_operators σgr, σrg per atom (two_atom_model.jl:38-44; g -> level 1); their coefficients are zero unless CA_2A_DIRECT */
+        spop d1r, dr1;
+        sp_sigma(&d1r, L1, LR); sp_sigma(&dr1, LR, L1);
+        sp_kron_left(&S->Hop[13], &d1r); sp_kron_left(&S->Hop[14], &dr1); sp_kron_right(&S->Hop[15], &d1r); sp_kron_right(&S->Hop[16], &dr1);
         for (int k = 0; k < 4; ++k) { sp_kron_left(&S->J[k], &js[k]); sp_kron_right(&S->J[4 + k], &js[k]); }
     }
     for (int i = 0; i < S->d; ++i) S->gam[i] = 0.0;
@@ -685,7 +712,7 @@ static void accumulate(int d, int nt, const cplx* traj, int rho2_mode, double* a
     }
 }
 
-static int run_ensemble(int natoms, const ca_model* model, const double* tspan, int nt, const double* psi0, int64_t n_traj,
+static int run_ensemble(int natoms, const ca_model* model, const double* tspan, int nt, int nt_seg1, const double* psi0, const double* rho0_in, int64_t n_traj,
                         int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2,
                         const double* const* phases, const double* f, const double* amp_red, const double* amp_blue, int nf,
                         const ca_ode_opts* ode, int out_flags, double* rho, double* rho2, ca_stats* stats, int nthreads) {
@@ -695,6 +722,7 @@ static int run_ensemble(int natoms, const ca_model* model, const double* tspan, 
     if (ode) oo = *ode; else { memset(&oo, 0, sizeof oo); oo.adaptive = 1; oo.dense = 1; }
     int n_nodes = model->n_noise_nodes > 0 ? model->n_noise_nodes : 1001;
     double tend = tspan[nt - 1];
+    if (nt_seg1 > 0 && tspan[nt_seg1 - 1] > tend) tend = tspan[nt_seg1 - 1];   /* two segments: tables span the longer time axis */
     double dtn = tend / (n_nodes - 1); /* tspan_noise = 0:tend/1000:tend (rydberg_model.jl:216) */
     double* tn = (double*)malloc(sizeof(double) * n_nodes);
     for (int j = 0; j < n_nodes; ++j) tn[j] = j * dtn;
@@ -702,8 +730,10 @@ static int run_ensemble(int natoms, const ca_model* model, const double* tspan, 
     int use_noise = model->laser_noise && f && nf > 0;
     int ntr = 2 * natoms;
     cplx rho0[625];
-    for (int b = 0; b < d; ++b) for (int a = 0; a < d; ++a)
+    if (rho0_in) { for (int i = 0; i < n; ++i) rho0[i] = rho0_in[2 * i] + I * rho0_in[2 * i + 1]; }   /* ρ0 = copy(ρ_1): two_atom_model.jl:226 */
+    else for (int b = 0; b < d; ++b) for (int a = 0; a < d; ++a)
         rho0[a + d * b] = (psi0[2 * a] + I * psi0[2 * a + 1]) * conj(psi0[2 * b] + I * psi0[2 * b + 1]);
+    const int shift_after = natoms == 2 && (model->two_atom_flags & CA_2A_SHIFT_AFTER_MOTION);
 #ifdef _OPENMP
     int T = nthreads > 0 ? nthreads : omp_get_max_threads();
 #else
@@ -741,7 +771,11 @@ static int run_ensemble(int natoms, const ca_model* model, const double* tspan, 
                     int64_t att = co_sample_one(trap, atom, seed, gi, (uint32_t)a, 1e-2, smp);
                     tot_att += att;
                 }
-                if (natoms == 2) { const double* c = a == 0 ? model->center1 : model->center2; smp[0] += c[0]; smp[1] += c[1]; smp[2] += c[2]; }
+                if (natoms == 2) {
+                    const double* c = a == 0 ? model->center1 : model->center2;
+                    if (shift_after) { S.shift[a][0] = c[0]; S.shift[a][1] = c[1]; S.shift[a][2] = c[2]; }
+                    else { smp[0] += c[0]; smp[1] += c[1]; smp[2] += c[2]; }
+                }
                 for (int k = 0; k < 6; ++k) S.s[a][k] = model->atom_motion ? smp[k] : 0.0; /* rydberg_model.jl:35 */
             }
             for (int tr = 0; tr < 4; ++tr) S.phi_tab[tr] = NULL;
@@ -754,7 +788,17 @@ static int run_ensemble(int natoms, const ca_model* model, const double* tspan, 
                 }
             S.n_rhs = 0;
             int64_t na = 0, nr = 0;
-            int rc = dp5_solve(&S, rho0, tspan, nt, &oo, traj, &na, &nr);
+            int rc;
+            S.segment = 0;
+            if (nt_seg1 > 0 && nt_seg1 < nt) {   /* two consecutive solves, the second from the final state of the first (two_atom_model.jl:304-305) */
+                rc = dp5_solve(&S, rho0, tspan, nt_seg1, &oo, traj, &na, &nr);
+                if (rc == 0) {
+                    S.segment = 1;
+                    cplx mid[625];
+                    memcpy(mid, traj + (size_t)(nt_seg1 - 1) * n, sizeof(cplx) * n);
+                    rc = dp5_solve(&S, mid, tspan + nt_seg1, nt - nt_seg1, &oo, traj + (size_t)nt_seg1 * n, &na, &nr);
+                }
+            } else rc = dp5_solve(&S, rho0, tspan, nt, &oo, traj, &na, &nr);
             if (rc != 0) {
 #pragma omp critical
                 status = rc;
@@ -785,7 +829,7 @@ int co_rydberg1_run(const ca_model* model, const double* tspan, int32_t nt, cons
                     const double* phases_blue, const double* f, const double* amp_red, const double* amp_blue, int32_t nf,
                     const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats, int32_t nthreads) {
     const double* ph[4] = {phases_red, phases_blue, NULL, NULL};
-    return run_ensemble(1, model, tspan, nt, psi0, n_traj, traj_offset, n_total, seed, samples, NULL, ph, f, amp_red, amp_blue, nf,
+    return run_ensemble(1, model, tspan, nt, 0, psi0, NULL, n_traj, traj_offset, n_total, seed, samples, NULL, ph, f, amp_red, amp_blue, nf,
                         ode, out_flags, rho, rho2, stats, nthreads);
 }
 
@@ -797,11 +841,23 @@ int co_rydberg2_run(const ca_model* model, const double* tspan, int32_t nt, cons
     const double* ph[4] = {NULL, NULL, NULL, NULL};
     if (phases4) for (int k = 0; k < 4; ++k) ph[k] = phases4[k];
     /* CZ draws noise even when laser_noise=false but with zero amplitudes (cz_model.jl:134-135): same as no noise */
-    return run_ensemble(2, model, tspan, nt, psi0, n_traj, traj_offset, n_total, seed, samples1, samples2, ph, f, amp_red, amp_blue,
+    return run_ensemble(2, model, tspan, nt, 0, psi0, NULL, n_traj, traj_offset, n_total, seed, samples1, samples2, ph, f, amp_red, amp_blue,
                         nf, ode, out_flags, rho, rho2, stats, nthreads);
 }
 
 /* release_evolve + release_recapture: src/basic_experiments.jl:25-47, :72-81 */
+/* two_atom_simulation / direct_CZ_simulation (src/two_atom_model.jl:89-190, :192-319) and simulation_czlp with a general initial state:
+ * rho0 (625 complex, column-major) replaces |psi0><psi0| when given; tspan[0..nt_seg1) and tspan[nt_seg1..nt) are two consecutive solves */
+int co_rydberg2_run_ex(const ca_model* model, const double* tspan, int32_t nt, int32_t nt_seg1, const double* psi0, const double* rho0,
+                       int64_t n_traj, int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2,
+                       const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int32_t nf,
+                       const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats, int32_t nthreads) {
+    const double* ph[4] = {NULL, NULL, NULL, NULL};
+    if (phases4) for (int k = 0; k < 4; ++k) ph[k] = phases4[k];
+    return run_ensemble(2, model, tspan, nt, nt_seg1, psi0, rho0, n_traj, traj_offset, n_total, seed, samples1, samples2, ph, f, amp_red, amp_blue,
+                        nf, ode, out_flags, rho, rho2, stats, nthreads);
+}
+
 int co_release_recapture(const double* trap, const double* atom, const double* tspan, int32_t nt, int64_t n, int64_t traj_offset,
                          int64_t n_total, double eps, uint64_t seed, const double* samples, int32_t out_flags, double* probs,
                          uint8_t* indicators) {

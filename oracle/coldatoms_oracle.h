@@ -21,6 +21,7 @@ void co_phase_draw(uint64_t seed, uint64_t index, uint32_t stream, int nf, doubl
 void co_phi(const double* tn, int n_nodes, const double* f, const double* amp, const double* phases, int nf, double* out);
 int co_rydberg1_run(const ca_model* model, const double* tspan, int32_t nt, const double* psi0, int64_t n_traj, int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples, const double* phases_red, const double* phases_blue, const double* f, const double* amp_red, const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats, int32_t nthreads);
 int co_rydberg2_run(const ca_model* model, const double* tspan, int32_t nt, const double* psi0, int64_t n_traj, int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2, const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats, int32_t nthreads);
+int co_rydberg2_run_ex(const ca_model* model, const double* tspan, int32_t nt, int32_t nt_seg1, const double* psi0, const double* rho0, int64_t n_traj, int64_t traj_offset, int64_t n_total, uint64_t seed, const double* samples1, const double* samples2, const double* const* phases4, const double* f, const double* amp_red, const double* amp_blue, int32_t nf, const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2, ca_stats* stats, int32_t nthreads);
 int co_release_recapture(const double* trap, const double* atom, const double* tspan, int32_t nt, int64_t n, int64_t traj_offset, int64_t n_total, double eps, uint64_t seed, const double* samples, int32_t out_flags, double* probs, uint8_t* indicators);
 int co_num_threads(void);
 void co_set_dense_emulation(int on); /* time the reference's dense mul! arithmetic (32 / 66 dense products per RHS) */

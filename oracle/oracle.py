@@ -182,6 +182,33 @@ def rydberg2_run(model, tspan, psi0, n_traj, traj_offset=0, n_total=0, seed=abi.
     return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
 
 
+def rydberg2_run_ex(model, tspan, psi0=None, rho0=None, n_traj=1, nt_seg1=0, traj_offset=0, n_total=0, seed=abi.DEFAULT_SEED, samples1=None,
+                    samples2=None, phases4=None, f=None, amp_red=None, amp_blue=None, ode=None, out_flags=0, nthreads=0):
+    """co_rydberg2_run_ex: general initial state (rho0[25,25] numpy [row, col]), two time segments, legacy two-atom flags."""
+    tspan = _arr(tspan)
+    nt = len(tspan)
+    samples1, samples2 = _arr(samples1), _arr(samples2)
+    f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
+    nf = 0 if f is None else len(f)
+    ph_arr, keep = None, []
+    if phases4 is not None:
+        keep = [_arr(p) for p in phases4]
+        ph_arr = (dp * 4)(*[_p(p) for p in keep])
+    r0 = None if rho0 is None else np.ascontiguousarray(np.asarray(rho0, dtype=np.complex128).T).view(np.float64)   # column-major
+    p0 = None if psi0 is None else _psi(psi0)
+    rho = np.zeros((nt, 25, 25), dtype=np.complex128)
+    rho2 = np.zeros((nt, 25, 25), dtype=np.complex128)
+    st = abi.ca_stats()
+    ode = ode if ode is not None else abi.ode_opts()
+    rc = lib().co_rydberg2_run_ex(C.byref(model), _p(tspan), C.c_int32(nt), C.c_int32(nt_seg1), _p(p0), _p(r0), C.c_int64(n_traj),
+                                  C.c_int64(traj_offset), C.c_int64(n_total), C.c_uint64(seed), _p(samples1), _p(samples2), ph_arr,
+                                  _p(f), _p(amp_red), _p(amp_blue), C.c_int32(nf), C.byref(ode), C.c_int32(out_flags),
+                                  rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), C.byref(st), C.c_int32(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"oracle rydberg2_ex failed rc={rc}")
+    return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
+
+
 def release_recapture(trap, atom, tspan, n, traj_offset=0, n_total=0, eps=1e-3, seed=abi.DEFAULT_SEED, samples=None,
                       out_flags=0, want_indicators=False):
     trap, atom, tspan, samples = _arr(trap), _arr(atom), _arr(tspan), _arr(samples)

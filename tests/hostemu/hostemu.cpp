@@ -9,6 +9,7 @@
 
 #include "../../coldatoms.jl_b200/csrc/ca_device.cuh"
 #include "../../coldatoms.jl_b200/csrc/ca_lindblad2.cuh"
+#include "../../coldatoms.jl_b200/csrc/ca_lindblad2f.cuh"
 #include "../../coldatoms.jl_b200/csrc/ca_model.h"
 
 using namespace ca;
@@ -79,6 +80,117 @@ static void* lane_main(void* p) {
     L.init(a->w.lane, *a->m);
     integrate2(a->w, L, *a->m, *a->oo, a->tspan, a->nt, a->tab, a->rho0, a->tr0, a->acc, a->st);
     return nullptr;
+}
+
+// ---- full-form two-atom kernel (ca_lindblad2f.cuh) run by 32 host threads in lock-step --------------------------------------------
+struct HostWarpF {
+    int lane;
+    double *xm, *xp, *kb;
+    double* coef;
+    double* smp;
+    HostShared* sh;
+    void sync() { pthread_barrier_wait(&sh->bar); }
+    double sum(double v) {
+        sh->red[lane][0] = v;
+        sync();
+        double s = 0.0;
+        for (int l = 0; l < 32; ++l) s += sh->red[l][0];
+        sync();
+        return s;
+    }
+};
+struct LaneArgsF {
+    HostWarpF w;
+    const DevModel* m; const DevModel2x* x; const OdeOpts* oo; const double* tspan; int nt, nt_seg1; const double* tab; double* acc;
+    Stats2 st;
+};
+static void* lane_main_f(void* p) {
+    LaneArgsF* a = static_cast<LaneArgsF*>(p);
+    a->st.n_rhs = a->st.n_acc = a->st.n_rej = a->st.n_exact = 0; a->st.status = 0;
+    if (a->nt_seg1 > 0 && a->nt_seg1 < a->nt) {
+        integrate2f(a->w, *a->m, *a->x, *a->oo, a->tspan, a->nt_seg1, 0, a->tab, a->acc, a->st);
+        if (a->st.status == 0)
+            integrate2f(a->w, *a->m, *a->x, *a->oo, a->tspan + a->nt_seg1, a->nt - a->nt_seg1, 1, a->tab, a->acc + (size_t)a->nt_seg1 * 2 * kF * 32, a->st);
+    } else integrate2f(a->w, *a->m, *a->x, *a->oo, a->tspan, a->nt, 0, a->tab, a->acc, a->st);
+    return nullptr;
+}
+
+extern "C" int he_rydberg2f_traj(const ca_model* model, const double* tspan, int nt, int nt_seg1, const double* psi0, const double* rho0,
+                                 const double* sample1, const double* sample2, const double* const* phases4, const double* f,
+                                 const double* amp_red, const double* amp_blue, int nf, const ca_ode_opts* ode, unsigned long long seed,
+                                 unsigned long long gi, double* rho, double* rho2, long long* stats) {
+    DevModel m;
+    double tmax = tspan[nt - 1];
+    if (nt_seg1 > 0 && tspan[nt_seg1 - 1] > tmax) tmax = tspan[nt_seg1 - 1];
+    int rc = derive_model(*model, nullptr, 0, tspan[0], tmax, &m);
+    if (rc) return rc;
+    DevModel2x x;
+    if ((rc = derive_model2x(*model, &x))) return rc;
+    OdeOpts oo;
+    const int n1 = nt_seg1 > 0 ? nt_seg1 : nt;
+    fill_ode(ode, tspan[0], tspan[n1 - 1], &oo);
+    if (nt_seg1 > 0 && !(ode && ode->dtmax > 0)) oo.dtmax = std::fmax(tspan[n1 - 1] - tspan[0], tspan[nt - 1] - tspan[nt_seg1]);
+    std::vector<double> tab;
+    const double* tp = nullptr;
+    if (m.laser_noise && nf > 0) {
+        tab.resize((size_t)4 * m.n_nodes);
+        std::vector<NoiseK> kr(nf), kb(nf);
+        fill_noise_k(f, amp_red, nf, m.dtn, kr.data());
+        fill_noise_k(f, amp_blue, nf, m.dtn, kb.data());
+        for (int q = 0; q < 4; ++q)
+            gen_noise_trace<64>((q & 1) ? kb.data() : kr.data(), nf, m.n_nodes, m.dtn, 0.0, phases4 ? phases4[q] : nullptr, seed, gi, 2u + q,
+                                tab.data() + (size_t)q * m.n_nodes, 1);
+        tp = tab.data();
+    }
+    std::vector<double> rho0f(32 * kF);
+    rho0_columns(psi0, rho0, rho0f.data());
+    HostShared sh;
+    pthread_barrier_init(&sh.bar, nullptr, 32);
+    sh.mem.assign(kWarpDoublesF + 2, 0.0);
+    double* base = sh.mem.data();
+    double* smp = base + 2 * kFXN + kFB * kF * 32 + kStages2 * kCoefF;
+    for (int a = 0; a < 2; ++a) {
+        double s6[6] = {0, 0, 0, 0, 0, 0};
+        const double* src = a == 0 ? sample1 : sample2;
+        if (src) std::memcpy(s6, src, sizeof s6);
+        else {
+            SamplerConsts sc;
+            for (int q = 0; q < 6; ++q) sc.sig[q] = m.sig[q];
+            sc.U0 = m.U0; sc.w0 = m.w0; sc.z0 = m.z0; sc.mfac = m.mfac; sc.ecut = m.ecut;
+            sample_atom_literal(sc, seed, gi, (uint32_t)a, s6);
+        }
+        if (!(x.flags & CA_2A_SHIFT_AFTER_MOTION)) for (int q = 0; q < 3; ++q) s6[q] += m.center[a][q];
+        for (int q = 0; q < 6; ++q) smp[6 * a + q] = m.atom_motion ? s6[q] : 0.0;
+    }
+    std::vector<double> acc((size_t)nt * 2 * kF * 32, 0.0);
+    std::vector<LaneArgsF> la(32);
+    std::vector<pthread_t> th(32);
+    for (int l = 0; l < 32; ++l) {
+        HostWarpF& w = la[l].w;
+        w.lane = l; w.xm = base; w.xp = base + kFXN; w.kb = base + 2 * kFXN + l;
+        w.coef = base + 2 * kFXN + kFB * kF * 32;
+        w.smp = smp;
+        w.sh = &sh;
+        for (int s = 0; s < kF; ++s) w.kb[(FB_Y * kF + s) * 32] = rho0f[l * kF + s];
+        la[l].m = &m; la[l].x = &x; la[l].oo = &oo; la[l].tspan = tspan; la[l].nt = nt; la[l].nt_seg1 = nt_seg1; la[l].tab = tp;
+        la[l].acc = acc.data() + l;
+    }
+    for (int l = 0; l < 32; ++l) pthread_create(&th[l], nullptr, lane_main_f, &la[l]);
+    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&sh.bar);
+    for (int j = 0; j < nt; ++j)
+        for (int which = 0; which < 2; ++which) {
+            const double* a = acc.data() + ((size_t)j * 2 + which) * kF * 32;
+            double* out = (which ? rho2 : rho) + (size_t)j * 1250;
+            for (int J = 0; J < 25; ++J)
+                for (int I = 0; I < 25; ++I) {
+                    const double s = a[I * 32 + J], st = a[J * 32 + I];
+                    out[2 * (I + 25 * J)] = 0.5 * (s + st);
+                    out[2 * (I + 25 * J) + 1] = I == J ? 0.0 : 0.5 * (s - st);
+                }
+        }
+    stats[0] = la[0].st.n_rhs; stats[1] = la[0].st.n_acc; stats[2] = la[0].st.n_rej; stats[3] = 0;
+    return la[0].st.status;
 }
 
 extern "C" {

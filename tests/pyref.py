@@ -184,3 +184,123 @@ def two_atom_traj(cfg, sample1, sample2, phases4=None, **kw):
 
     psi = np.asarray(cfg.ψ0, dtype=complex)
     return master(np.asarray(cfg.tspan), np.outer(psi, psi.conj()), H, J, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Legacy two-atom drivers, src/two_atom_model.jl, restated in the reference's OLD basis (g, p, r, gt, zero) with dense operators:
+# two_atom_simulation (:89-190) and direct_CZ_simulation (:192-319).  Used only to pin the oracle's / the kernels' handling of the
+# legacy parameterisations (level map g->1, p->p, r->r, gt->0, zero->l done by the HOST wrappers, not here).
+# ---------------------------------------------------------------------------------------------------------------------------
+from scipy.special import eval_genlaguerre, eval_hermite  # noqa: E402
+
+G_, P_, R_, GT_, Z_ = (ket(i) for i in range(5))   # two_atom_model.jl:3-8
+
+
+def _fact(n):
+    return float(math.factorial(n))
+
+
+def LG_coeff(k, n):   # arbitrary_beams.jl:24-30
+    return (-1.0) ** k * sum(_fact(i) / (2 ** i * _fact(i - k)) for i in range(k, n + 1)) / _fact(k)
+
+
+def HG_coeff(k, n):   # arbitrary_beams.jl:32-38
+    return sum(_fact(2 * i) / (_fact(i) * 2 ** (3 * i) * _fact(i - k) * _fact(2 * k)) for i in range(k, n + 1))
+
+
+def flattopHG(x, y, z, p):   # arbitrary_beams.jl:50-67
+    Ω, w0, zr, _, n, m, sqz = p
+    w = w0 * math.sqrt(1 + (z / zr) ** 2)
+    k = 2 * zr / w0 ** 2
+    phase0 = k * z + k / 2 * z * (x * x + y * y) / (z * z + zr * zr)
+    E = 0j
+    for i in range(0, int(n) + 1, 2):
+        for j in range(0, int(m) + 1, 2):
+            gouy = (i + j + 1) * math.atan(z / zr)
+            cij = HG_coeff(i // 2, int(n) // 2) * HG_coeff(j // 2, int(m) // 2)
+            hx = math.exp(-x * x / w ** 2) * eval_hermite(i, math.sqrt(2) * x / w)
+            hy = math.exp(-y * y / (w * sqz) ** 2) * eval_hermite(j, math.sqrt(2) * y / (w * sqz))
+            E += cij * hx * hy * np.exp(-1j * gouy)
+    return Ω * w0 * E / w * np.exp(-1j * phase0)
+
+
+def flattopLG(x, y, z, p):   # arbitrary_beams.jl:69-81
+    Ω, w0, zr, _, l, _m = p
+    w = w0 * math.sqrt(1 + (z / zr) ** 2)
+    k = 2 * zr / w0 ** 2
+    r2 = x * x + y * y
+    phase0 = k * z + k / 2 * z * r2 / (z * z + zr * zr)
+    E = 0j
+    for i in range(int(l) // 2 + 1):
+        E += LG_coeff(i, int(l) // 2) * math.exp(-r2 / w ** 2) * eval_genlaguerre(i, 0, 2 * r2 / w ** 2) * np.exp(-1j * (i + 1) * math.atan(z / zr))
+    return Ω * w0 / w * np.exp(-1j * phase0) * E
+
+
+def Omega_blue(x, y, z, p):   # rydberg_model_arb_bms.jl:6-13
+    return flattopLG(x, y, z, p) if p[3] == "simp_flattop_LG" else flattopHG(x, y, z, p)
+
+
+def _legacy_detunings(vz, red, blue, parallel):
+    """Δ(Vz, red) and δ(Vz, red, blue[1:3]; parallel): absent from the snapshot, semantics of SURVEY App. B7."""
+    kr, kb = 2 * red[2] / red[1] ** 2, 2 * blue[2] / blue[1] ** 2
+    return kr * vz, (kr + kb if parallel else kr - kb) * vz
+
+
+def legacy_two_atom_traj(tspan, psi0, atom_params, trap_params, s1, s2, red1, blue1, red2, blue2, det1, det2, decay_params, V_rr, beam_coords,
+                         atom_motion=True, free_motion=True, spontaneous_decay=True, parallel=False, **kw):
+    """two_atom_simulation (two_atom_model.jl:89-190) for ONE sample pair; ρ(t) in the old basis, index a1 + 5 a2."""
+    dist = 3.4
+    X0, Y0 = beam_coords
+    ωr, ωz = trap_frequencies(atom_params, trap_params)
+    Δ01, δ01 = det1
+    Δ02, δ02 = det2
+    Γg, Γgt = decay_params if spontaneous_decay else (0.0, 0.0)
+    one = [outer(P_, P_), outer(R_, R_), outer(G_, P_), outer(P_, G_), outer(P_, R_), outer(R_, P_)]   # np, nr, σgp, σpg, σpr, σrp
+    ops = [kron_q(o, Id) for o in one] + [kron_q(Id, o) for o in one] + [kron_q(outer(R_, R_), outer(R_, R_))]
+    j1 = [math.sqrt(Γg) * outer(G_, P_), math.sqrt(Γgt) * outer(GT_, P_)]
+    J = [kron_q(j, Id) for j in j1] + [kron_q(Id, j) for j in j1]   # physically correct Jdagger (SURVEY App. B11)
+    a = [np.array(s1, float) if atom_motion else np.zeros(6), np.array(s2, float) if atom_motion else np.zeros(6)]
+    fr = free_motion
+
+    def H(t):
+        c = []
+        for k, (red, blue, Δ0, δ0, off) in enumerate(((red1, blue1, Δ01, δ01, 0.0), (red2, blue2, Δ02, δ02, dist))):
+            x, y, z, vx, vy, vz = a[k]
+            X, Y, Z, Vz = R(t, x, vx, ωr, fr), R(t, y, vy, ωr, fr), R(t, z, vz, ωz, fr), V(t, z, vz, ωz, fr)
+            D, d = _legacy_detunings(Vz, red1, blue1, parallel)    # both atoms: the FIRST atom's laser parameters (:158-159, :168-169)
+            Ωr, Ωb = red[0], Omega_blue(off + X - X0, Y - Y0, Z, blue)
+            c += [-D - Δ0, -d - δ0, Ωr / 2, np.conj(Ωr) / 2, Ωb / 2, np.conj(Ωb) / 2]
+        c.append(V_rr)
+        return sum(ci * op for ci, op in zip(c, ops))
+
+    psi = np.asarray(psi0, dtype=complex)
+    return master(np.asarray(tspan), np.outer(psi, psi.conj()), H, J, **kw)
+
+
+def legacy_direct_cz_traj(tspan1, tspan2, rho1, atom_params, trap_params, s1, s2, blue1, blue2, det1, det2, decay_params, V_rr, phase,
+                          atom_motion=True, free_motion=True, spontaneous_decay=True, **kw):
+    """direct_CZ_simulation (two_atom_model.jl:192-319) for ONE sample pair: two consecutive solves, the second with exp(i phase)
+    on the couplings; Hermitian couplings in BOTH segments (the reference's first segment is not, see include/coldatoms_b200.h)."""
+    ωr, ωz = trap_frequencies(atom_params, trap_params)
+    Γg, Γgt = decay_params if spontaneous_decay else (0.0, 0.0)
+    one = [outer(R_, R_), outer(G_, R_), outer(R_, G_)]   # nr, σgr, σrg
+    ops = [kron_q(o, Id) for o in one] + [kron_q(Id, o) for o in one] + [kron_q(outer(R_, R_), outer(R_, R_))]
+    j1 = [math.sqrt(Γg) * outer(G_, P_), math.sqrt(Γgt) * outer(GT_, P_)]
+    J = [kron_q(j, Id) for j in j1] + [kron_q(Id, j) for j in j1]
+    a = [np.array(s1, float) if atom_motion else np.zeros(6), np.array(s2, float) if atom_motion else np.zeros(6)]
+    fr = free_motion
+
+    def Hseg(ph):
+        def H(t):
+            c = []
+            for k, (blue, Δ0) in enumerate(((blue1, det1[0]), (blue2, det2[0]))):
+                x, y, z, vx, vy, vz = a[k]
+                Ωd = np.exp(1j * ph) * Omega(R(t, x, vx, ωr, fr), R(t, y, vy, ωr, fr), R(t, z, vz, ωz, fr), blue)
+                c += [Δ0, Ωd / 2, np.conj(Ωd) / 2]
+            c.append(V_rr)
+            return sum(ci * op for ci, op in zip(c, ops))
+        return H
+
+    r1, n1 = master(np.asarray(tspan1), np.asarray(rho1, dtype=complex), Hseg(0.0), J, **kw)
+    r2, n2 = master(np.asarray(tspan2), r1[-1], Hseg(phase), J, **kw)
+    return np.concatenate([r1, r2]), n1 + n2

@@ -48,7 +48,7 @@ def test_struct_layouts_match_header(pkg):
     assert C.sizeof(abi.ca_beam) == 6 * 8 + 5 * 4 + 4  # 72 with tail padding
     assert C.sizeof(abi.ca_ode_opts) == 48
     assert C.sizeof(abi.ca_stats) == 5 * 8 + 3 * 8 + 8 + 8
-    assert C.sizeof(abi.ca_model) == 5 * 8 + 2 * 72 + 6 * 8 + 12 * 4 + 6 * 8 + 16
+    assert C.sizeof(abi.ca_model) == 5 * 8 + 2 * 72 + 6 * 8 + 12 * 4 + 6 * 8 + 16 + 8 + 2 * 72 + 4 * 8
 
 
 def test_default_configs_match_reference_numbers(pkg):
