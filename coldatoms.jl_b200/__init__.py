@@ -15,5 +15,5 @@ from .config import (RydbergConfig, CZLPConfig, get_default_configs, model_from_
 from .api import *  # noqa: F401,F403
 from .gates import get_gate, project_on_qubit, Id, Hadamard, X, Y, Z, RX, RY, RZ, op_tensor  # noqa: F401
 from .fidelity import (basis_fidelity_states, get_rydberg_fidelity_configs, get_rydberg_infidelity, get_parity_fidelity,  # noqa: F401
-                       get_parity_fidelity_temp, get_cz_infidelity, parity_scan)
+                       get_parity_fidelity_temp, get_cz_infidelity, parity_scan, cz_infidelity_points)
 from .legacy import two_atom_simulation, direct_CZ_simulation, legacy_two_atom_model, legacy_direct_model  # noqa: F401

@@ -24,7 +24,7 @@ EXPORTS = [
     "ca_collect_stats", "ca_stats_to_device",
     "ca_init_multi", "ca_finalize_multi", "ca_multi_size", "ca_multi_context", "ca_rydberg1_run_multi", "ca_rydberg2_run_multi",
     "ca_rydberg1_sweep_multi", "ca_release_recapture_multi",
-    "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg2_run_ex", "ca_rydberg1_sweep", "ca_release_recapture",
+    "ca_measure_fp64_peak", "ca_rydberg1_run", "ca_rydberg2_run", "ca_rydberg2_run_ex", "ca_rydberg1_sweep", "ca_rydberg2_sweep", "ca_release_recapture",
     "ca_sample_atoms", "ca_sample_atoms_metropolis", "ca_phase_noise", "ca_eval_beam", "ca_thermal_average",
 ]
 
@@ -209,6 +209,26 @@ class Context:
                                       C.byref(st)))
         if rho is None:
             return None, None, st.as_dict()
+        return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
+
+    def rydberg2_sweep(self, models, psi0s, t_end, n_traj_per_point, traj_offset=0, seed=_abi.DEFAULT_SEED, f=None, amp_red=None,
+                       amp_blue=None, ode=None, out_flags=0):
+        """ca_rydberg2_sweep: n_points CZ configurations in one launch; `n_traj_per_point` is an int or one count per point.
+        Returns (ρ(t_end)[n_points, 25, 25], ρ²(t_end), stats)."""
+        n_points = len(models)
+        marr = models if isinstance(models, C.Array) else (_abi.ca_model * n_points)(*models)
+        psi = np.ascontiguousarray(np.asarray(psi0s, dtype=np.complex128).reshape(n_points, 25)).view(np.float64)
+        t_end = _arr(t_end, (n_points,))
+        cnt = np.ascontiguousarray(np.broadcast_to(np.asarray(n_traj_per_point, dtype=np.int64), (n_points,)))
+        f, amp_red, amp_blue = _arr(f), _arr(amp_red), _arr(amp_blue)
+        nf = 0 if f is None else len(f)
+        rho = np.zeros((n_points, 25, 25), dtype=np.complex128)
+        rho2 = np.zeros((n_points, 25, 25), dtype=np.complex128)
+        st = _abi.ca_stats()
+        ode = ode if ode is not None else _abi.ode_opts()
+        _check(load().ca_rydberg2_sweep(self._h, marr, _p(psi), _p(t_end), C.c_int32(n_points), cnt.ctypes.data_as(C.POINTER(C.c_int64)),
+                                        C.c_int64(traj_offset), C.c_uint64(seed), _p(f), _p(amp_red), _p(amp_blue), C.c_int32(nf),
+                                        C.byref(ode), C.c_int32(out_flags), rho.ctypes.data_as(dp), rho2.ctypes.data_as(dp), C.byref(st)))
         return rho.transpose(0, 2, 1).copy(), rho2.transpose(0, 2, 1).copy(), st.as_dict()
 
     def rydberg2_run_ex(self, model, tspan, psi0=None, rho0=None, n_traj=1, nt_seg1=0, traj_offset=0, n_total=0, seed=_abi.DEFAULT_SEED,

@@ -216,6 +216,43 @@ CA_HD double exp_d(double x) {
     return ldexp(p, (int)n);
 #endif
 }
+// MUFU seed + ONE refinement (relative error ~1e-11): scale factors of the two-atom kernels' error norm
+CA_HD double rcp_r1(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+#else
+    return 1.0 / x;
+#endif
+}
+CA_HD double sqrt_r1(double x) {
+#if defined(__CUDA_ARCH__)
+    if (!(x > 0.0)) return 0.0;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double g = x * y, h = 0.5 * y;
+    return fma(g, fma(-h, g, 0.5), g);
+#else
+    return sqrt(x);
+#endif
+}
+// ln x for normal x > 0 (~1 ulp): x = m 2^e with m in [sqrt(1/2), sqrt(2)), ln m = 2 atanh((m - 1)/(m + 1)) by the odd series
+// (|u| <= 0.1716: u^21/21 < 4e-18), e ln2 added in two pieces.  No special cases: callers pass finite positive arguments.
+CA_HD double log_d(double x) {
+    int e;
+    double m;
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(x);
+    e = ((hi >> 20) & 0x7ff) - 1022;
+    m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(x));   // m in [0.5, 1)
+#else
+    m = frexp(x, &e);
+#endif
+    if (m < 0.70710678118654752440) { m *= 2.0; e -= 1; }
+    const double u = (m - 1.0) * rcp_d(m + 1.0);
+    return fma((double)e, MC.ln2_hi, fma((double)e, MC.ln2_lo, 2.0 * odd_series(u, false)));
+}
 CA_HD void sincos_fast(double a, double* sn, double* cs) {
     if (!(fabs(a) < 1.0e6)) { sincos_d(a, sn, cs); return; }
     const double t = fma(a, MC.two_over_pi, MC.magic);

@@ -100,6 +100,41 @@ CA_HD void scatter_entry(int lane, int slot, double v, double vt, double* out) {
     out[2 * (I + 25 * J) + 1] = I == J ? 0.0 : 0.5 * (v - vt);
 }
 
+// Step-size control of the two-atom kernels.  The one-atom kernel sizes its steps with single-precision log2 / exp2 and MUFU-seeded
+// reciprocals in the error norm (a step there is ~3 k cycles and the controller sat on its critical path).  A two-atom step is ~14 k
+// cycles, and its ensembles reject steps 30 times per trajectory, so EEst sits next to 1 often: with the approximate controller one
+// trajectory in six took a different accept / reject sequence than the reference algorithm (a different, equally valid DP5 solution,
+// but 1e-5 away in the coherences of an undamped thermal ensemble).  Here the norm uses once-refined reciprocals / square roots (1e-11)
+// and the controller the double-precision powers of OrdinaryDiffEq's PI controller (see oracle): the step sequence is the oracle's to
+// rounding (~+3 % run time with in-house double log / exp; the library pow / sqrt / division cost 25 %).
+#ifndef CA_CTRL_PRECISE2
+#define CA_CTRL_PRECISE2 1
+#endif
+struct StepCtrl2 {
+#if CA_CTRL_PRECISE2
+    double l_qold;   // ln(qold)
+    CA_HD void reset() { l_qold = -9.2103403719761827361; }   // ln(1e-4)
+    // accept: q = EEst^0.17 qold^-0.04 / 0.9 in [0.1, 5], dt = h / q, qold <- max(EEst, 1e-4); reject: dt = h / min(5, EEst^0.17 / 0.9)
+    // (DP5's PIController in OrdinaryDiffEq, see oracle) with in-house double log / exp (~1 ulp, no slow paths)
+    CA_HD double decide(double EEst2, bool acc) {   // returns dt / h
+        const double lE = EEst2 > 1e-300 ? 0.5 * log_d(EEst2) : -350.0;                       // ln(EEst); EEst = 0 saturates the clamps
+        const double base = fma(0.17, lE, 0.10536051565782630123);                            // - ln(0.9)
+        const double la = fmax(-2.3025850929940456840, fmin(1.6094379124341003746, fma(-0.04, l_qold, base)));   // ln q in [ln 0.1, ln 5]
+        const double lr = fmin(1.6094379124341003746, base);
+        l_qold = acc ? fmax(lE, -9.2103403719761827361) : l_qold;
+        return exp_d(-(acc ? la : lr));
+    }
+    static CA_HD double rcpn(double x) { return rcp_r1(x); }    // (1e-11: a decision could only flip for |EEst² - 1| < 1e-11)
+    static CA_HD double sqrtn(double x) { return sqrt_r1(x); }
+#else
+    StepCtrl c;
+    CA_HD void reset() { c.reset(); }
+    CA_HD double decide(double EEst2, bool acc) { return c.decide(EEst2, acc); }
+    static CA_HD double rcpn(double x) { return rcp_norm(x); }
+    static CA_HD double sqrtn(double x) { return sqrt_norm(x); }
+#endif
+};
+
 // Per-lane static data.
 struct Lane2 {
     int lane, h;
@@ -527,7 +562,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
     const double t0 = tspan[0], tend = tspan[nt - 1];
     double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0;
     bool pending = false;   // (un, k7, unt) hold an accepted step that is not yet in the buffers
-    StepCtrl ctrl;
+    StepCtrl2 ctrl;
     ctrl.reset();
     long long iters = 0;
     int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0, n_exact = 0;
@@ -644,7 +679,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 for (int s = 0; s < kS2; ++s) {
                     const double e = hh * fma(MC.e7, k7[s], er[s]);
                     const double yv = CA_KB(KB_Y, s), yt = CA_KB(KB_YT, s);
-                    const double isc = rcp_norm(atol + rtol * sqrt_norm(0.5 * fmax(yv * yv + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
+                    const double isc = StepCtrl2::rcpn(atol + rtol * StepCtrl2::sqrtn(0.5 * fmax(yv * yv + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
                     const bool eq = L.is_eq(s);
                     sacc += (e * e) * (isc * isc);
                     sdu += eq ? un[s] : 0.0; sde += eq ? e : 0.0;
@@ -652,7 +687,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 w.sum3(sacc, sdu, sde);
                 un_ll_new = tr0 - sdu;
                 {
-                    const double isc = rcp_norm(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
+                    const double isc = StepCtrl2::rcpn(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
                     sacc += (sde * sde) * (isc * isc);   // err of ρ_ll,ll = -Σ err of the other diagonal entries
                 }
                 const double EEst2 = sacc * (1.0 / 625.0);
@@ -714,7 +749,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
     for (int s = 0; s < kS2; ++s) { y[s] = rho0[s]; un[s] = y[s]; }
     const double t0 = tspan[0], tend = tspan[nt - 1];
     double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0;
-    StepCtrl ctrl;
+    StepCtrl2 ctrl;
     ctrl.reset();
     long long iters = 0;
     int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0, n_exact = 0;
@@ -828,7 +863,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 for (int s = 0; s < kS2; ++s) {
                     const double e = hh * fma(MC.e7, k7[s], er[s]);
                     const double yt = kb[(KB_YT * kS2 + s) * 32];
-                    const double isc = rcp_norm(atol + rtol * sqrt_norm(0.5 * fmax(y[s] * y[s] + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
+                    const double isc = StepCtrl2::rcpn(atol + rtol * StepCtrl2::sqrtn(0.5 * fmax(y[s] * y[s] + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
                     const bool eq = L.is_eq(s);
                     sacc += (e * e) * (isc * isc);
                     sdu += eq ? un[s] : 0.0; sde += eq ? e : 0.0;
@@ -836,7 +871,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 w.sum3(sacc, sdu, sde);
                 un_ll_new = tr0 - sdu;
                 {
-                    const double isc = rcp_norm(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
+                    const double isc = StepCtrl2::rcpn(atol + rtol * fmax(fabs(y_ll), fabs(un_ll_new)));
                     sacc += (sde * sde) * (isc * isc);   // err of ρ_ll,ll = -Σ err of the other diagonal entries
                 }
                 const double EEst2 = sacc * (1.0 / 625.0);

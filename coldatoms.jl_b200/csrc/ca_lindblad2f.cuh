@@ -264,7 +264,7 @@ CA_HD void integrate2f(W& w, const DevModel& m, const DevModel2x& x, const OdeOp
     const double t0 = tspan[0], tend = tspan[nt - 1];
     double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0;
     bool pending = false;
-    StepCtrl ctrl;
+    StepCtrl2 ctrl;
     ctrl.reset();
     long long iters = 0;
     int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0;
@@ -363,7 +363,7 @@ CA_HD void integrate2f(W& w, const DevModel& m, const DevModel2x& x, const OdeOp
                 for (int s = 0; s < kF; ++s) {
                     const double e = hh * fma(MC.e7, k7[s], ut[s]);
                     const double yv = CA_FB(FB_Y, s), yt = CA_FB(FB_YT, s);
-                    const double isc = rcp_norm(atol + rtol * sqrt_norm(0.5 * fmax(yv * yv + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
+                    const double isc = StepCtrl2::rcpn(atol + rtol * StepCtrl2::sqrtn(0.5 * fmax(yv * yv + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
                     sacc += act ? (e * e) * (isc * isc) : 0.0;
                 }
                 sacc = w.sum(sacc);

@@ -39,6 +39,12 @@ struct R2Params {
     DevModel2x x;            // legacy parameterisations (ca_model.two_atom_flags)
     const double* rho0f;     // [32][kF] columns of M(ρ0)
     int nt_seg1;             // 0, or the number of leading tspan points that form the first time segment
+    // sweeps (ca_rydberg2_sweep; blocked kernel only): rho0m is [n_points][32][kS2], tspan is [n_points][nt]
+    const DevModel* models;  // NULL, or one model per point
+    const double* tr0s;      // [n_points]
+    const long long* first;  // [n_points + 1] prefix sums of the per-point trajectory counts
+    double* accum_pt;        // [n_points][nt][2][kAccSlots][32] sums per point (atomics)
+    int n_points, n_nodes_max;
 };
 
 int run_r2_full(ca_ctx* c, const ca_model* model, const double* tspan, int32_t nt, int32_t nt_seg1, const double* psi0, const double* rho0,

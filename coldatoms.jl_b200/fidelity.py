@@ -122,27 +122,54 @@ def get_parity_fidelity_temp(ρ, ϕ_RZ):
     return float(np.real(np.conj(_Phi_p) @ ρt @ _Phi_p)), ρt
 
 
-def get_cz_infidelity(cfg, n_samples=1, seed=None, device=None, **ode_kwargs):
-    """src/fidelity.jl:193-240 -> ({name: infidelity above the calibration error}, calibration_error).
-    As in the reference only the calibration run sees ode_kwargs-free defaults; here ode_kwargs apply to every run."""
-    configs = get_rydberg_fidelity_configs(cfg, n_samples)
-    sd = _next_seed(seed)
+def cz_infidelity_points(cfg, n_samples=1):
+    """The seven simulation_czlp ensembles behind get_cz_infidelity (src/fidelity.jl:193-240), in the reference's order: the parity-scan
+    run that fixes ϕ_RZ (:205, n = 1), the calibration-error run (:225, n = 1), then the five error-budget configurations."""
     c = cfg.copy()
     c.spontaneous_decay_intermediate = c.spontaneous_decay_rydberg = c.laser_noise = False
     c.atom_params[1] = 1.0
     c.n_samples = 1
-    ϕ_RZ = get_parity_fidelity(c, seed=sd, device=device, **ode_kwargs)[2]
-    A = _Had2 @ op_tensor(RZ(ϕ_RZ), RZ(ϕ_RZ))
-
-    def infid(cc, k):
+    pts = [("parity scan", c), ("calibration", c.copy())] + list(get_rydberg_fidelity_configs(cfg, n_samples).items())
+    out = []
+    for name, cc in pts:
         cc = cc.copy()
         cc.ψ0 = tensor(_ket_pos, _ket_pos)
-        ρ = simulation_czlp(cc, seed=sd + k, device=device, **ode_kwargs)[0][-1]
+        out.append((name, cc))
+    return out
+
+
+def get_cz_infidelity(cfg, n_samples=1, seed=None, device=None, batched=True, **ode_kwargs):
+    """src/fidelity.jl:193-240 -> ({name: infidelity above the calibration error}, calibration_error).
+
+    batched=True (default): the seven ensembles run as ONE `ca_rydberg2_sweep` launch, trajectories of all of them handed
+    out longest first; point p uses the global trajectory indices Σ_{q<p} n_q + i of one Philox key.  batched=False: seven serial
+    `ca_rydberg2_run` calls on the SAME indices (so both paths agree to rounding).  ode_kwargs apply to every run."""
+    pts = cz_infidelity_points(cfg, n_samples)
+    sd = _next_seed(seed)
+    ctx = _lib.default_context(device)
+    ode = _ode(ode_kwargs)
+    kw = dict(f=cfg.f, amp_red=cfg.red_laser_phase_amplitudes, amp_blue=cfg.blue_laser_phase_amplitudes)
+    models = [model_from_config(c, two_atom=True) for _, c in pts]
+    counts = [int(c.n_samples) for _, c in pts]
+    if batched:
+        rho_end, _, _ = ctx.rydberg2_sweep(models, [c.ψ0 for _, c in pts], [c.tspan[-1] for _, c in pts], counts, seed=sd, ode=ode, **kw)
+    else:
+        rho_end, off = [], 0
+        for (_, c), m, n in zip(pts, models, counts):
+            noise = kw if c.laser_noise else {}
+            ρ, _, _ = ctx.rydberg2_run(m, [c.tspan[0], c.tspan[-1]], c.ψ0, n, traj_offset=off, seed=sd, ode=ode, **noise)
+            rho_end.append(ρ[-1])
+            off += n
+    ϕ_list = np.arange(0.0, 2 * np.pi, 1e-4)
+    ϕ_RZ = float(ϕ_list[int(np.argmax(parity_scan(rho_end[0], ϕ_list)))])
+    A = _Had2 @ op_tensor(RZ(ϕ_RZ), RZ(ϕ_RZ))
+
+    def infid(ρ):
         ρ = A @ ρ @ A.conj().T
         return 1.0 - float(np.real(np.conj(_Phi_p) @ ρ @ _Phi_p))
 
-    calibration_error = infid(c, 0)
+    calibration_error = infid(rho_end[1])
     out = OrderedDict()
-    for k, (name, cc) in enumerate(configs.items()):
-        out[name] = max(infid(cc, 1 + k) - calibration_error, 0.0)
+    for (name, _), ρ in zip(pts[2:], rho_end[2:]):
+        out[name] = max(infid(ρ) - calibration_error, 0.0)
     return out, calibration_error

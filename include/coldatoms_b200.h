@@ -15,6 +15,7 @@
  *   ca_sample_atoms_metropolis <- samples_generate (harmonic=false branch) src/atom_sampler.jl:97-120
  *   ca_phase_noise       <- ϕ                         src/lasernoise_sampler.jl:31-37
  *   ca_rydberg1_sweep    <- the (config, ψ0) loops of src/fidelity.jl:78-88 and BASELINE config 5
+ *   ca_rydberg2_sweep    <- the seven simulation_czlp ensembles of get_cz_infidelity src/fidelity.jl:193-240
  *   ca_thermal_average   <- the sample loops of calibrate_two_photon src/rydberg_model.jl:285-306 and
  *                           get_blockade_stark_shift_factor src/cz_model.jl:77-104
  *
@@ -249,6 +250,18 @@ int ca_rydberg1_sweep(ca_ctx* ctx, const ca_model* models, const double* psi0s, 
                       uint64_t seed, const double* f, const double* amp_red, const double* amp_blue,
                       int32_t nf, const ca_ode_opts* ode, int32_t out_flags, double* rho, double* rho2,
                       ca_stats* stats);
+
+/*
+ * Batched two-atom sweep: n_points CZ configurations in one launch (the seven ensembles of get_cz_infidelity, src/fidelity.jl:193-240;
+ * SURVEY 8f-1).  Point p has its own model, ψ0 (25 complex, inside the {0,1,r,p}^2 block), end time t_end[p] (tspan = [0, t_end[p]];
+ * only ρ(t_end), ρ²(t_end) are returned) and trajectory count n_traj_per_point[p]; its trajectories carry the global indices
+ * traj_offset + (Σ_{q<p} n_traj_per_point[q]) + i, and all trajectories are handed out longest first across the points.
+ * rho/rho2: n_points*625 complex128, each point divided by its own count (CA_OUT_MEAN) or left as sums (CA_OUT_SUMS).
+ */
+int ca_rydberg2_sweep(ca_ctx* ctx, const ca_model* models, const double* psi0s, const double* t_end, int32_t n_points,
+                      const int64_t* n_traj_per_point, int64_t traj_offset, uint64_t seed, const double* f,
+                      const double* amp_red, const double* amp_blue, int32_t nf, const ca_ode_opts* ode,
+                      int32_t out_flags, double* rho, double* rho2, ca_stats* stats);
 
 /*
  * Release and recapture (basic_experiments.jl:25-81).  trap = (U0,w0,z0), atom = (m,T).

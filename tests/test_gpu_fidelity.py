@@ -36,6 +36,29 @@ def test_cz_parity_pipeline(pkg, oracle):
     o, _, _ = oracle.rydberg2_run(pkg.model_from_config(c, two_atom=True), c.tspan, c.ψ0, 1, seed=3)
     assert np.abs(pkg.parity_scan(o[-1], ϕs[::97]) - F[::97]).max() < 1e-6
     inf, cal = pkg.get_cz_infidelity(cz, n_samples=2, seed=3)
-    assert abs(cal - (1.0 - F.max())) < 1e-9   # calibration run = the scan's trajectory at its best phase
+    assert abs(cal - (1.0 - F.max())) < 1e-6   # calibration run: another 1 µK sample of the scan's configuration at its best phase
     assert set(inf) == {"Intermdeiate state decay", "Rydberg state decay", "Laser noise", "Atom motion", "Total"}
     assert all(0 <= v < 0.5 for v in inf.values())
+
+
+def test_cz_infidelity_sweep_matches_oracle_and_serial(pkg, oracle, ctx):
+    """get_cz_infidelity's seven ensembles as ONE ca_rydberg2_sweep launch: every point against the ORACLE on the same global
+    trajectory indices, and the batched pipeline against the serial one."""
+    _, cz = pkg.get_default_configs()
+    pts = pkg.cz_infidelity_points(cz, n_samples=5)
+    assert [n for n, _ in pts][:2] == ["parity scan", "calibration"] and len(pts) == 7
+    models = [pkg.model_from_config(c, two_atom=True) for _, c in pts]
+    counts = [int(c.n_samples) for _, c in pts]
+    kw = dict(f=cz.f, amp_red=cz.red_laser_phase_amplitudes, amp_blue=cz.blue_laser_phase_amplitudes)
+    ode = pkg._abi.ode_opts(maxiters=10 ** 6)
+    rho, rho2, st = ctx.rydberg2_sweep(models, [c.ψ0 for _, c in pts], [c.tspan[-1] for _, c in pts], counts, seed=11, traj_offset=100, ode=ode, **kw)
+    assert st["n_traj"] == sum(counts) and st["status"] == 0
+    off = 100
+    for k, ((name, c), m, n) in enumerate(zip(pts, models, counts)):
+        noise = kw if c.laser_noise else {}
+        o, o2, _ = oracle.rydberg2_run(m, [0.0, c.tspan[-1]], c.ψ0, n, traj_offset=off, seed=11, ode=ode, **noise)
+        assert np.abs(rho[k] - o[-1]).max() < 1e-6 and np.abs(rho2[k] - o2[-1]).max() < 1e-6, name
+        off += n
+    a, ca = pkg.get_cz_infidelity(cz, n_samples=3, seed=5, batched=True)
+    b, cb = pkg.get_cz_infidelity(cz, n_samples=3, seed=5, batched=False)
+    assert abs(ca - cb) < 1e-9 and all(abs(a[k] - b[k]) < 1e-8 for k in a)
