@@ -56,7 +56,13 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
     double* sab = scb + 30 * T;                                                         // [2][2][5][T] beam anchors (NS <= 15)
     DevModel* sm_models = reinterpret_cast<DevModel*>(sk + smem_doubles_per_thread<NS>() * T);  // [warps] (sweeps only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wg = (long long)blockIdx.x * (T / 32) + warp;
+#ifndef CA_WARP_MAJOR
+#define CA_WARP_MAJOR 1
+#endif
+    // Warp-major numbering: the groups of a round go to warp 0 of every CTA first, then warp 1, ...  A PARTIAL last round (strong
+    // scaling: 10^6 / 8 GPUs = 3.3 rounds) is then spread over all SMs with fewer resident warps each, which finish sooner than a
+    // few fully loaded SMs would.
+    const long long wg = CA_WARP_MAJOR ? (long long)warp * gridDim.x + blockIdx.x : (long long)blockIdx.x * (T / 32) + warp;
     const long long W = (long long)gridDim.x * (T / 32);
     long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0, tot_exact = 0;
     long long cyc_noise = 0, cyc_all = -clock64();
