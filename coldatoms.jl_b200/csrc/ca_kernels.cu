@@ -375,8 +375,8 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     }
     // grid: persistent warps, 3 (NS=9) / 2 / 1 CTAs of 128 threads per SM
     const int ns_sel = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
-    const int wpb = (ns_sel == 9 ? 256 : (ns_sel == 15 ? 96 : 128)) / 32;
-    const int bps = ns_sel == 9 ? 1 : (ns_sel == 15 ? 2 : 1);
+    const int wpb = (ns_sel == 9 ? threads_for<9>() : (ns_sel == 15 ? threads_for<15>() : threads_for<21>())) / 32;
+    const int bps = ns_sel == 9 ? blocks_per_sm<9>() : (ns_sel == 15 ? blocks_per_sm<15>() : blocks_per_sm<21>());
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
     int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
     if (any_noise) {

@@ -22,7 +22,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ----------------------------------------------------------------------------------------------------
 // K1+K2+K3: fused one-atom ensemble kernel
 // ----------------------------------------------------------------------------------------------------
-template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? 96 : 128); }
+// NS = 15 (a |0> or |l> component in ψ0: four of the six fidelity basis states) spills ~0.5 KB per thread at 255 registers.  With two CTAs
+// of 96 threads the shared-memory carve-out (215 KB) left no L1 for those spills: they went to L2 and `long_scoreboard` on LDL was the
+// largest stall (profiles/r2/k_lindblad1_ns15_ncu_summary.txt).  One CTA of 128 threads (143 KB) leaves ~100 KB of L1: 404k -> 452k traj/s
+// although a third of the warps are gone (160 threads: 393k; y_new / error in two passes to cut the live vectors: 378k).
+#ifndef CA_NS15_THREADS
+#define CA_NS15_THREADS 128
+#define CA_NS15_BLOCKS 1
+#endif
+template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? CA_NS15_THREADS : 128); }
 template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS <= 15 ? 20 : 0); }   // k slots + stage coefficients + anchors (NS <= 15)
 constexpr int kNoiseChunk = 64;
 
@@ -45,7 +53,7 @@ struct R1Params {
 };
 
 template <int NS>
-__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 1 : (NS == 15 ? 2 : 1); }
+__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 1 : (NS == 15 ? CA_NS15_BLOCKS : 1); }
 
 template <int NS, bool SWEEP, int BEAMS>
 __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {

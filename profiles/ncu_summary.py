@@ -1,4 +1,6 @@
-"""Summarise an .ncu-rep (read here, no GPU needed): key raw metrics, dynamic opcode mix, stall breakdown.
+"""Summarise an .ncu-rep (read here, no GPU needed): key raw metrics incl. register-spill (local-memory) counters, dynamic opcode mix,
+stall breakdown.  With NCU_TRAJ=<trajectories of the captured launch> and NCU_KEY=<name> the DRAM bytes per trajectory are merged into
+profiles/ncu_traffic.json (what bench.py reports as roofline.traffic).
     python profiles/ncu_summary.py gpurun_out/x.ncu-rep [kernel-index]"""
 import collections, csv, io, re, subprocess, sys
 rep = sys.argv[1]
@@ -12,10 +14,25 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "smsp__warps_eligible.avg.per_cycle_active", "l1tex__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__cycles_active.avg", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
+        "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        # occupancy and register spills (local memory)
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic",
+        "sm__maximum_warps_per_active_cycle_pct", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "smsp__sass_inst_executed_op_local.sum"]
 for k in keys:
     if k in d:
         print(f"{k:78s} {d[k][0]:14s} {d[k][1]}")
+import json, os
+if os.environ.get("NCU_TRAJ") and os.environ.get("NCU_KEY"):
+    tf = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
+    tj = json.load(open(tf)) if os.path.exists(tf) else {}
+    def _bytes(k):
+        u, v = d[k]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    tot_b = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+    tj[os.environ["NCU_KEY"]] = {"dram_bytes_per_trajectory": tot_b / float(os.environ["NCU_TRAJ"]), "dram_bytes": tot_b,
+                                "trajectories": int(os.environ["NCU_TRAJ"]), "source": os.environ.get("NCU_SRC", os.path.basename(rep))}
+    json.dump(tj, open(tf, "w"), indent=1)
 print("--- stall reasons (warps per issue-active cycle)")
 for h in hdr:
     if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h:
