@@ -149,26 +149,34 @@ class Workload:
         if self.name == "c1":
             return 25.0 * self.nt * n
         traces = 2 * self.natoms if self.noise else 0
-        c = noise_coarse(self.cfg) if (self.natoms == 1 and self.noise) else 1
-        nodes_summed = 1001 if c == 1 else (1000 + c - 1) // c + 8
+        c, pw = noise_plan(self.cfg) if (self.natoms == 1 and self.noise) else (1, 8)
+        nodes_summed = 1001 if c == 1 else (1000 + c - 1) // c + pw
         nf = len(self.cfg.f) if self.noise else 0
-        f_noise = traces * (nodes_summed * nf * F_NOISE_PER + (0 if c == 1 else 1001 * 16)) * n
+        f_noise = traces * (nodes_summed * nf * F_NOISE_PER + (0 if c == 1 else 1001 * 2 * pw)) * n   # (one FMA per window node and table entry)
         nt_out = 1 if self.name == "s1" else self.nt
         f_obs = nt_out * (8 * self.d ** 3 + 4 * self.d ** 2) * n
         return st["n_rhs"] * self.f_rhs + f_noise + f_obs
 
 
-def noise_coarse(cfg):
-    """The coarsening factor the one-atom kernel picks for its phase-noise tables (choose_noise_coarse, ca_device.cuh)."""
-    dtn = cfg.tspan[-1] / 1000.0
-    for c in (32, 16, 8, 4, 2):
-        if ((1000 + c - 1) // c + 8) * c > 2 * 1001:
-            continue
-        b = max(float(np.sum(np.abs(a) * (2 * np.pi * np.abs(cfg.f) * c * dtn) ** 8))
-                for a in (cfg.red_laser_phase_amplitudes, cfg.blue_laser_phase_amplitudes))
-        if b * 43.07 / 40320.0 <= 1e-14:
-            return c
-    return 1
+def noise_plan(cfg, n_nodes=1001, chunk=64):
+    """(c, p): the interpolation plan the one-atom kernel picks for its phase-noise tables (choose_noise_coarse, ca_device.cuh):
+    every c-th node is summed over the frequencies, the others follow from p-point Lagrange interpolation."""
+    dtn = cfg.tspan[-1] / (n_nodes - 1.0)
+    nf = len(cfg.f)
+    best, best_cost = (1, 8), float("inf")
+    for p in (8, 16):
+        for c in ((32, 16, 8, 4, 2) if p == 8 else (32, 16, 8)):
+            n_c = (n_nodes - 1 + c - 1) // c + p
+            if p == 8 and n_c * c > 2 * n_nodes:
+                continue
+            b = max(float(np.sum(np.abs(a) * (2 * np.pi * np.abs(cfg.f) * c * dtn) ** p))
+                    for a in (cfg.red_laser_phase_amplitudes, cfg.blue_laser_phase_amplitudes))
+            if not b * (2.9966e-6 if p == 16 else 43.07 / 40320.0) <= 1e-14:
+                continue
+            cost = ((n_c + chunk - 1) // chunk) * nf * 45.0 + n_c * nf * 3.0 + n_nodes * p
+            if cost < best_cost:
+                best, best_cost = (c, p), cost
+    return best
 
 
 class ClockSampler:

@@ -308,7 +308,7 @@ struct DevModel {
     int atom_motion, free_motion, laser_noise;
     int vz_from_vy, doppler_z_legacy, rho2_mode;
     int rows;                   // bit0: ψ0 has a |0> component, bit1: |l> component
-    int noise_coarse;           // phase-noise tables: every noise_coarse-th node is summed exactly (see gen_noise_trace_c)
+    int noise_coarse;           // phase-noise tables: interpolation plan (noise_c / noise_p): every c-th node is summed exactly (see gen_noise_trace_c)
     double rho0[25];            // Hermitian-packed initial state (see pack order below)
 };
 
@@ -699,6 +699,7 @@ CA_HD void gen_noise_trace(const NoiseK* __restrict__ nk, int nf, int n_nodes, d
             acc[0] += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
 #pragma unroll
             for (int j = 1; j < CH; ++j) {
+                if ((j & 7) == 0 && c0 + j >= n_nodes) break;   // (uniform) the last chunk stops at the end of the table, to a multiple of 8 nodes
 #pragma unroll
                 for (int q = 0; q < KB; ++q) { c[q] += d[q]; d[q] = fma(sig[q], c[q], d[q]); }
                 acc[j] += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
@@ -795,51 +796,93 @@ static const LagrangeW h_lw = CA_LAGRANGE_INIT;
 #define LW h_lw
 #endif
 
-CA_HD int noise_coarse_count(int n_nodes, int c) { return (n_nodes - 1 + c - 1) / c + 8; }   // coarse nodes m = -3 .. ceil((n-1)/c) + 4
+// 16-point (degree 15) weights: the same construction with twice the window lets the coarse grid be 4x sparser at the same error bound
+// (R1: every 16th node instead of every 4th, 79 summed nodes per trace instead of 258).
+#include "ca_lagrange16.h"
+struct LagrangeW16 { double w[53][16]; };
+#if defined(__CUDACC__)
+static __constant__ LagrangeW16 c_lw16 = CA_LAGRANGE16_INIT;
+#endif
+static const LagrangeW16 h_lw16 = CA_LAGRANGE16_INIT;
+#if defined(__CUDA_ARCH__)
+#define LW16 c_lw16
+#else
+#define LW16 h_lw16
+#endif
 
-// host: largest coarsening factor whose interpolation error bound stays below 1e-14 rad (1 = sum every node)
+// Interpolation plan, encoded in one int (DevModel::noise_coarse): low byte = coarsening factor c (1: every node is summed), bit 8 set =
+// 16-point window (else 8-point).
+CA_HD int noise_c(int plan) { return plan & 0xff; }
+CA_HD int noise_p(int plan) { return (plan & 0x100) ? 16 : 8; }
+CA_HD int noise_coarse_count(int n_nodes, int plan) {   // coarse nodes m = -(p/2 - 1) .. ceil((n-1)/c) + p/2
+    const int c = noise_c(plan);
+    return (n_nodes - 1 + c - 1) / c + noise_p(plan);
+}
+#ifndef CA_NOISE_CHUNK
+#define CA_NOISE_CHUNK 64
+#endif
+constexpr int kNoiseChunk = CA_NOISE_CHUNK;   // nodes summed per pass over the frequencies (accumulators in registers)
+
+// host: the cheapest plan whose interpolation error bound stays below 1e-14 rad (1 = sum every node).  p-point central Lagrange
+// interpolation of cos(ω t + φ) on nodes of spacing H errs by at most (ω H)^p / p! · max_s Π|s - j| = (ω H)^p · K_p / p!, with
+// K_8 = (0.5·1.5·2.5·3.5)² = 43.07 and K_16 = (0.5·1.5· … ·7.5)² = 6.2696e7.  Cost model: one sincos set-up per (pass, frequency) ~45
+// flop-equivalents, 3 per (summed node, frequency), p per interpolated node.
 inline int choose_noise_coarse(const double* f, const double* amp_a, const double* amp_b, int nf, double dtn, int n_nodes) {
     if (n_nodes < 64) return 1;
-    for (int c = 32; c >= 2; c >>= 1) {
-        if (noise_coarse_count(n_nodes, c) * c > 2 * n_nodes) continue;   // the 8 padding nodes must not dominate
-        double ba = 0.0, bb = 0.0;
-        for (int k = 0; k < nf; ++k) {
-            const double x = kTwoPi * fabs(f[k]) * c * dtn, x2 = x * x, x8 = (x2 * x2) * (x2 * x2);
-            ba += fabs(amp_a[k]) * x8; bb += fabs(amp_b ? amp_b[k] : 0.0) * x8;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int p = 8; p <= 16; p += 8) {
+        for (int c = 32; c >= (p == 16 ? 8 : 2); c >>= 1) {
+            const int plan = c | (p == 16 ? 0x100 : 0), n_c = noise_coarse_count(n_nodes, plan);
+            if (p == 8 && n_c * c > 2 * n_nodes) continue;   // the padding nodes must not dominate
+            double ba = 0.0, bb = 0.0;
+            for (int k = 0; k < nf; ++k) {
+                const double x = kTwoPi * fabs(f[k]) * c * dtn, x2 = x * x, x8 = (x2 * x2) * (x2 * x2), xp = p == 16 ? x8 * x8 : x8;
+                ba += fabs(amp_a[k]) * xp; bb += fabs(amp_b ? amp_b[k] : 0.0) * xp;
+            }
+            const double kp = p == 16 ? 2.9966e-6 : 43.07 / 40320.0;   // K_p / p!
+            if (!(fmax(ba, bb) * kp <= 1e-14)) continue;
+            const double cost = (double)((n_c + kNoiseChunk - 1) / kNoiseChunk) * nf * 45.0 + (double)n_c * nf * 3.0 + (double)n_nodes * p;
+            if (cost < best_cost) { best_cost = cost; best = plan; }
         }
-        if (fmax(ba, bb) * (43.07 / 40320.0) <= 1e-14) return c;
     }
-    return 1;
+    return best;
 }
 
-// nk must hold the recurrence constants of spacing c*dtn (fill_noise_k(f, amp, nf, c*dtn)); tmp: noise_coarse_count(n_nodes, c) slots.
-template <int CH>
-CA_HD void gen_noise_trace_c(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, int c, const double* __restrict__ phases, uint64_t seed,
-                             uint64_t gi, uint32_t stream, double* __restrict__ out, int stride, double* __restrict__ tmp, int tstride) {
-    if (c <= 1) { gen_noise_trace<CH>(nk, nf, n_nodes, dtn, 0.0, phases, seed, gi, stream, out, stride); return; }
-    const int n_c = noise_coarse_count(n_nodes, c);
-    gen_noise_trace<CH>(nk, nf, n_c, c * dtn, -3.0 * c * dtn, phases, seed, gi, stream, tmp, tstride);
-    const int row0 = c == 2 ? 0 : (c == 4 ? 1 : (c == 8 ? 4 : (c == 16 ? 11 : 26)));
-    double win[8];
+// nk must hold the recurrence constants of spacing c*dtn (fill_noise_k(f, amp, nf, noise_c(plan)*dtn)); tmp: noise_coarse_count(n_nodes, plan) slots.
+template <int CH, int PW>
+CA_HD void interpolate_noise(int n_nodes, int c, const double* __restrict__ tmp, int tstride, double* __restrict__ out, int stride) {
+    const int row0 = PW == 8 ? (c == 2 ? 0 : (c == 4 ? 1 : (c == 8 ? 4 : (c == 16 ? 11 : 26)))) : (c == 8 ? 0 : (c == 16 ? 7 : 22));
+    double win[PW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) win[i] = tmp[(size_t)i * tstride];
+    for (int i = 0; i < PW; ++i) win[i] = tmp[(size_t)i * tstride];
     for (int mc = 0; mc * c < n_nodes; ++mc) {
         if (mc > 0) {
 #pragma unroll
-            for (int i = 0; i < 7; ++i) win[i] = win[i + 1];
-            win[7] = tmp[(size_t)(mc + 7) * tstride];
+            for (int i = 0; i < PW - 1; ++i) win[i] = win[i + 1];
+            win[PW - 1] = tmp[(size_t)(mc + PW - 1) * tstride];
         }
-        out[(size_t)(mc * c) * stride] = win[3];
+        out[(size_t)(mc * c) * stride] = win[PW / 2 - 1];
         for (int r = 1; r < c; ++r) {
             const int j = mc * c + r;
             if (j >= n_nodes) break;
-            const double* wv = LW.w[row0 + r - 1];
-            double a = wv[0] * win[0];
+            const double* wv = PW == 8 ? LW.w[row0 + r - 1] : LW16.w[row0 + r - 1];
+            double a = wv[0] * win[0], b = wv[1] * win[1];   // two chains
 #pragma unroll
-            for (int i = 1; i < 8; ++i) a = fma(wv[i], win[i], a);
-            out[(size_t)j * stride] = a;
+            for (int i = 2; i < PW; i += 2) { a = fma(wv[i], win[i], a); b = fma(wv[i + 1], win[i + 1], b); }
+            out[(size_t)j * stride] = a + b;
         }
     }
+}
+template <int CH>
+CA_HD void gen_noise_trace_c(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, int plan, const double* __restrict__ phases, uint64_t seed,
+                             uint64_t gi, uint32_t stream, double* __restrict__ out, int stride, double* __restrict__ tmp, int tstride) {
+    const int c = noise_c(plan);
+    if (c <= 1) { gen_noise_trace<CH>(nk, nf, n_nodes, dtn, 0.0, phases, seed, gi, stream, out, stride); return; }
+    const int n_c = noise_coarse_count(n_nodes, plan), pw = noise_p(plan);
+    gen_noise_trace<CH>(nk, nf, n_c, c * dtn, -(pw / 2 - 1.0) * c * dtn, phases, seed, gi, stream, tmp, tstride);
+    if (pw == 8) interpolate_noise<CH, 8>(n_nodes, c, tmp, tstride, out, stride);
+    else interpolate_noise<CH, 16>(n_nodes, c, tmp, tstride, out, stride);
 }
 
 // ---------------------------------------------------------------------------------------------------

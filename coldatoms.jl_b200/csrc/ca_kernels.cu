@@ -363,8 +363,8 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
         if ((rc = ensure_pinned(c, nkb))) return rc;
         NoiseK* hk = (NoiseK*)c->pinned;
         for (int p = 0; p < n_points; ++p) {
-            fill_noise_k(f, amp_red, nf, dm[p].noise_coarse * dm[p].dtn, hk + (size_t)p * nf);
-            fill_noise_k(f, amp_blue, nf, dm[p].noise_coarse * dm[p].dtn, hk + (size_t)(n_points + p) * nf);
+            fill_noise_k(f, amp_red, nf, noise_c(dm[p].noise_coarse) * dm[p].dtn, hk + (size_t)p * nf);
+            fill_noise_k(f, amp_blue, nf, noise_c(dm[p].noise_coarse) * dm[p].dtn, hk + (size_t)(n_points + p) * nf);
         }
         if ((rc = c->in_f.ensure(nkb))) return rc;
         CA_CUDA(cudaMemcpyAsync(c->in_f.p, c->pinned, nkb, cudaMemcpyHostToDevice, c->stream));
@@ -701,7 +701,7 @@ int ca_phase_noise(ca_ctx* c, const double* tnodes, int32_t n_nodes, const doubl
     int rc;
     std::vector<NoiseK> hk((size_t)nf);
     const int coarse = choose_noise_coarse(f, amp, nullptr, nf, dtn, n_nodes);
-    fill_noise_k(f, amp, nf, coarse * dtn, hk.data());
+    fill_noise_k(f, amp, nf, noise_c(coarse) * dtn, hk.data());
     if ((rc = upload(c, c->in_f, hk.data(), sizeof(NoiseK) * (size_t)nf))) return rc;
     CA_CUDA(cudaStreamSynchronize(c->stream));
     const double* d_ph = nullptr;

@@ -32,7 +32,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 #endif
 template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? CA_NS15_THREADS : 128); }
 template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS <= 15 ? 20 : 0); }   // k slots + stage coefficients + anchors (NS <= 15)
-constexpr int kNoiseChunk = 64;
 
 struct R1Params {
     DevModel model;            // single-point runs: lives in the constant bank with the other params

@@ -284,8 +284,8 @@ int he_rydberg1_traj(const ca_model* model, const double* tspan, int nt, const d
         std::vector<NoiseK> kr(nf), kb(nf);
         const int cz = choose_noise_coarse(f, amp_red, amp_blue, nf, m.dtn, m.n_nodes);   // same plan as run_r1
         std::vector<double> tmp(noise_coarse_count(m.n_nodes, cz));
-        fill_noise_k(f, amp_red, nf, cz * m.dtn, kr.data());
-        fill_noise_k(f, amp_blue, nf, cz * m.dtn, kb.data());
+        fill_noise_k(f, amp_red, nf, noise_c(cz) * m.dtn, kr.data());
+        fill_noise_k(f, amp_blue, nf, noise_c(cz) * m.dtn, kb.data());
         gen_noise_trace_c<64>(kr.data(), nf, m.n_nodes, m.dtn, cz, phases_red, seed, gi, 2u, tab.data(), 1, tmp.data(), 1);
         gen_noise_trace_c<64>(kb.data(), nf, m.n_nodes, m.dtn, cz, phases_blue, seed, gi, 3u, tab.data() + m.n_nodes, 1, tmp.data(), 1);
         tp = tab.data();
@@ -309,7 +309,7 @@ int he_noise_trace(const double* f, const double* amp, int nf, int n_nodes, doub
     std::vector<NoiseK> kk(nf);
     const int cz = choose_noise_coarse(f, amp, nullptr, nf, dtn, n_nodes);
     std::vector<double> tmp(noise_coarse_count(n_nodes, cz));
-    fill_noise_k(f, amp, nf, cz * dtn, kk.data());
+    fill_noise_k(f, amp, nf, noise_c(cz) * dtn, kk.data());
     gen_noise_trace_c<64>(kk.data(), nf, n_nodes, dtn, cz, phases, seed, gi, stream, out, 1, tmp.data(), 1);
     return 0;
 }
