@@ -40,12 +40,21 @@ constexpr int kXN = kXL + 32;      // doubles per exchange buffer
 #if CA_RK_SMEM
 enum { KB_3 = 0, KB_4 = 1, KB_5 = 2, KB_6 = 3, KB_YT = 4, KB_Y = 5, KB_1 = 6, KB_2 = 7, kKB = 8 };   // per-lane buffers in shared memory
 #else
-enum { KB_3 = 0, KB_4 = 1, KB_5 = 2, KB_6 = 3, KB_YT = 4, kKB = 5 };   // per-lane buffers in shared memory
+#ifndef CA_Y_SMEM
+#define CA_Y_SMEM 0    // 1: y (start of the step) lives in shared memory between its uses (stage combinations, norm, dense output)
+#endif
+#ifndef CA_K1_SMEM
+#define CA_K1_SMEM 0   // 1: the same for k1
+#endif
+enum { KB_3 = 0, KB_4 = 1, KB_5 = 2, KB_6 = 3, KB_YT = 4, KB_Y = 5, KB_1 = 6, kKB = 5 + 2 * (CA_Y_SMEM || CA_K1_SMEM) };   // per-lane buffers in shared memory
 #endif
 constexpr int kStages2 = 5;        // distinct stage times c2,c3,c4,c5,c6(=c7)
 constexpr int kAccSlots = 10;      // accumulator slots per lane: 9 + ρ_ll,ll (lane 0)
 // per-lane anchor state of the coefficient evaluation, in shared memory as an[slot * 32] (see eval_coefficients2)
 enum { AN_CR = 0, AN_CI, AN_B1R, AN_B1I, AN_B2R, AN_B2I, AN_PHI, AN_TA, AN_TEND, AN_V0, AN_V1, AN_V2, AN_J, kAN };
+#ifndef CA_RHS2_BF
+#define CA_RHS2_BF 0   // 1: the H couplings of rhs2 written breadth-first (experiment: ptxas re-schedules both forms to the same SASS)
+#endif
 #ifndef CA_ANCHOR2
 #define CA_ANCHOR2 1   // 0: exact exp + sincos on every step (the round-1 behaviour)
 #endif
@@ -237,6 +246,48 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
         for (int i = 0; i < 4; ++i) sm_[i] = xm[L.o_sib + i * kRS];
     }
     double S[8], D[8];
+#if CA_RHS2_BF
+    {   // breadth-first emission: every round touches each accumulator at most once, so consecutive FMAs are independent (the depth-first
+        // coupling-by-coupling order left chains of dependent DFMAs back to back: `wait` was the largest stall of the kernel)
+        const double e2lo = L.h ? -cf.dr2 : 0.0, e2hi = L.h ? -cf.dp2 : 0.0, vrr = L.h ? cf.V : 0.0;
+        const double e1[4] = {0.0, 0.0, -cf.dr1, -cf.dp1};
+        const double k01r = L.h ? cf.br2 : 0.0, k01i = L.h ? -cf.bi2 : 0.0;   // row r <- (Ωb/2)* p
+        const double k10r = L.h ? cf.br2 : 0.0, k10i = L.h ? cf.bi2 : 0.0;    // row p <- Ωb/2 r
+        const double ksr = cf.ar2, ksi = L.h ? -cf.ai2 : cf.ai2;              // row p <- (Ωr/2)* 1 ; row 1 <- Ωr/2 p
+        const double ar1 = cf.ar1, ai1 = cf.ai1, br1 = cf.br1, bi1 = cf.bi1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // real diagonal of H: S += e m, D -= e mt
+            double e = e1[j & 3] + (j < 4 ? e2lo : e2hi);
+            if (j == 2) e += vrr;   // |rr><rr| (get_V, cz_model.jl:12-17,63)
+            S[j] = e * u[j]; D[j] = -e * tp[j];
+        }
+        // round 1: 1 ⊗ H2, first halves (all sixteen accumulators)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { S[a] = fma(k01r, u[4 + a], S[a]); D[a] = fma(k01i, u[4 + a], D[a]); S[4 + a] = fma(ksr, sm_[a], S[4 + a]); D[4 + a] = fma(ksi, sm_[a], D[4 + a]); }
+        // round 2: second halves
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { S[a] = fma(k01i, tp[4 + a], S[a]); D[a] = fma(-k01r, tp[4 + a], D[a]); S[4 + a] = fma(ksi, st[a], S[4 + a]); D[4 + a] = fma(-ksr, st[a], D[4 + a]); }
+        // round 3: rows p <- r of atom 2 (upper half) and H1 ⊗ 1 rows 1, r (first halves; rows 5, 6 wait for round 5)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { S[4 + a] = fma(k10r, u[a], S[4 + a]); D[4 + a] = fma(k10i, u[a], D[4 + a]); }
+        S[1] = fma(ar1, u[3], S[1]); D[1] = fma(ai1, u[3], D[1]); S[2] = fma(br1, u[3], S[2]); D[2] = fma(-bi1, u[3], D[2]);
+        S[3] = fma(ar1, u[1], S[3]); D[3] = fma(-ai1, u[1], D[3]);
+        // round 4
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { S[4 + a] = fma(k10i, tp[a], S[4 + a]); D[4 + a] = fma(-k10r, tp[a], D[4 + a]); }
+        S[1] = fma(ai1, tp[3], S[1]); D[1] = fma(-ar1, tp[3], D[1]); S[2] = fma(-bi1, tp[3], S[2]); D[2] = fma(-br1, tp[3], D[2]);
+        S[3] = fma(-ai1, tp[1], S[3]); D[3] = fma(-ar1, tp[1], D[3]);
+        // round 5
+        S[5] = fma(ar1, u[7], S[5]); D[5] = fma(ai1, u[7], D[5]); S[6] = fma(br1, u[7], S[6]); D[6] = fma(-bi1, u[7], D[6]);
+        S[7] = fma(ar1, u[5], S[7]); D[7] = fma(-ai1, u[5], D[7]); S[3] = fma(br1, u[2], S[3]); D[3] = fma(bi1, u[2], D[3]);
+        // round 6
+        S[5] = fma(ai1, tp[7], S[5]); D[5] = fma(-ar1, tp[7], D[5]); S[6] = fma(-bi1, tp[7], S[6]); D[6] = fma(-br1, tp[7], D[6]);
+        S[7] = fma(-ai1, tp[5], S[7]); D[7] = fma(-ar1, tp[5], D[7]); S[3] = fma(bi1, tp[2], S[3]); D[3] = fma(-br1, tp[2], D[3]);
+        // rounds 7, 8
+        S[7] = fma(br1, u[6], S[7]); D[7] = fma(bi1, u[6], D[7]);
+        S[7] = fma(bi1, tp[6], S[7]); D[7] = fma(-br1, tp[6], D[7]);
+    }
+#else
     {
         const double e2lo = L.h ? -cf.dr2 : 0.0, e2hi = L.h ? -cf.dp2 : 0.0, vrr = L.h ? cf.V : 0.0;
         const double e1[4] = {0.0, 0.0, -cf.dr1, -cf.dp1};
@@ -266,6 +317,7 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
             CA_MMAC(S[4 + a], D[4 + a], k10r, k10i, u[a], tp[a]);
         }
     }
+#endif
     // l-block element (a8, b): H_s L with H_s the Hamiltonian of the surviving atom
     double S8, D8;
     {
@@ -456,6 +508,9 @@ CA_HD void eval_coefficients2(W& w, const DevModel& m, const double* tab, double
 // The kernel is bound by shared-memory wavefronts, so k3 and k5 stay in registers for their later uses (switches kept for
 // experiments); their shared-memory copies (and k6's) exist only for Hairer's dense output and are written only by a step that
 // overshoots the next output time.
+#ifndef CA_DENSE_ALWAYS
+#define CA_DENSE_ALWAYS 0   // 1: k3, k5, k6 are stored for the dense output on every step (no warp-uniform branches around the stores)
+#endif
 #ifndef CA_K3_SMEM
 #define CA_K3_SMEM 0
 #endif
@@ -744,9 +799,21 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                       const double* rho0, double tr0, double* acc, Stats2& st) {
     const double rtol = oo.rtol, atol = oo.atol;
     double* kb = w.kb;   // kb[(buf*kS2 + s)*32], lane offset included
-    double y[kS2], un[kS2], k1[kS2], k7[kS2], unt[kS2], ut[kS2];
+#if CA_Y_SMEM
+#define CA_YL(s) kb[(KB_Y * kS2 + (s)) * 32]
+#else
+    double y[kS2];
+#define CA_YL(s) y[s]
+#endif
+#if CA_K1_SMEM
+#define CA_K1L(s) kb[(KB_1 * kS2 + (s)) * 32]
+#else
+    double k1[kS2];
+#define CA_K1L(s) k1[s]
+#endif
+    double un[kS2], k7[kS2], unt[kS2], ut[kS2];
 #pragma unroll
-    for (int s = 0; s < kS2; ++s) { y[s] = rho0[s]; un[s] = y[s]; }
+    for (int s = 0; s < kS2; ++s) { CA_YL(s) = rho0[s]; un[s] = rho0[s]; }
     const double t0 = tspan[0], tend = tspan[nt - 1];
     double t = t0, h = 0.0, tcommit = t0, dt = oo.dt0;
     StepCtrl2 ctrl;
@@ -762,36 +829,36 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
     };
     // k1 = f(t0, y)
     eval_coefficients2(w, m, tab, t0, 0.0, t0, false, n_exact);
-    rhs2(w, L, m, w.coef[kStages2 - 1], y, k1, unt);
+    rhs2(w, L, m, w.coef[kStages2 - 1], un, k7, unt);
 #pragma unroll
-    for (int s = 0; s < kS2; ++s) { kb[(KB_YT * kS2 + s) * 32] = unt[s]; k7[s] = k1[s]; }
+    for (int s = 0; s < kS2; ++s) { kb[(KB_YT * kS2 + s) * 32] = unt[s]; CA_K1L(s) = k7[s]; }
     n_rhs = 1;
-    double y_ll = tr0 - w.sum(diag_sum(y)), un_ll = y_ll;
+    double y_ll = tr0 - w.sum(diag_sum(un)), un_ll = y_ll;
     if (dt <= 0.0) {  // OrdinaryDiffEq initial step (Hairer), norms over all 625 entries
         double d0 = 0.0, d1 = 0.0, isk2[kS2];
 #pragma unroll
         for (int s = 0; s < kS2; ++s) {
-            const double a2 = 0.5 * (y[s] * y[s] + unt[s] * unt[s]);   // |ρ_AB|²
+            const double a2 = 0.5 * (CA_YL(s) * CA_YL(s) + unt[s] * unt[s]);   // |ρ_AB|²
             const double sk = atol + sqrt(a2) * rtol;
             isk2[s] = 1.0 / (sk * sk);   // the entries (A,B) and (B,A) of the full matrix share |err|² = (e² + e_t²)/2: weight 1 per real
-            d0 += isk2[s] * y[s] * y[s];
-            d1 += isk2[s] * k1[s] * k1[s];
+            d0 += isk2[s] * CA_YL(s) * CA_YL(s);
+            d1 += isk2[s] * CA_K1L(s) * CA_K1L(s);
         }
-        const double f0_ll = -w.sum(diag_sum(k1));
+        const double f0_ll = -w.sum(diag_sum(k7));
         const double sk_ll = atol + fabs(y_ll) * rtol;
         d0 = sqrt((w.sum(d0) + y_ll * y_ll / (sk_ll * sk_ll)) / 625.0);
         d1 = sqrt((w.sum(d1) + f0_ll * f0_ll / (sk_ll * sk_ll)) / 625.0);
         double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         dt0 = fmin(dt0, oo.dtmax);
 #pragma unroll
-        for (int s = 0; s < kS2; ++s) ut[s] = y[s] + dt0 * k1[s];
+        for (int s = 0; s < kS2; ++s) ut[s] = CA_YL(s) + dt0 * CA_K1L(s);
         eval_coefficients2(w, m, tab, t0, 0.0, t0 + dt0, false, n_exact);
         double k2[kS2], dum[kS2];
         rhs2(w, L, m, w.coef[kStages2 - 1], ut, k2, dum);
         n_rhs++;
         double d2 = 0.0;
 #pragma unroll
-        for (int s = 0; s < kS2; ++s) { const double a = k2[s] - k1[s]; d2 += isk2[s] * a * a; }
+        for (int s = 0; s < kS2; ++s) { const double a = k2[s] - CA_K1L(s); d2 += isk2[s] * a * a; }
         const double f1_ll = -w.sum(diag_sum(k2));
         d2 = sqrt((w.sum(d2) + (f1_ll - f0_ll) * (f1_ll - f0_ll) / (sk_ll * sk_ll)) / 625.0) / dt0;
         const double mx = fmax(d1, d2);
@@ -804,7 +871,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
         while (status == 0 && tcommit < T) {
             if (h != 0.0) {  // commit the pending accepted step (FSAL)
 #pragma unroll
-                for (int s = 0; s < kS2; ++s) { y[s] = un[s]; k1[s] = k7[s]; }
+                for (int s = 0; s < kS2; ++s) { CA_YL(s) = un[s]; CA_K1L(s) = k7[s]; }
                 y_ll = un_ll;
                 t = tcommit; h = 0.0;
             }
@@ -815,32 +882,32 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             const double tn = clipped ? tstop : t + hh;
             CA_TICK(w, 3);
             eval_coefficients2(w, m, tab, t, hh, tn, ((iters - 1) & (kAnchorEvery2 - 1)) == 0, n_exact);
-            const bool for_dense = tn > T || CA_K3_SMEM || CA_K5_SMEM;   // this step may be interpolated at T (warp-uniform)
+            const bool for_dense = tn > T || CA_K3_SMEM || CA_K5_SMEM || CA_DENSE_ALWAYS;   // this step may be interpolated at T (warp-uniform)
             CA_TICK(w, 1);
             double k2[kS2], k3[kS2], k5[kS2], kk[kS2], er[kS2], dum[kS2];
 #pragma unroll
-            for (int s = 0; s < kS2; ++s) ut[s] = fma(hh * MC.a21, k1[s], y[s]);
+            for (int s = 0; s < kS2; ++s) ut[s] = fma(hh * MC.a21, CA_K1L(s), CA_YL(s));
             rhs2(w, L, m, w.coef[0], ut, k2, dum);
 #pragma unroll
-            for (int s = 0; s < kS2; ++s) ut[s] = fma(hh, fma(MC.a32, k2[s], MC.a31 * k1[s]), y[s]);
+            for (int s = 0; s < kS2; ++s) ut[s] = fma(hh, fma(MC.a32, k2[s], MC.a31 * CA_K1L(s)), CA_YL(s));
             rhs2(w, L, m, w.coef[1], ut, k3, dum);
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
                 if (for_dense) kb[(KB_3 * kS2 + s) * 32] = k3[s];
-                ut[s] = fma(hh, fma(MC.a43, k3[s], fma(MC.a42, k2[s], MC.a41 * k1[s])), y[s]);
+                ut[s] = fma(hh, fma(MC.a43, k3[s], fma(MC.a42, k2[s], MC.a41 * CA_K1L(s))), CA_YL(s));
             }
             rhs2(w, L, m, w.coef[2], ut, kk, dum);   // k4
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
                 kb[(KB_4 * kS2 + s) * 32] = kk[s];
-                ut[s] = fma(hh, fma(MC.a54, kk[s], fma(MC.a53, CA_K3L(s), fma(MC.a52, k2[s], MC.a51 * k1[s]))), y[s]);
+                ut[s] = fma(hh, fma(MC.a54, kk[s], fma(MC.a53, CA_K3L(s), fma(MC.a52, k2[s], MC.a51 * CA_K1L(s)))), CA_YL(s));
             }
             rhs2(w, L, m, w.coef[3], ut, k5, dum);
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
                 if (for_dense) kb[(KB_5 * kS2 + s) * 32] = k5[s];
                 const double k4 = kb[(KB_4 * kS2 + s) * 32];
-                ut[s] = fma(hh, fma(MC.a65, k5[s], fma(MC.a64, k4, fma(MC.a63, CA_K3L(s), fma(MC.a62, k2[s], MC.a61 * k1[s])))), y[s]);
+                ut[s] = fma(hh, fma(MC.a65, k5[s], fma(MC.a64, k4, fma(MC.a63, CA_K3L(s), fma(MC.a62, k2[s], MC.a61 * CA_K1L(s))))), CA_YL(s));
             }
             rhs2(w, L, m, w.coef[4], ut, kk, dum);   // k6
 #pragma unroll
@@ -848,8 +915,8 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 if (for_dense) kb[(KB_6 * kS2 + s) * 32] = kk[s];
                 const double k4 = kb[(KB_4 * kS2 + s) * 32];
                 const double k3v = CA_K3L(s), k5v = CA_K5L(s);
-                un[s] = fma(hh, fma(MC.b6, kk[s], fma(MC.b5, k5v, fma(MC.b4, k4, fma(MC.b3, k3v, MC.b1 * k1[s])))), y[s]);
-                er[s] = fma(MC.e6, kk[s], fma(MC.e5, k5v, fma(MC.e4, k4, fma(MC.e3, k3v, MC.e1 * k1[s]))));
+                un[s] = fma(hh, fma(MC.b6, kk[s], fma(MC.b5, k5v, fma(MC.b4, k4, fma(MC.b3, k3v, MC.b1 * CA_K1L(s))))), CA_YL(s));
+                er[s] = fma(MC.e6, kk[s], fma(MC.e5, k5v, fma(MC.e4, k4, fma(MC.e3, k3v, MC.e1 * CA_K1L(s)))));
             }
             CA_TICK(w, 3);
             rhs2(w, L, m, w.coef[4], un, k7, unt);   // stage 7 = next step's stage 1 (c6 = c7 = 1)
@@ -863,7 +930,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
                 for (int s = 0; s < kS2; ++s) {
                     const double e = hh * fma(MC.e7, k7[s], er[s]);
                     const double yt = kb[(KB_YT * kS2 + s) * 32];
-                    const double isc = StepCtrl2::rcpn(atol + rtol * StepCtrl2::sqrtn(0.5 * fmax(y[s] * y[s] + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
+                    const double isc = StepCtrl2::rcpn(atol + rtol * StepCtrl2::sqrtn(0.5 * fmax(CA_YL(s) * CA_YL(s) + yt * yt, un[s] * un[s] + unt[s] * unt[s])));
                     const bool eq = L.is_eq(s);
                     sacc += (e * e) * (isc * isc);
                     sdu += eq ? un[s] : 0.0; sde += eq ? e : 0.0;
@@ -906,9 +973,9 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
 #pragma unroll
             for (int s = 0; s < kS2; ++s) {
                 const double k3 = kb[(KB_3 * kS2 + s) * 32], k4 = kb[(KB_4 * kS2 + s) * 32], k5 = kb[(KB_5 * kS2 + s) * 32], k6 = kb[(KB_6 * kS2 + s) * 32];
-                const double r2 = un[s] - y[s], r3 = h * k1[s] - r2, r4 = r2 - h * k7[s] - r3;
-                const double r5 = h * (MC.d1 * k1[s] + MC.d3 * k3 + MC.d4 * k4 + MC.d5 * k5 + MC.d6 * k6 + MC.d7 * k7[s]);
-                o[s] = y[s] + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+                const double r2 = un[s] - CA_YL(s), r3 = h * CA_K1L(s) - r2, r4 = r2 - h * k7[s] - r3;
+                const double r5 = h * (MC.d1 * CA_K1L(s) + MC.d3 * k3 + MC.d4 * k4 + MC.d5 * k5 + MC.d6 * k6 + MC.d7 * k7[s]);
+                o[s] = CA_YL(s) + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
             }
         }
         if (status != 0) {
@@ -917,6 +984,8 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
         }
         accumulate_output2(w, L, m, o, tr0, status, acc + (size_t)j * 2 * kAccSlots * 32);
     }
+#undef CA_YL
+#undef CA_K1L
     st.n_rhs = n_rhs; st.n_acc = n_acc; st.n_rej = n_rej; st.n_exact = n_exact; st.status = status;
 }
 #endif
