@@ -850,9 +850,17 @@ inline int choose_noise_coarse(const double* f, const double* amp_a, const doubl
 }
 
 // nk must hold the recurrence constants of spacing c*dtn (fill_noise_k(f, amp, nf, noise_c(plan)*dtn)); tmp: noise_coarse_count(n_nodes, plan) slots.
-template <int CH, int PW>
-CA_HD void interpolate_noise(int n_nodes, int c, const double* __restrict__ tmp, int tstride, double* __restrict__ out, int stride) {
-    const int row0 = PW == 8 ? (c == 2 ? 0 : (c == 4 ? 1 : (c == 8 ? 4 : (c == 16 ? 11 : 26)))) : (c == 8 ? 0 : (c == 16 ? 7 : 22));
+// weights of the plan: (c - 1) rows (fine offsets r = 1..c-1) of p doubles, row-major, in the constant tables
+CA_HD const double* noise_weight_rows(int plan) {
+    const int c = noise_c(plan);
+    if (noise_p(plan) == 8) return LW.w[c == 2 ? 0 : (c == 4 ? 1 : (c == 8 ? 4 : (c == 16 ? 11 : 26)))];
+    return LW16.w[c == 8 ? 0 : (c == 16 ? 7 : 22)];
+}
+// `wrow`: the plan's weight rows.  The one-atom kernel stages them in shared memory first: read through the constant cache with a
+// run-time row index, the 31 x 16 rows of (c = 32, p = 16) thrashed it (S1 sweep: +7 % kernel time).
+template <int PW>
+CA_HD void interpolate_noise(int n_nodes, int c, const double* __restrict__ wrow, const double* __restrict__ tmp, int tstride, double* __restrict__ out,
+                             int stride) {
     double win[PW];
 #pragma unroll
     for (int i = 0; i < PW; ++i) win[i] = tmp[(size_t)i * tstride];
@@ -866,7 +874,7 @@ CA_HD void interpolate_noise(int n_nodes, int c, const double* __restrict__ tmp,
         for (int r = 1; r < c; ++r) {
             const int j = mc * c + r;
             if (j >= n_nodes) break;
-            const double* wv = PW == 8 ? LW.w[row0 + r - 1] : LW16.w[row0 + r - 1];
+            const double* wv = wrow + (r - 1) * PW;
             double a = wv[0] * win[0], b = wv[1] * win[1];   // two chains
 #pragma unroll
             for (int i = 2; i < PW; i += 2) { a = fma(wv[i], win[i], a); b = fma(wv[i + 1], win[i + 1], b); }
@@ -874,15 +882,18 @@ CA_HD void interpolate_noise(int n_nodes, int c, const double* __restrict__ tmp,
         }
     }
 }
+// wrow: noise_weight_rows(plan), or a copy of those (c - 1) * p doubles in faster memory
 template <int CH>
 CA_HD void gen_noise_trace_c(const NoiseK* __restrict__ nk, int nf, int n_nodes, double dtn, int plan, const double* __restrict__ phases, uint64_t seed,
-                             uint64_t gi, uint32_t stream, double* __restrict__ out, int stride, double* __restrict__ tmp, int tstride) {
+                             uint64_t gi, uint32_t stream, double* __restrict__ out, int stride, double* __restrict__ tmp, int tstride,
+                             const double* __restrict__ wrow = nullptr) {
     const int c = noise_c(plan);
     if (c <= 1) { gen_noise_trace<CH>(nk, nf, n_nodes, dtn, 0.0, phases, seed, gi, stream, out, stride); return; }
     const int n_c = noise_coarse_count(n_nodes, plan), pw = noise_p(plan);
     gen_noise_trace<CH>(nk, nf, n_c, c * dtn, -(pw / 2 - 1.0) * c * dtn, phases, seed, gi, stream, tmp, tstride);
-    if (pw == 8) interpolate_noise<CH, 8>(n_nodes, c, tmp, tstride, out, stride);
-    else interpolate_noise<CH, 16>(n_nodes, c, tmp, tstride, out, stride);
+    if (!wrow) wrow = noise_weight_rows(plan);
+    if (pw == 8) interpolate_noise<8>(n_nodes, c, wrow, tmp, tstride, out, stride);
+    else interpolate_noise<16>(n_nodes, c, wrow, tmp, tstride, out, stride);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
     // Warp-major numbering: the groups of a round go to warp 0 of every CTA first, then warp 1, ...  A PARTIAL last round (strong
     // scaling: 10^6 / 8 GPUs = 3.3 rounds) is then spread over all SMs with fewer resident warps each, which finish sooner than a
     // few fully loaded SMs would.
-    const long long wg = CA_WARP_MAJOR ? (long long)warp * gridDim.x + blockIdx.x : (long long)blockIdx.x * (T / 32) + warp;
+    // Sweeps keep the block-major numbering: consecutive groups belong to the same grid point, so the warps of a CTA, which walk the list in
+    // lock-step, integrate windows of the same length (warp-major mixed pulse times 10x apart in one CTA: S1 -7 %).
+    const long long wg = (CA_WARP_MAJOR && !SWEEP) ? (long long)warp * gridDim.x + blockIdx.x : (long long)blockIdx.x * (T / 32) + warp;
     const long long W = (long long)gridDim.x * (T / 32);
     long long tot_rhs = 0, tot_acc = 0, tot_rej = 0, tot_att = 0, tot_exact = 0;
     long long cyc_noise = 0, cyc_all = -clock64();
@@ -79,12 +81,15 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
     // 85.8 -> 96.8 ms per wave between 3 and 27 waves.
     const long long n_iter = (P.n_groups + W - 1) / W;
     for (long long it = 0; it < n_iter; ++it) {
-        const long long g = wg + it * W;
+        const long long g_raw = wg + it * W;
         __syncthreads();
-        if (g >= P.n_groups) continue;
+        // (a warp without a group in the last round still walks through K1 / K2 with valid = false: both barriers of the round are
+        // executed by every thread of the CTA)
+        const bool active = g_raw < P.n_groups;
+        const long long g = active ? g_raw : 0;
         const int pt = (int)(g / P.groups_per_point);
         const long long il = (g - (long long)pt * P.groups_per_point) * 32 + lane;
-        const bool valid = il < P.n_per_point;
+        const bool valid = active && il < P.n_per_point;
         const long long li = (long long)pt * P.n_per_point + il;  // index into host-supplied arrays
         const uint64_t gi = (uint64_t)(P.traj_offset + li);
         if (SWEEP) {
@@ -121,16 +126,27 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
         if (m.laser_noise && P.nf > 0) {
             cyc_noise -= clock64();
             tab = P.scratch + (size_t)wg * (2 * P.n_nodes_max + P.n_coarse_max) * 32 + lane;
+            // the plan's Lagrange weights ((c - 1) x p <= 496 doubles) staged in the stage-derivative area, which is idle during K2: the
+            // interpolation reads them as uniform shared-memory loads instead of run-time-indexed constant loads
+            double* wsm = sk + warp * 512;
+            const int nwt = (noise_c(m.noise_coarse) - 1) * noise_p(m.noise_coarse);
+            if (nwt > 0) {
+                const double* wr = noise_weight_rows(m.noise_coarse);
+                for (int q = lane; q < nwt; q += 32) wsm[q] = wr[q];
+            }
+            __syncwarp();
             if (valid) {
                 double* tmp = tab + (size_t)2 * P.n_nodes_max * 32;
                 gen_noise_trace_c<kNoiseChunk>(P.nk_red + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn, m.noise_coarse,
-                                               P.phases_red ? P.phases_red + li * P.nf : nullptr, P.seed, gi, 2u, tab, 32, tmp, 32);
+                                               P.phases_red ? P.phases_red + li * P.nf : nullptr, P.seed, gi, 2u, tab, 32, tmp, 32, wsm);
                 gen_noise_trace_c<kNoiseChunk>(P.nk_blue + (size_t)pt * P.nf, P.nf, m.n_nodes, m.dtn, m.noise_coarse,
-                                               P.phases_blue ? P.phases_blue + li * P.nf : nullptr, P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32, tmp, 32);
+                                               P.phases_blue ? P.phases_blue + li * P.nf : nullptr, P.seed, gi, 3u, tab + (size_t)m.n_nodes * 32, 32, tmp, 32, wsm);
             }
             __syncwarp();
             cyc_noise += clock64();
         }
+        __syncthreads();   // every warp's K2 is over before any warp's K3 writes stage derivatives over the staged weights
+        if (!active) continue;
         // ---- K3: integrate
         Lane1<NS, BEAMS> L;
         L.init(m, rt, P.ode, smp, tab, 32, tsp[0], sk + threadIdx.x, T, scb + threadIdx.x, NS <= 15 ? sab + threadIdx.x : nullptr);
