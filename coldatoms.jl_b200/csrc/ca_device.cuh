@@ -40,6 +40,9 @@ constexpr int kMaxModes = 17;  // flat-top orders up to 32
 #ifndef CA_NORM_SHORT
 #define CA_NORM_SHORT 2
 #endif
+#ifndef CA_L1_SPLIT
+#define CA_L1_SPLIT 0   // 1: one-atom steps integrate the spectator rows (NS > 9) in a second phase (see Lane1::attempt)
+#endif
 struct U4 { uint32_t x, y, z, w; };
 
 CA_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -947,6 +950,18 @@ CA_HD void lindblad_rhs(const Coef& c, const Rates& g, const double* u, double* 
     }
 }
 
+// One spectator row alone (the rows do not feed back into the core block): the same arithmetic as the loop body above.
+CA_HD void spectator_rhs(const Coef& c, const Rates& g, const double* v, double* dv) {
+    const double v1r = v[0], v1i = v[1], vrr = v[2], vri = v[3], vpr = v[4], vpi = v[5];
+    double t1r = vpr * c.Ar + vpi * c.Ai, t1i = vpi * c.Ar - vpr * c.Ai;  // vp A*
+    dv[0] = -t1i; dv[1] = t1r;
+    double t2r = -c.dr * vrr + vpr * c.Br - vpi * c.Bi, t2i = -c.dr * vri + vpr * c.Bi + vpi * c.Br;
+    dv[2] = -t2i - g.gr2 * vrr; dv[3] = t2r - g.gr2 * vri;
+    double t3r = v1r * c.Ar - v1i * c.Ai + vrr * c.Br + vri * c.Bi - c.dp * vpr;
+    double t3i = v1r * c.Ai + v1i * c.Ar + vri * c.Br - vrr * c.Bi - c.dp * vpi;
+    dv[4] = -t3i - g.gp2 * vpr; dv[5] = t3r - g.gp2 * vpi;
+}
+
 // Dormand-Prince 5(4) tableau and Hairer's dense-output weights (see oracle).
 namespace dp {
 constexpr double a21 = 1.0 / 5.0, a31 = 3.0 / 40.0, a32 = 9.0 / 40.0, a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0,
@@ -1502,7 +1517,12 @@ struct Lane1 {
         bool clipped = false;
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
         const double tn = clipped ? tstop : t + hh;
-        double us[NS], ko[NS];
+        // NS > 9: the spectator rows (ψ0 with |0> / |l> components) do not feed back into the core block {1, r, p}; they only enter the
+        // error norm.  They are integrated in a SECOND PHASE of the step, row by row, from the stage coefficients that are still in shared
+        // memory: the register footprint of a step is the core's (NS = 9) plus one six-real row instead of all NS components at once
+        // (0.5 KB of spills per thread before).  Every component sees exactly the arithmetic of the one-phase form.
+        constexpr int NC = CA_L1_SPLIT ? 9 : NS;
+        double us[NC], ko[NC];
         stage_coefficients(m, t, hh, tn, refresh);
         Coef cf;
         // population quadratures ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr: the b/e/d-weighted sums of the STAGE VALUES of ρpp and ρrr are
@@ -1513,13 +1533,13 @@ struct Lane1 {
         for (int s = 2; s <= 6; ++s) {   // fully unrolled: tableau weights become constant-bank operands, slots immediates
             // y + Σ_j (h a_sj) k_j with the weights scaled once per stage: s-1 multiplications instead of NS
 #pragma unroll
-            for (int i = 0; i < NS; ++i) us[i] = y[i];
+            for (int i = 0; i < NC; ++i) us[i] = y[i];
 #pragma unroll
             for (int j = 1; j < s; ++j) {
                 const double w = hh * MC.ra[s][j];
                 const double* kp = kptr(j);
 #pragma unroll
-                for (int i = 0; i < NS; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
+                for (int i = 0; i < NC; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
             }
             {
                 const double* o = cb + (size_t)(s - 2) * 6 * kstride;
@@ -1527,7 +1547,7 @@ struct Lane1 {
                 if (BEAMS == 1 || BEAMS == 2) { cf.dp = dpc; cf.dr = drc; }   // free flight: the detunings are constants of the trajectory
                 else { cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride]; }
             }
-            lindblad_rhs<NS>(cf, g, us, ko);
+            lindblad_rhs<NC>(cf, g, us, ko);
             {
                 const double wb = MC.rb[s], we = MC.re[s], wd = MC.rd[s];
                 SBp = fma(wb, us[2], SBp); SBr = fma(wb, us[1], SBr); SEp = fma(we, us[2], SEp); SEr = fma(we, us[1], SEr);
@@ -1535,40 +1555,95 @@ struct Lane1 {
             }
             double* ks = kptr(s);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) ks[i * kstride] = ko[i];
+            for (int i = 0; i < NC; ++i) ks[i * kstride] = ko[i];
         }
         // y_new and the error combination share one pass over k1,k3..k6 (ko still holds k6)
-        double er[NS], un[NS], Pn[2];
+        double er[NC], un[NS], Pn[2];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { un[i] = MC.rb[6] * ko[i]; er[i] = MC.re[6] * ko[i]; }
+        for (int i = 0; i < NC; ++i) { un[i] = MC.rb[6] * ko[i]; er[i] = MC.re[6] * ko[i]; }
 #pragma unroll
         for (int j = 1; j <= 5; ++j) {
             if (j == 2) continue;
             const double wb = MC.rb[j], we = MC.re[j];
             const double* kp = kptr(j);
-            double kv[NS];
+            double kv[NC];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) kv[i] = kp[i * kstride];
+            for (int i = 0; i < NC; ++i) kv[i] = kp[i * kstride];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { un[i] = fma(wb, kv[i], un[i]); er[i] = fma(we, kv[i], er[i]); }
+            for (int i = 0; i < NC; ++i) { un[i] = fma(wb, kv[i], un[i]); er[i] = fma(we, kv[i], er[i]); }
         }
 #pragma unroll
-        for (int i = 0; i < NS; ++i) un[i] = fma(hh, un[i], y[i]);
-        lindblad_rhs<NS>(cf, g, un, ko);  // stage 7 = next step's stage 1; same coefficients as stage 6 (c6 = c7 = 1)
+        for (int i = 0; i < NC; ++i) un[i] = fma(hh, un[i], y[i]);
+        lindblad_rhs<NC>(cf, g, un, ko);  // stage 7 = next step's stage 1; same coefficients as stage 6 (c6 = c7 = 1)
         {
             double* k7p = kptr(7);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { k7p[i * kstride] = ko[i]; er[i] = fma(MC.re[7], ko[i], er[i]); }   // error / h (h² goes into EEst² once)
+            for (int i = 0; i < NC; ++i) { k7p[i * kstride] = ko[i]; er[i] = fma(MC.re[7], ko[i], er[i]); }   // error / h (h² goes into EEst² once)
         }
         SEp = fma(MC.re[7], un[2], SEp); SEr = fma(MC.re[7], un[1], SEr); SDp = fma(MC.rd[7], un[2], SDp); SDr = fma(MC.rd[7], un[1], SDr);
         Pn[0] = fma(hh * g.G0, SBp, P[0]); Pn[1] = fma(hh, fma(g.Gl, SBp, g.Gr * SBr), P[1]);
         n_rhs += 6;
+        // ---- second phase: the spectator rows, one at a time (NS > 9 in the two-phase form only)
+        double s_spec[NS > NC ? (NS - NC) / 2 : 1];   // their error-norm terms, in component order
+        if constexpr (NS > NC) {
+#pragma unroll
+            for (int o = NC; o < NS; o += 6) {
+                double vs[6], kv6[6], vn[6], ve[6];
+#pragma unroll
+                for (int s2 = 2; s2 <= 6; ++s2) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) vs[i] = y[o + i];
+#pragma unroll
+                    for (int j = 1; j < s2; ++j) {
+                        const double w = hh * MC.ra[s2][j];
+                        const double* kp = kptr(j) + (size_t)o * kstride;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) vs[i] = fma(w, kp[i * kstride], vs[i]);
+                    }
+                    {
+                        const double* oc = cb + (size_t)(s2 - 2) * 6 * kstride;
+                        cf.Ar = oc[0]; cf.Ai = oc[kstride]; cf.Br = oc[2 * kstride]; cf.Bi = oc[3 * kstride];
+                        if (BEAMS == 1 || BEAMS == 2) { cf.dp = dpc; cf.dr = drc; }
+                        else { cf.dp = oc[4 * kstride]; cf.dr = oc[5 * kstride]; }
+                    }
+                    spectator_rhs(cf, g, vs, kv6);
+                    double* ks = kptr(s2) + (size_t)o * kstride;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) ks[i * kstride] = kv6[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { vn[i] = MC.rb[6] * kv6[i]; ve[i] = MC.re[6] * kv6[i]; }
+#pragma unroll
+                for (int j = 1; j <= 5; ++j) {
+                    if (j == 2) continue;
+                    const double wb = MC.rb[j], we = MC.re[j];
+                    const double* kp = kptr(j) + (size_t)o * kstride;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { const double kq = kp[i * kstride]; vn[i] = fma(wb, kq, vn[i]); ve[i] = fma(we, kq, ve[i]); }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) vn[i] = fma(hh, vn[i], y[o + i]);
+                spectator_rhs(cf, g, vn, kv6);   // stage 7 (cf still holds the coefficients of t + h)
+                {
+                    double* k7p = kptr(7) + (size_t)o * kstride;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { k7p[i * kstride] = kv6[i]; ve[i] = fma(MC.re[7], kv6[i], ve[i]); un[o + i] = vn[i]; }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i += 2)
+                    s_spec[(o - NC + i) / 2] = nrm_cplx(ve[i], ve[i + 1], y[o + i], y[o + i + 1], vn[i], vn[i + 1], oo.atol, oo.rtol);
+            }
+        }
         if (oo.adaptive) {
             double s = nrm_real(g.G0 * SEp, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(fma(g.Gl, SEp, g.Gr * SEr), P[1], Pn[1], oo.atol, oo.rtol);
 #pragma unroll
             for (int i = 0; i < 3; ++i) s += nrm_real(er[i], y[i], un[i], oo.atol, oo.rtol);
 #pragma unroll
-            for (int i = 3; i < NS; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
+            for (int i = 3; i < NC; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
+            if constexpr (NS > NC) {
+#pragma unroll
+                for (int i = 0; i < (NS - NC) / 2; ++i) s += s_spec[i];
+            }
             double EEst2 = s * (hh * hh * (1.0 / 25.0));
             const bool acc = EEst2 <= 1.0;                 // NaN and overflow fail it and are sorted out on the rare side
             const double prop = hh * ctrl.decide(EEst2, acc);

@@ -32,9 +32,11 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         ts = np.array([0.0, float(os.environ.get("AB_TEND", cz.tspan[-1]))])
         run = lambda: ctx.rydberg2_run(m2, ts, cz.ψ0, n, seed=7, f=cz.f, amp_red=cz.red_laser_phase_amplitudes,   # noqa: E731
                                        amp_blue=cz.blue_laser_phase_amplitudes, ode=pkg._abi.ode_opts(maxiters=10 ** 7))
-    elif os.environ.get("AB_WORKLOAD") == "ns15":   # R1 with a superposition initial state (fidelity callers)
+    elif os.environ.get("AB_WORKLOAD") in ("ns15", "ns21"):   # R1 with a superposition initial state (fidelity callers) / a general one
         model = pkg.model_from_config(cfg)
         psi = (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2)
+        if os.environ.get("AB_WORKLOAD") == "ns21":
+            psi = (pkg.ket_0 + pkg.ket_1 + pkg.ket_l + 0.5j * pkg.ket_r) / np.sqrt(3.25)
         run = lambda: ctx.rydberg1_run(model, cfg.tspan, psi, n, seed=7, f=cfg.f, amp_red=cfg.red_laser_phase_amplitudes,   # noqa: E731
                                        amp_blue=cfg.blue_laser_phase_amplitudes)
     else:
