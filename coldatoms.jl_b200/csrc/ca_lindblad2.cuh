@@ -388,35 +388,55 @@ CA_HD void atom_position2(const DevModel& m, const double* s, double tt, double*
     }
 }
 
-// Gridded(Linear) phase of trace `tr` at time tt (cz_model.jl:45-46) through the lane's cached window of three nodes J, J+1, J+2
-CA_HD double noise_phase2(const DevModel& m, const double* tr, double* an, double tt) {
-    int j = (int)(tt * m.inv_dtn);
-    j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
-    const int J = (int)an[AN_J * 32];
-    double v0 = an[AN_V0 * 32], v1 = an[AN_V1 * 32], v2 = an[AN_V2 * 32];
-    if (j != J) {
+// Per-lane registers of the coefficient evaluation that persist over the steps of a trajectory.
+struct CoefLane2 {
+    double pf;    // prefetched table value of node J + 3 (requested one window advance ago: nothing waits for the load)
+    double cst;   // c_s of this lane's stage (Dormand-Prince nodes 0.2, 0.3, 0.8, 8/9; the fifth stage sits at t + h itself)
+    int J;        // first node of the cached window (J, J+1, J+2 in shared memory: AN_V0..2), -10: empty
+    CA_HD void reset(int lane) { pf = 0.0; J = -10; const int si = lane / 5; cst = si < 4 ? MC.rc[si + 2] : 1.0; }
+};
+
+// Gridded(Linear) phase of trace `tr` at time tt (cz_model.jl:45-46) through the lane's cached window of three nodes J, J+1, J+2.
+// The common cases -- tt still inside [t_J, t_J+1), or one interval further -- touch no global memory and convert no integers: the window
+// start time t_J is cached (AN_J), node J+2 is in the window and node J+3 was prefetched into a register when the window last advanced
+// (the first version converted tt to an index and back on every call, and a lane that advanced stored a freshly loaded value at
+// once: the whole warp waited for that load at the barrier, 1 % of the kernel's samples on one STS).
+CA_HD double noise_phase2(const DevModel& m, const double* tr, double* an, CoefLane2& cl, double tt) {
+    double tJ = an[AN_J * 32], v0 = an[AN_V0 * 32], v1 = an[AN_V1 * 32];
+    const double rel = tt - tJ;
+    if (!(cl.J >= 0 && rel >= 0.0 && rel < m.dtn)) {
         const int last = m.n_nodes - 1;
-        if (j == J + 1) { v0 = v1; v1 = v2; }
-        else { v0 = tr[j]; v1 = tr[j + 1]; }
-        v2 = tr[j + 2 < last ? j + 2 : last];
-        an[AN_V0 * 32] = v0; an[AN_V1 * 32] = v1; an[AN_V2 * 32] = v2; an[AN_J * 32] = (double)j;
+        if (cl.J >= 0 && rel >= m.dtn && rel < 2.0 * m.dtn && cl.J + 1 <= m.n_nodes - 2) {   // the next interval
+            cl.J += 1;
+            v0 = v1; v1 = an[AN_V2 * 32];
+            an[AN_V2 * 32] = cl.pf;
+        } else {   // first use, a jump (rejected step), or the end of the table
+            int j = (int)(tt * m.inv_dtn);
+            j = j < 0 ? 0 : (j > m.n_nodes - 2 ? m.n_nodes - 2 : j);
+            cl.J = j;
+            v0 = tr[j]; v1 = tr[j + 1];
+            an[AN_V2 * 32] = tr[j + 2 < last ? j + 2 : last];
+        }
+        cl.pf = tr[cl.J + 3 < last ? cl.J + 3 : last];
+        tJ = cl.J * m.dtn;
+        an[AN_V0 * 32] = v0; an[AN_V1 * 32] = v1; an[AN_J * 32] = tJ;
     }
-    const double wgt = (tt - j * m.dtn) * m.inv_dtn;
+    const double wgt = (tt - tJ) * m.inv_dtn;
     return v0 + wgt * (v1 - v0);
 }
 
 template <class W>
-CA_HD void eval_coefficients2(W& w, const DevModel& m, const double* tab, double t0, double hh, double tn, bool refresh, int& n_exact) {
+CA_HD void eval_coefficients2(W& w, const DevModel& m, const double* tab, CoefLane2& cl, double t0, double hh, double tn, bool refresh, int& n_exact) {
     const int q = w.lane % 5, si = w.lane / 5;
     if (si < kStages2) {
-        const double tt = si == kStages2 - 1 ? tn : t0 + MC.rc[si + 2] * hh;
+        const double tt = si == kStages2 - 1 ? tn : t0 + cl.cst * hh;
         double* o = reinterpret_cast<double*>(w.coef + si);
         if (q < 4) {
             const int a = q >> 1;
             const double* s = w.smp + 6 * a;
             double* an = w.anc;
             double ph = 0.0;
-            if (tab) ph = noise_phase2(m, tab + (size_t)q * m.n_nodes, an, tt);
+            if (tab) ph = noise_phase2(m, tab + (size_t)q * m.n_nodes, an, cl, tt);
             if (!(q & 1) && tt >= m.tau) ph += m.xi;  // ϕr(t) = t < τ ? 0 : ξ on both red beams (cz_model.jl:136-137,48)
             double re, im;
             const DevBeam& bm = (q & 1) ? m.blue : m.red;
@@ -621,7 +641,9 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
     ctrl.reset();
     long long iters = 0;
     int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0, n_exact = 0;
-    w.anc[AN_TA * 32] = 1e300; w.anc[AN_TEND * 32] = -1e300; w.anc[AN_J * 32] = -10.0;   // no anchor, empty noise window
+    w.anc[AN_TA * 32] = 1e300; w.anc[AN_TEND * 32] = -1e300; w.anc[AN_J * 32] = 0.0;   // no anchor
+    CoefLane2 cl;
+    cl.reset(w.lane);   // empty noise window
     auto diag_sum = [&](const double (&v)[kS2]) {
         double s = 0.0;
 #pragma unroll
@@ -629,7 +651,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
         return s;
     };
     // k1 = f(t0, y)
-    eval_coefficients2(w, m, tab, t0, 0.0, t0, false, n_exact);
+    eval_coefficients2(w, m, tab, cl, t0, 0.0, t0, false, n_exact);
     rhs2(w, L, m, w.coef[kStages2 - 1], un, k7, unt);
 #pragma unroll
     for (int s = 0; s < kS2; ++s) { CA_KB(KB_YT, s) = unt[s]; CA_KB(KB_1, s) = k7[s]; }
@@ -653,7 +675,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
         dt0 = fmin(dt0, oo.dtmax);
 #pragma unroll
         for (int s = 0; s < kS2; ++s) ut[s] = un[s] + dt0 * k7[s];
-        eval_coefficients2(w, m, tab, t0, 0.0, t0 + dt0, false, n_exact);
+        eval_coefficients2(w, m, tab, cl, t0, 0.0, t0 + dt0, false, n_exact);
         double k2[kS2], dum[kS2];
         rhs2(w, L, m, w.coef[kStages2 - 1], ut, k2, dum);
         n_rhs++;
@@ -682,7 +704,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
             const double tn = clipped ? tstop : t + hh;
             CA_TICK(w, 3);
-            eval_coefficients2(w, m, tab, t, hh, tn, ((iters - 1) & (kAnchorEvery2 - 1)) == 0, n_exact);
+            eval_coefficients2(w, m, tab, cl, t, hh, tn, ((iters - 1) & (kAnchorEvery2 - 1)) == 0, n_exact);
             CA_TICK(w, 1);
             double kk[kS2], dum[kS2];
             // stage 2
@@ -820,7 +842,9 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
     ctrl.reset();
     long long iters = 0;
     int status = 0, n_rhs = 0, n_acc = 0, n_rej = 0, n_exact = 0;
-    w.anc[AN_TA * 32] = 1e300; w.anc[AN_TEND * 32] = -1e300; w.anc[AN_J * 32] = -10.0;   // no anchor, empty noise window
+    w.anc[AN_TA * 32] = 1e300; w.anc[AN_TEND * 32] = -1e300; w.anc[AN_J * 32] = 0.0;   // no anchor
+    CoefLane2 cl;
+    cl.reset(w.lane);   // empty noise window
     auto diag_sum = [&](const double (&v)[kS2]) {
         double s = 0.0;
 #pragma unroll
@@ -828,7 +852,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
         return s;
     };
     // k1 = f(t0, y)
-    eval_coefficients2(w, m, tab, t0, 0.0, t0, false, n_exact);
+    eval_coefficients2(w, m, tab, cl, t0, 0.0, t0, false, n_exact);
     rhs2(w, L, m, w.coef[kStages2 - 1], un, k7, unt);
 #pragma unroll
     for (int s = 0; s < kS2; ++s) { kb[(KB_YT * kS2 + s) * 32] = unt[s]; CA_K1L(s) = k7[s]; }
@@ -852,7 +876,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
         dt0 = fmin(dt0, oo.dtmax);
 #pragma unroll
         for (int s = 0; s < kS2; ++s) ut[s] = CA_YL(s) + dt0 * CA_K1L(s);
-        eval_coefficients2(w, m, tab, t0, 0.0, t0 + dt0, false, n_exact);
+        eval_coefficients2(w, m, tab, cl, t0, 0.0, t0 + dt0, false, n_exact);
         double k2[kS2], dum[kS2];
         rhs2(w, L, m, w.coef[kStages2 - 1], ut, k2, dum);
         n_rhs++;
@@ -881,7 +905,7 @@ CA_HD void integrate2(W& w, const Lane2& L, const DevModel& m, const OdeOpts& oo
             if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
             const double tn = clipped ? tstop : t + hh;
             CA_TICK(w, 3);
-            eval_coefficients2(w, m, tab, t, hh, tn, ((iters - 1) & (kAnchorEvery2 - 1)) == 0, n_exact);
+            eval_coefficients2(w, m, tab, cl, t, hh, tn, ((iters - 1) & (kAnchorEvery2 - 1)) == 0, n_exact);
             const bool for_dense = tn > T || CA_K3_SMEM || CA_K5_SMEM || CA_DENSE_ALWAYS;   // this step may be interpolated at T (warp-uniform)
             CA_TICK(w, 1);
             double k2[kS2], k3[kS2], k5[kS2], kk[kS2], er[kS2], dum[kS2];

@@ -10,5 +10,5 @@ mkdir -p $R/variants
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v ${CA_DEFS} \
     -DCA_INST_NS=$NS -DCA_INST_BEAMS=$BM -c -o $R/variants/$N.o $C/ca_l1_inst.cu 2> $R/variants/$N.log
 OBJS=$(ls $C/build/*.o | grep -v l1_${NS}_${BM}.o)
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $R/variants/$N.so $R/variants/$N.o $OBJS -ldl
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -cudart shared -shared -o $R/variants/$N.so $R/variants/$N.o $OBJS -ldl
 grep -A2 "Function properties for _ZN2ca11k_lindblad1ILi${NS}ELb0" $R/variants/$N.log | grep -v Compiling | paste - - - | sed 's/ptxas info    : //g; s/Function properties for //'
