@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 
 #include "../../include/coldatoms_b200.h"
 
@@ -71,6 +72,24 @@ CA_HD double u53(uint32_t a, uint32_t b) {
 }
 CA_HD double u53_open(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+#ifndef CA_TRACE_LL
+#define CA_TRACE_LL 1   // ρ_ll from the conserved trace (Runge-Kutta steps keep linear invariants) instead of a second population quadrature
+#endif
+#ifndef CA_GUARD_INT
+#define CA_GUARD_INT 0   // 1: per-step guard of the anchored Gaussian-pair evaluation as an integer maximum of |Im δ|
+#endif
+#ifndef CA_ANCH_V2
+#define CA_ANCH_V2 1   // Gaussian-pair anchored coefficients as functions of τ with the noise slopes folded in (see eval_anchored)
+#endif
+CA_HD int abs_hi32(double x) {   // high word of |x|: orders non-negative doubles like integers
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x) & 0x7fffffff;
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    return (int)((b >> 32) & 0x7fffffff);
+#endif
 }
 CA_HD void sincos_d(double a, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
@@ -1061,6 +1080,7 @@ struct Lane1 {
     double t, h, dt;                      // committed time, size of the last accepted step (0: none yet), proposed next step size
     StepCtrl ctrl;
     double y[NS];                         // committed state (the end of the last accepted step)
+    double tr0;                           // trace of ρ0
     double P[2], SB[2], SD[2];            // ρ00, ρll quadratures; SB / SD = Σ_j b_j / d_j (ρpp, ρrr)(stage j) of the last accepted step (dense output)
     unsigned iters_left;                  // attempts left before CA_ERR_MAXITERS (maxiters clamped to 2^32-1)
     int n_rhs, n_acc, n_rej, n_exact;     // n_exact: steps whose coefficients took the exact (generic / guard-failed) path
@@ -1313,6 +1333,40 @@ struct Lane1 {
         }
         const double ta = anchor_t0();
         double worst[2] = {0.0, 0.0};   // one accumulator per beam: two short chains instead of one long one
+#if CA_ANCH_V2 || CA_GUARD_INT
+        int worst_hi = 0;
+#endif
+#if CA_ANCH_V2
+        // Gaussian pair, second form: everything is a function of τ = t - t_a alone.  The piecewise-linear noise phase of the two cached
+        // intervals (anchored at their common node, phases_lin) is folded into the imaginary part of the quadratic model once per step,
+        //     Im δ(τ) = τ (b1i + s + τ b2i) + [φ_mid - φ_a + (t_a - t_mid) s],      s = slope of the interval τ falls into,
+        // so a stage costs one FMA for τ, one comparison and two FMAs per beam for Im δ (it was 12 FP64 operations, now 6), and the
+        // per-evaluation guard is the largest |Im δ| compared as an integer (high word of the double) instead of a running sum.
+        if (GP) {
+            const double tau0 = tt0 - ta, thr = tnx - ta, tam = ta - tmid;
+            const double g0[2] = {b1[0][1] + sr0, b1[1][1] + sb0}, g1[2] = {b1[0][1] + sr1, b1[1][1] + sb1};
+            const double pm[2] = {nr1 - pa[0], nb1 - pa[1]};
+            const double c0[2] = {fma(tam, sr0, pm[0]), fma(tam, sb0, pm[1])}, c1[2] = {fma(tam, sr1, pm[0]), fma(tam, sb1, pm[1])};
+#pragma unroll
+            for (int n = 0; n < 5; ++n) {
+                const double tau = n == 4 ? tn - ta : fma(MC.rc[n + 2], hh, tau0);
+                const bool hi = !(tau < thr);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const double dr = tau * fma(tau, b2[q][0], b1[q][0]);
+                    const double di = fma(tau, fma(tau, b2[q][1], hi ? g1[q] : g0[q]), hi ? c1[q] : c0[q]);
+                    const double d2 = di * di;
+                    { const int ah = abs_hi32(di); worst_hi = ah > worst_hi ? ah : worst_hi; }
+                    const double ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
+                    const double cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
+                    const double sn = di * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                    const double er = ed * cs, ei = ed * sn;
+                    cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
+                    cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
+                }
+            }
+        } else
+#endif
 #pragma unroll
         for (int n = 0; n < 5; ++n) {
             const double tt = n == 4 ? tn : fma(MC.rc[n + 2], hh, tt0);
@@ -1331,7 +1385,11 @@ struct Lane1 {
                     di = fma(tau, fma(tau, fma(tau, b3[q][1], b2[q][1]), b1[q][1]), ph[q] - pa[q]);
                 }
                 const double d2 = di * di;
+#if CA_GUARD_INT
+                if (GP) { const int ah = abs_hi32(di); worst_hi = ah > worst_hi ? ah : worst_hi; }   // largest |Im δ| of the step, compared as an integer
+#else
                 if (GP) worst[q] += d2;   // |Re δ| is bounded once per anchor (refresh_anchor); Σ di² >= max di² is the per-step guard
+#endif
                 else worst[q] = fma(400.0 * dr, dr, worst[q] + d2);
                 if (GP) {
                     ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
@@ -1368,6 +1426,9 @@ struct Lane1 {
             for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
         }
         // Gaussian pair: every |di| < 6e-3 (di⁶/720 < 7e-17), |dr| < 3e-4 (dr⁴/24 < 4e-16); else |di| < 0.1 (di¹⁰/3.6e6 < 3e-17), |dr| < 5e-3 (dr⁷/5040 < 2e-20)
+#if CA_ANCH_V2 || CA_GUARD_INT
+        if (GP) return worst_hi < 0x3f789374;   // every |Im δ| < 6e-3 (high word of 6.0e-3 = 0x3f789374bc6a7efa)
+#endif
         return worst[0] + worst[1] < (GP ? 3.6e-5 : 1e-2);
     }
 
@@ -1451,6 +1512,7 @@ struct Lane1 {
             y[19] = m.rho0[5 + 18]; y[20] = -m.rho0[5 + 19];
         }
         P[0] = m.rho0[0]; P[1] = m.rho0[4];
+        tr0 = ((m.rho0[0] + m.rho0[1]) + (m.rho0[2] + m.rho0[3])) + m.rho0[4];
         t = t0; h = 0.0; iters_left = oo.maxiters > 0xffffffffLL ? 0xffffffffu : (unsigned)oo.maxiters; n_rhs = 0; n_acc = 0; n_rej = 0; n_exact = 0; status = 0;
         ctrl.reset();
         double k1[NS];
@@ -1527,8 +1589,11 @@ struct Lane1 {
         Coef cf;
         // population quadratures ρ00' = Γ0 ρpp, ρll' = Γl ρpp + Γr ρrr: the b/e/d-weighted sums of the STAGE VALUES of ρpp and ρrr are
         // accumulated (the rates are applied once per step to the sums, not to every stage)
-        double SBp = MC.rb[1] * y[2], SBr = MC.rb[1] * y[1], SEp = MC.re[1] * y[2], SEr = MC.re[1] * y[1], SDp = MC.rd[1] * y[2],
-               SDr = MC.rd[1] * y[1];
+        // (with CA_TRACE_LL only the ρpp sums are needed: ρll' = Γl ρpp + Γr ρrr follows from the conserved trace)
+        double SBp = MC.rb[1] * y[2], SEp = MC.re[1] * y[2], SDp = MC.rd[1] * y[2];
+#if !CA_TRACE_LL
+        double SBr = MC.rb[1] * y[1], SEr = MC.re[1] * y[1], SDr = MC.rd[1] * y[1];
+#endif
 #pragma unroll
         for (int s = 2; s <= 6; ++s) {   // fully unrolled: tableau weights become constant-bank operands, slots immediates
             // y + Σ_j (h a_sj) k_j with the weights scaled once per stage: s-1 multiplications instead of NS
@@ -1550,8 +1615,10 @@ struct Lane1 {
             lindblad_rhs<NC>(cf, g, us, ko);
             {
                 const double wb = MC.rb[s], we = MC.re[s], wd = MC.rd[s];
-                SBp = fma(wb, us[2], SBp); SBr = fma(wb, us[1], SBr); SEp = fma(we, us[2], SEp); SEr = fma(we, us[1], SEr);
-                SDp = fma(wd, us[2], SDp); SDr = fma(wd, us[1], SDr);
+                SBp = fma(wb, us[2], SBp); SEp = fma(we, us[2], SEp); SDp = fma(wd, us[2], SDp);
+#if !CA_TRACE_LL
+                SBr = fma(wb, us[1], SBr); SEr = fma(we, us[1], SEr); SDr = fma(wd, us[1], SDr);
+#endif
             }
             double* ks = kptr(s);
 #pragma unroll
@@ -1580,8 +1647,14 @@ struct Lane1 {
 #pragma unroll
             for (int i = 0; i < NC; ++i) { k7p[i * kstride] = ko[i]; er[i] = fma(MC.re[7], ko[i], er[i]); }   // error / h (h² goes into EEst² once)
         }
-        SEp = fma(MC.re[7], un[2], SEp); SEr = fma(MC.re[7], un[1], SEr); SDp = fma(MC.rd[7], un[2], SDp); SDr = fma(MC.rd[7], un[1], SDr);
-        Pn[0] = fma(hh * g.G0, SBp, P[0]); Pn[1] = fma(hh, fma(g.Gl, SBp, g.Gr * SBr), P[1]);
+        SEp = fma(MC.re[7], un[2], SEp); SDp = fma(MC.rd[7], un[2], SDp);
+        Pn[0] = fma(hh * g.G0, SBp, P[0]);
+#if CA_TRACE_LL
+        Pn[1] = tr0 - ((Pn[0] + un[0]) + (un[1] + un[2]));
+#else
+        SEr = fma(MC.re[7], un[1], SEr); SDr = fma(MC.rd[7], un[1], SDr);
+        Pn[1] = fma(hh, fma(g.Gl, SBp, g.Gr * SBr), P[1]);
+#endif
         n_rhs += 6;
         // ---- second phase: the spectator rows, one at a time (NS > 9 in the two-phase form only)
         double s_spec[NS > NC ? (NS - NC) / 2 : 1];   // their error-norm terms, in component order
@@ -1635,7 +1708,12 @@ struct Lane1 {
             }
         }
         if (oo.adaptive) {
+#if CA_TRACE_LL
+            const double e00 = g.G0 * SEp;   // the error of ρll is minus the sum of the other populations' errors
+            double s = nrm_real(e00, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real((e00 + er[0]) + (er[1] + er[2]), P[1], Pn[1], oo.atol, oo.rtol);
+#else
             double s = nrm_real(g.G0 * SEp, P[0], Pn[0], oo.atol, oo.rtol) + nrm_real(fma(g.Gl, SEp, g.Gr * SEr), P[1], Pn[1], oo.atol, oo.rtol);
+#endif
 #pragma unroll
             for (int i = 0; i < 3; ++i) s += nrm_real(er[i], y[i], un[i], oo.atol, oo.rtol);
 #pragma unroll
@@ -1665,7 +1743,10 @@ struct Lane1 {
         for (int i = 0; i < NS; ++i) y[i] = un[i];
         P[0] = Pn[0]; P[1] = Pn[1];
         t = tn; h = hh; p ^= 1;
-        SB[0] = SBp; SB[1] = SBr; SD[0] = SDp; SD[1] = SDr;
+        SB[0] = SBp; SD[0] = SDp;
+#if !CA_TRACE_LL
+        SB[1] = SBr; SD[1] = SDr;
+#endif
     }
 
     // State at time T inside the last accepted step [t-h, t] (Hairer contd5), Hermitian-packed ρ into out[0..24].  The increment
@@ -1698,8 +1779,13 @@ struct Lane1 {
                 const double g10 = m.G0 * yo2, g11 = m.Gl * yo2 + m.Gr * yo1, g70 = m.G0 * y[2], g71 = m.Gl * y[2] + m.Gr * y[1];
                 double r2 = h * (m.G0 * SB[0]), r3 = h * g10 - r2, r4 = r2 - h * g70 - r3, r5 = h * (m.G0 * SD[0]);
                 p0 = (P[0] - r2) + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+#if CA_TRACE_LL
+                (void)g11; (void)g71;
+                p1 = tr0 - ((p0 + s[0]) + (s[1] + s[2]));   // the dense output is a linear combination of stage derivatives: it keeps the trace too
+#else
                 r2 = h * (m.Gl * SB[0] + m.Gr * SB[1]); r3 = h * g11 - r2; r4 = r2 - h * g71 - r3; r5 = h * (m.Gl * SD[0] + m.Gr * SD[1]);
                 p1 = (P[1] - r2) + th * (r2 + th1 * (r3 + th * (r4 + th1 * r5)));
+#endif
             }
         }
 #pragma unroll

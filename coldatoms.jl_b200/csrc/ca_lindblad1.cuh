@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
             double mine0 = 0.0, mine1 = 0.0;
 #pragma unroll
             for (int q = 0; q < kNV; ++q) {
+                // NS = 9 (ψ0 inside the core block): only the five populations and the three core coherences of ρ and of ρ·ρ are non-zero
+                // (packed indices 0-4, 13-16, 19-20 of each half), the other 28 sums are skipped at compile time
+                if (NS == 9) { const int r = q % 25; if (!(r < 5 || (r >= 13 && r <= 16) || r == 19 || r == 20)) continue; }
                 double s = warp_sum(ok ? v[q] : 0.0);
                 if (q < 32) { if (lane == q) mine0 = s; }
                 else { if (lane == q - 32) mine1 = s; }
