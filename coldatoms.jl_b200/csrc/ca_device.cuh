@@ -41,9 +41,6 @@ constexpr int kMaxModes = 17;  // flat-top orders up to 32
 #ifndef CA_NORM_SHORT
 #define CA_NORM_SHORT 2
 #endif
-#ifndef CA_L1_SPLIT
-#define CA_L1_SPLIT 0   // 1: one-atom steps integrate the spectator rows (NS > 9) in a second phase (see Lane1::attempt)
-#endif
 struct U4 { uint32_t x, y, z, w; };
 
 CA_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -75,9 +72,6 @@ CA_HD double u53_open(uint32_t a, uint32_t b) {
 }
 #ifndef CA_TRACE_LL
 #define CA_TRACE_LL 1   // ρ_ll from the conserved trace (Runge-Kutta steps keep linear invariants) instead of a second population quadrature
-#endif
-#ifndef CA_GUARD_INT
-#define CA_GUARD_INT 0   // 1: per-step guard of the anchored Gaussian-pair evaluation as an integer maximum of |Im δ|
 #endif
 #ifndef CA_ANCH_V2
 #define CA_ANCH_V2 1   // Gaussian-pair anchored coefficients as functions of τ with the noise slopes folded in (see eval_anchored)
@@ -969,18 +963,6 @@ CA_HD void lindblad_rhs(const Coef& c, const Rates& g, const double* u, double* 
     }
 }
 
-// One spectator row alone (the rows do not feed back into the core block): the same arithmetic as the loop body above.
-CA_HD void spectator_rhs(const Coef& c, const Rates& g, const double* v, double* dv) {
-    const double v1r = v[0], v1i = v[1], vrr = v[2], vri = v[3], vpr = v[4], vpi = v[5];
-    double t1r = vpr * c.Ar + vpi * c.Ai, t1i = vpi * c.Ar - vpr * c.Ai;  // vp A*
-    dv[0] = -t1i; dv[1] = t1r;
-    double t2r = -c.dr * vrr + vpr * c.Br - vpi * c.Bi, t2i = -c.dr * vri + vpr * c.Bi + vpi * c.Br;
-    dv[2] = -t2i - g.gr2 * vrr; dv[3] = t2r - g.gr2 * vri;
-    double t3r = v1r * c.Ar - v1i * c.Ai + vrr * c.Br + vri * c.Bi - c.dp * vpr;
-    double t3i = v1r * c.Ai + v1i * c.Ar + vri * c.Br - vrr * c.Bi - c.dp * vpi;
-    dv[4] = -t3i - g.gp2 * vpr; dv[5] = t3r - g.gp2 * vpi;
-}
-
 // Dormand-Prince 5(4) tableau and Hairer's dense-output weights (see oracle).
 namespace dp {
 constexpr double a21 = 1.0 / 5.0, a31 = 3.0 / 40.0, a32 = 9.0 / 40.0, a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0,
@@ -1333,7 +1315,7 @@ struct Lane1 {
         }
         const double ta = anchor_t0();
         double worst[2] = {0.0, 0.0};   // one accumulator per beam: two short chains instead of one long one
-#if CA_ANCH_V2 || CA_GUARD_INT
+#if CA_ANCH_V2
         int worst_hi = 0;
 #endif
 #if CA_ANCH_V2
@@ -1385,11 +1367,7 @@ struct Lane1 {
                     di = fma(tau, fma(tau, fma(tau, b3[q][1], b2[q][1]), b1[q][1]), ph[q] - pa[q]);
                 }
                 const double d2 = di * di;
-#if CA_GUARD_INT
-                if (GP) { const int ah = abs_hi32(di); worst_hi = ah > worst_hi ? ah : worst_hi; }   // largest |Im δ| of the step, compared as an integer
-#else
                 if (GP) worst[q] += d2;   // |Re δ| is bounded once per anchor (refresh_anchor); Σ di² >= max di² is the per-step guard
-#endif
                 else worst[q] = fma(400.0 * dr, dr, worst[q] + d2);
                 if (GP) {
                     ed = fma(dr, fma(dr, fma(dr, 1.0 / 6.0, 0.5), 1.0), 1.0);
@@ -1426,7 +1404,7 @@ struct Lane1 {
             for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
         }
         // Gaussian pair: every |di| < 6e-3 (di⁶/720 < 7e-17), |dr| < 3e-4 (dr⁴/24 < 4e-16); else |di| < 0.1 (di¹⁰/3.6e6 < 3e-17), |dr| < 5e-3 (dr⁷/5040 < 2e-20)
-#if CA_ANCH_V2 || CA_GUARD_INT
+#if CA_ANCH_V2
         if (GP) return worst_hi < 0x3f789374;   // every |Im δ| < 6e-3 (high word of 6.0e-3 = 0x3f789374bc6a7efa)
 #endif
         return worst[0] + worst[1] < (GP ? 3.6e-5 : 1e-2);
@@ -1579,11 +1557,7 @@ struct Lane1 {
         bool clipped = false;
         if (t + hh >= tstop || (tstop - (t + hh)) < 1e-13 * fabs(tstop)) { hh = tstop - t; clipped = true; }
         const double tn = clipped ? tstop : t + hh;
-        // NS > 9: the spectator rows (ψ0 with |0> / |l> components) do not feed back into the core block {1, r, p}; they only enter the
-        // error norm.  They are integrated in a SECOND PHASE of the step, row by row, from the stage coefficients that are still in shared
-        // memory: the register footprint of a step is the core's (NS = 9) plus one six-real row instead of all NS components at once
-        // (0.5 KB of spills per thread before).  Every component sees exactly the arithmetic of the one-phase form.
-        constexpr int NC = CA_L1_SPLIT ? 9 : NS;
+        constexpr int NC = NS;   // (a two-phase form that integrated the spectator rows after the core block was 2-6 % slower: DESIGN.md §10)
         double us[NC], ko[NC];
         stage_coefficients(m, t, hh, tn, refresh);
         Coef cf;
@@ -1656,57 +1630,6 @@ struct Lane1 {
         Pn[1] = fma(hh, fma(g.Gl, SBp, g.Gr * SBr), P[1]);
 #endif
         n_rhs += 6;
-        // ---- second phase: the spectator rows, one at a time (NS > 9 in the two-phase form only)
-        double s_spec[NS > NC ? (NS - NC) / 2 : 1];   // their error-norm terms, in component order
-        if constexpr (NS > NC) {
-#pragma unroll
-            for (int o = NC; o < NS; o += 6) {
-                double vs[6], kv6[6], vn[6], ve[6];
-#pragma unroll
-                for (int s2 = 2; s2 <= 6; ++s2) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) vs[i] = y[o + i];
-#pragma unroll
-                    for (int j = 1; j < s2; ++j) {
-                        const double w = hh * MC.ra[s2][j];
-                        const double* kp = kptr(j) + (size_t)o * kstride;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) vs[i] = fma(w, kp[i * kstride], vs[i]);
-                    }
-                    {
-                        const double* oc = cb + (size_t)(s2 - 2) * 6 * kstride;
-                        cf.Ar = oc[0]; cf.Ai = oc[kstride]; cf.Br = oc[2 * kstride]; cf.Bi = oc[3 * kstride];
-                        if (BEAMS == 1 || BEAMS == 2) { cf.dp = dpc; cf.dr = drc; }
-                        else { cf.dp = oc[4 * kstride]; cf.dr = oc[5 * kstride]; }
-                    }
-                    spectator_rhs(cf, g, vs, kv6);
-                    double* ks = kptr(s2) + (size_t)o * kstride;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) ks[i * kstride] = kv6[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { vn[i] = MC.rb[6] * kv6[i]; ve[i] = MC.re[6] * kv6[i]; }
-#pragma unroll
-                for (int j = 1; j <= 5; ++j) {
-                    if (j == 2) continue;
-                    const double wb = MC.rb[j], we = MC.re[j];
-                    const double* kp = kptr(j) + (size_t)o * kstride;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) { const double kq = kp[i * kstride]; vn[i] = fma(wb, kq, vn[i]); ve[i] = fma(we, kq, ve[i]); }
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) vn[i] = fma(hh, vn[i], y[o + i]);
-                spectator_rhs(cf, g, vn, kv6);   // stage 7 (cf still holds the coefficients of t + h)
-                {
-                    double* k7p = kptr(7) + (size_t)o * kstride;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) { k7p[i * kstride] = kv6[i]; ve[i] = fma(MC.re[7], kv6[i], ve[i]); un[o + i] = vn[i]; }
-                }
-#pragma unroll
-                for (int i = 0; i < 6; i += 2)
-                    s_spec[(o - NC + i) / 2] = nrm_cplx(ve[i], ve[i + 1], y[o + i], y[o + i + 1], vn[i], vn[i + 1], oo.atol, oo.rtol);
-            }
-        }
         if (oo.adaptive) {
 #if CA_TRACE_LL
             const double e00 = g.G0 * SEp;   // the error of ρll is minus the sum of the other populations' errors
@@ -1718,10 +1641,6 @@ struct Lane1 {
             for (int i = 0; i < 3; ++i) s += nrm_real(er[i], y[i], un[i], oo.atol, oo.rtol);
 #pragma unroll
             for (int i = 3; i < NC; i += 2) s += nrm_cplx(er[i], er[i + 1], y[i], y[i + 1], un[i], un[i + 1], oo.atol, oo.rtol);
-            if constexpr (NS > NC) {
-#pragma unroll
-                for (int i = 0; i < (NS - NC) / 2; ++i) s += s_spec[i];
-            }
             double EEst2 = s * (hh * hh * (1.0 / 25.0));
             const bool acc = EEst2 <= 1.0;                 // NaN and overflow fail it and are sorted out on the rare side
             const double prop = hh * ctrl.decide(EEst2, acc);

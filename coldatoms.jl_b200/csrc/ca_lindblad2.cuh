@@ -52,9 +52,6 @@ constexpr int kStages2 = 5;        // distinct stage times c2,c3,c4,c5,c6(=c7)
 constexpr int kAccSlots = 10;      // accumulator slots per lane: 9 + ρ_ll,ll (lane 0)
 // per-lane anchor state of the coefficient evaluation, in shared memory as an[slot * 32] (see eval_coefficients2)
 enum { AN_CR = 0, AN_CI, AN_B1R, AN_B1I, AN_B2R, AN_B2I, AN_PHI, AN_TA, AN_TEND, AN_V0, AN_V1, AN_V2, AN_J, kAN };
-#ifndef CA_RHS2_BF
-#define CA_RHS2_BF 0   // 1: the H couplings of rhs2 written breadth-first (experiment: ptxas re-schedules both forms to the same SASS)
-#endif
 #ifndef CA_ANCHOR2
 #define CA_ANCHOR2 1   // 0: exact exp + sincos on every step (the round-1 behaviour)
 #endif
@@ -246,48 +243,6 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
         for (int i = 0; i < 4; ++i) sm_[i] = xm[L.o_sib + i * kRS];
     }
     double S[8], D[8];
-#if CA_RHS2_BF
-    {   // breadth-first emission: every round touches each accumulator at most once, so consecutive FMAs are independent (the depth-first
-        // coupling-by-coupling order left chains of dependent DFMAs back to back: `wait` was the largest stall of the kernel)
-        const double e2lo = L.h ? -cf.dr2 : 0.0, e2hi = L.h ? -cf.dp2 : 0.0, vrr = L.h ? cf.V : 0.0;
-        const double e1[4] = {0.0, 0.0, -cf.dr1, -cf.dp1};
-        const double k01r = L.h ? cf.br2 : 0.0, k01i = L.h ? -cf.bi2 : 0.0;   // row r <- (Ωb/2)* p
-        const double k10r = L.h ? cf.br2 : 0.0, k10i = L.h ? cf.bi2 : 0.0;    // row p <- Ωb/2 r
-        const double ksr = cf.ar2, ksi = L.h ? -cf.ai2 : cf.ai2;              // row p <- (Ωr/2)* 1 ; row 1 <- Ωr/2 p
-        const double ar1 = cf.ar1, ai1 = cf.ai1, br1 = cf.br1, bi1 = cf.bi1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {   // real diagonal of H: S += e m, D -= e mt
-            double e = e1[j & 3] + (j < 4 ? e2lo : e2hi);
-            if (j == 2) e += vrr;   // |rr><rr| (get_V, cz_model.jl:12-17,63)
-            S[j] = e * u[j]; D[j] = -e * tp[j];
-        }
-        // round 1: 1 ⊗ H2, first halves (all sixteen accumulators)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { S[a] = fma(k01r, u[4 + a], S[a]); D[a] = fma(k01i, u[4 + a], D[a]); S[4 + a] = fma(ksr, sm_[a], S[4 + a]); D[4 + a] = fma(ksi, sm_[a], D[4 + a]); }
-        // round 2: second halves
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { S[a] = fma(k01i, tp[4 + a], S[a]); D[a] = fma(-k01r, tp[4 + a], D[a]); S[4 + a] = fma(ksi, st[a], S[4 + a]); D[4 + a] = fma(-ksr, st[a], D[4 + a]); }
-        // round 3: rows p <- r of atom 2 (upper half) and H1 ⊗ 1 rows 1, r (first halves; rows 5, 6 wait for round 5)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { S[4 + a] = fma(k10r, u[a], S[4 + a]); D[4 + a] = fma(k10i, u[a], D[4 + a]); }
-        S[1] = fma(ar1, u[3], S[1]); D[1] = fma(ai1, u[3], D[1]); S[2] = fma(br1, u[3], S[2]); D[2] = fma(-bi1, u[3], D[2]);
-        S[3] = fma(ar1, u[1], S[3]); D[3] = fma(-ai1, u[1], D[3]);
-        // round 4
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { S[4 + a] = fma(k10i, tp[a], S[4 + a]); D[4 + a] = fma(-k10r, tp[a], D[4 + a]); }
-        S[1] = fma(ai1, tp[3], S[1]); D[1] = fma(-ar1, tp[3], D[1]); S[2] = fma(-bi1, tp[3], S[2]); D[2] = fma(-br1, tp[3], D[2]);
-        S[3] = fma(-ai1, tp[1], S[3]); D[3] = fma(-ar1, tp[1], D[3]);
-        // round 5
-        S[5] = fma(ar1, u[7], S[5]); D[5] = fma(ai1, u[7], D[5]); S[6] = fma(br1, u[7], S[6]); D[6] = fma(-bi1, u[7], D[6]);
-        S[7] = fma(ar1, u[5], S[7]); D[7] = fma(-ai1, u[5], D[7]); S[3] = fma(br1, u[2], S[3]); D[3] = fma(bi1, u[2], D[3]);
-        // round 6
-        S[5] = fma(ai1, tp[7], S[5]); D[5] = fma(-ar1, tp[7], D[5]); S[6] = fma(-bi1, tp[7], S[6]); D[6] = fma(-br1, tp[7], D[6]);
-        S[7] = fma(-ai1, tp[5], S[7]); D[7] = fma(-ar1, tp[5], D[7]); S[3] = fma(bi1, tp[2], S[3]); D[3] = fma(-br1, tp[2], D[3]);
-        // rounds 7, 8
-        S[7] = fma(br1, u[6], S[7]); D[7] = fma(bi1, u[6], D[7]);
-        S[7] = fma(bi1, tp[6], S[7]); D[7] = fma(-br1, tp[6], D[7]);
-    }
-#else
     {
         const double e2lo = L.h ? -cf.dr2 : 0.0, e2hi = L.h ? -cf.dp2 : 0.0, vrr = L.h ? cf.V : 0.0;
         const double e1[4] = {0.0, 0.0, -cf.dr1, -cf.dp1};
@@ -317,7 +272,6 @@ CA_HD void rhs2(W& w, const Lane2& L, const DevModel& m, const Coef2& cf, const 
             CA_MMAC(S[4 + a], D[4 + a], k10r, k10i, u[a], tp[a]);
         }
     }
-#endif
     // l-block element (a8, b): H_s L with H_s the Hamiltonian of the surviving atom
     double S8, D8;
     {
