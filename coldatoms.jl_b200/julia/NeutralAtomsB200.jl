@@ -71,21 +71,41 @@ const COMPAT_DEFAULT = Int32(1)
 
 const LIB = Ref{Ptr{Cvoid}}(C_NULL)
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+const MULTI = Ref{Ptr{Cvoid}}(C_NULL)   # ca_multi* when several GPUs are driven from this process (init!(...; devices = ...))
 const SEED = Ref{UInt64}(0xC01DA705)
 
 sym(name) = Libdl.dlsym(LIB[], name)
 lasterr() = unsafe_string(ccall(sym(:ca_last_error), Cstring, ()))
 check(rc) = rc == 0 ? nothing : error("coldatoms_b200 error $rc: $(lasterr())")
 
-"Load the library and create the context on `device`. Throws if there is no sm_100 GPU (no fallback)."
-function init!(path::AbstractString; device::Integer = 0)
+"""
+Load the library and create the context on `device`. Throws if there is no sm_100 GPU (no fallback).
+`devices = :all` (every visible GPU) or a list of device ordinals additionally creates the multi-GPU handle (`ca_init_multi`: one context
+per GPU in THIS process and an NCCL clique): `simulation`, `simulation_czlp`, `release_recapture` and the batched `get_rydberg_infidelity`
+then shard their trajectories (grid points) over those GPUs inside the one `ccall` they make, with one `ncclAllReduce` of the sums.
+"""
+function init!(path::AbstractString; device::Integer = 0, devices = nothing)
     LIB[] = Libdl.dlopen(path)
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall(sym(:ca_init), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx))
     CTX[] = ctx[]
+    if devices !== nothing
+        devs = devices === :all ? Cint[] : Cint.(collect(devices))
+        m = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve devs check(ccall(sym(:ca_init_multi), Cint, (Ptr{Cint}, Int32, Ref{Ptr{Cvoid}}),
+                                      isempty(devs) ? Ptr{Cint}(C_NULL) : pointer(devs), length(devs), m))
+        MULTI[] = m[]
+    end
     return nothing
 end
-finalize!() = (CTX[] != C_NULL && ccall(sym(:ca_finalize), Cint, (Ptr{Cvoid},), CTX[]); CTX[] = C_NULL; nothing)
+function finalize!()
+    MULTI[] != C_NULL && ccall(sym(:ca_finalize_multi), Cint, (Ptr{Cvoid},), MULTI[])
+    CTX[] != C_NULL && ccall(sym(:ca_finalize), Cint, (Ptr{Cvoid},), CTX[])
+    MULTI[] = C_NULL; CTX[] = C_NULL
+    return nothing
+end
+# entry point and handle of an ensemble call: the *_multi functions take the argument list of their single-GPU counterparts
+entry(single::Symbol, multi::Symbol) = MULTI[] == C_NULL ? (sym(single), CTX[]) : (sym(multi), MULTI[])
 seed!(s::Integer) = (SEED[] = UInt64(s); nothing)
 function next_seed()   # successive calls draw independent ensembles, like Julia's advancing global RNG
     SEED[] += 0x9E3779B97F4A7C15
@@ -146,11 +166,12 @@ function run1(m::CaModel, tspan, ψ0data, n; samples = nothing, seed = next_seed
     st = CaStats()
     smp = samples === nothing ? null() : pointer(samples)
     nf = f === nothing ? 0 : length(f)
+    fp, h = entry(:ca_rydberg1_run, :ca_rydberg1_run_multi)
     GC.@preserve samples f ar ab begin
-        check(ccall(sym(:ca_rydberg1_run), Cint,
+        check(ccall(fp, Cint,
             (Ptr{Cvoid}, Ref{CaModel}, Ptr{Float64}, Int32, Ptr{ComplexF64}, Int64, Int64, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
              Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
-            CTX[], m, Float64.(tspan), nt, ComplexF64.(ψ0data), n, 0, n, seed, smp, null(), null(),
+            h, m, Float64.(tspan), nt, ComplexF64.(ψ0data), n, 0, n, seed, smp, null(), null(),
             f === nothing ? null() : pointer(f), ar === nothing ? null() : pointer(ar), ab === nothing ? null() : pointer(ab),
             nf, o, 0, ρ, ρ2, st))
     end
@@ -224,11 +245,12 @@ function simulation_czlp(cfg::NeutralAtoms.CZLPConfig; ode_kwargs...)
     st = CaStats()
     noise = cfg.laser_noise
     f, ar, ab = cfg.f, cfg.red_laser_phase_amplitudes, cfg.blue_laser_phase_amplitudes
+    fp, h = entry(:ca_rydberg2_run, :ca_rydberg2_run_multi)
     GC.@preserve f ar ab begin
-        check(ccall(sym(:ca_rydberg2_run), Cint,
+        check(ccall(fp, Cint,
             (Ptr{Cvoid}, Ref{CaModel}, Ptr{Float64}, Int32, Ptr{ComplexF64}, Int64, Int64, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
              Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
-            CTX[], model(cfg; two_atom = true), Float64.(cfg.tspan), nt, ComplexF64.(cfg.ψ0.data), cfg.n_samples, 0, cfg.n_samples,
+            h, model(cfg; two_atom = true), Float64.(cfg.tspan), nt, ComplexF64.(cfg.ψ0.data), cfg.n_samples, 0, cfg.n_samples,
             next_seed(), null(), null(), Ptr{Ptr{Float64}}(C_NULL), noise ? pointer(f) : null(), noise ? pointer(ar) : null(),
             noise ? pointer(ab) : null(), noise ? length(f) : 0, ode(; ode_kwargs...), 0, ρ, ρ2, st))
     end
@@ -247,11 +269,21 @@ function release_recapture(tspan, trap_params, atom_params, N; freq = 10, skip =
         samples, acc = samples_generate(trap_params, atom_params, N; freq = freq, skip = skip, harmonic = false)
         smp = reduce(hcat, samples)   # 6 x N column-major = N x 6 row-major
     end
-    GC.@preserve smp check(ccall(sym(:ca_release_recapture), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Int32,
-         Ptr{Float64}, Ptr{UInt8}, Ref{CaStats}),
-        CTX[], Float64.(trap_params), Float64.(atom_params), Float64.(tspan), length(tspan), N, 0, N, eps, next_seed(), smp, 0,
-        probs, Ptr{UInt8}(C_NULL), st))
+    GC.@preserve smp begin
+        if MULTI[] == C_NULL
+            check(ccall(sym(:ca_release_recapture), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Int32,
+                 Ptr{Float64}, Ptr{UInt8}, Ref{CaStats}),
+                CTX[], Float64.(trap_params), Float64.(atom_params), Float64.(tspan), length(tspan), N, 0, N, eps, next_seed(), smp, 0,
+                probs, Ptr{UInt8}(C_NULL), st))
+        else   # (the multi-GPU entry has no per-atom indicator output)
+            check(ccall(sym(:ca_release_recapture_multi), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int64, Int64, Int64, Float64, UInt64, Ptr{Float64}, Int32,
+                 Ptr{Float64}, Ref{CaStats}),
+                MULTI[], Float64.(trap_params), Float64.(atom_params), Float64.(tspan), length(tspan), N, 0, N, eps, next_seed(), smp, 0,
+                probs, st))
+        end
+    end
     return probs, acc
 end
 
@@ -302,10 +334,11 @@ function get_rydberg_infidelity(cfg::NeutralAtoms.RydbergConfig;
         tends = Float64[points[i][2].tspan[end] for i in idx]
         ρ = zeros(ComplexF64, 25 * length(idx)); ρ2 = similar(ρ)
         st = CaStats()
-        GC.@preserve models psis tends f ar ab check(ccall(sym(:ca_rydberg1_sweep), Cint,
+        fp, h = entry(:ca_rydberg1_sweep, :ca_rydberg1_sweep_multi)
+        GC.@preserve models psis tends f ar ab check(ccall(fp, Cint,
             (Ptr{Cvoid}, Ptr{CaModel}, Ptr{ComplexF64}, Ptr{Float64}, Int32, Int64, Int64, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
              Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
-            CTX[], models, psis, tends, length(idx), n, offset, 0, seed, f, ar, ab, length(f), ode(; ode_kwargs...), 0, ρ, ρ2, st))
+            h, models, psis, tends, length(idx), n, offset, 0, seed, f, ar, ab, length(f), ode(; ode_kwargs...), 0, ρ, ρ2, st))
         for (k, i) in enumerate(idx)
             ρend[i] = reshape(ρ[(k-1)*25+1:k*25], 5, 5)
         end
