@@ -1044,6 +1044,8 @@ template <int NS, int BEAMS = 0>   // BEAMS: 0 decide at run time (all coefficie
                                      // 2 other beam kinds (free flight), 3 Gaussian pair + trap oscillation
 struct Lane1 {
     static constexpr int kEvery = BEAMS == 2 ? kAnchorEveryGeneric : kAnchorEvery;   // attempts between re-anchorings of this variant
+    static constexpr int kAB = BEAMS == 1 ? 7 : 9;   // anchor slots per beam: the free-flight Gaussian pair has no cubic term (slots 7, 8) and no trap rotation
+    static constexpr int kCB = (BEAMS == 1 || BEAMS == 2) ? 4 : 6;   // doubles per stage in cb: Ar, Ai, Br, Bi (+ dp, dr unless the free-flight variants read them from registers)
     // trajectory
     double x0, y0, z0, vx, vy, vz, vzq;  // vzq: velocity used for "Vz" (vy when the B1 quirk is on)
     double dpc, drc;                      // constant detunings (free motion) incl. Δ0, δ0
@@ -1056,7 +1058,7 @@ struct Lane1 {
     // integrator
     double* kb;                           // k storage: kb[(slot*NS + i)*kstride]
     double* cb;                           // stage coefficients cb[(n*6 + c)*kstride], n = stage 2..6, c = Ar,Ai,Br,Bi,dp,dr
-    double* ab;                           // per beam q: ab[(q*9 + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a) | b3 re,im; ab[18] = t_a, ab[19] = end of validity
+    double* ab;                           // per beam q: ab[(q*kAB + i)*kstride], i = c(t_a) re,im | b1 re,im | b2 re,im | φ(t_a) | b3 re,im (kAB = 9) or without b3 (kAB = 7)
     int kstride, p;                       // p: slot of k1 (0/1); k2 and k7 live in slot 1-p; k3..k6 in slots 2..5
     bool win_ok;                          // the anchor's quadratic model of ln B passed its guard
     double t, h, dt;                      // committed time, size of the last accepted step (0: none yet), proposed next step size
@@ -1212,7 +1214,7 @@ struct Lane1 {
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
             const DevBeam& bm = q == 0 ? m.red : m.blue;
-            double* a = ab + (size_t)q * 9 * kstride;
+            double* a = ab + (size_t)q * kAB * kstride;
             double c0r = 0.0, c0i = 0.0, inv0 = 0.0, l[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
@@ -1261,7 +1263,7 @@ struct Lane1 {
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
             const DevBeam& bm = q == 0 ? m.red : m.blue;
-            double* a = ab + (size_t)q * 9 * kstride;
+            double* a = ab + (size_t)q * kAB * kstride;
             // rolled on purpose: this code runs once per 16 steps and must not evict the step loop from the instruction cache
             double L0r = 0.0, L0i = 0.0, L1r = 0.0, L1i = 0.0, L2r = 0.0, L2i = 0.0;
 #pragma unroll 1
@@ -1307,7 +1309,7 @@ struct Lane1 {
         double ca[2][2], b1[2][2], b2[2][2], b3[2][2], pa[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const double* a = ab + (size_t)q * 9 * kstride;
+            const double* a = ab + (size_t)q * kAB * kstride;
             ca[q][0] = a[0]; ca[q][1] = a[kstride];
             b1[q][0] = a[2 * kstride]; b1[q][1] = a[3 * kstride]; b2[q][0] = a[4 * kstride]; b2[q][1] = a[5 * kstride];
             pa[q] = a[6 * kstride];
@@ -1343,8 +1345,8 @@ struct Lane1 {
                     const double cs = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);
                     const double sn = di * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
                     const double er = ed * cs, ei = ed * sn;
-                    cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
-                    cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
+                    cb[(n * kCB + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
+                    cb[(n * kCB + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
                 }
             }
         } else
@@ -1379,8 +1381,8 @@ struct Lane1 {
                     sn = di * fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 362880.0, -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
                 }
                 const double er = ed * cs, ei = ed * sn;
-                cb[(n * 6 + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
-                cb[(n * 6 + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
+                cb[(n * kCB + 2 * q) * kstride] = ca[q][0] * er - ca[q][1] * ei;
+                cb[(n * kCB + 2 * q + 1) * kstride] = ca[q][0] * ei + ca[q][1] * er;
             }
         }
         if (GP && (BEAMS == 0 || BEAMS == 3) && !m.free_motion) {
@@ -1397,11 +1399,11 @@ struct Lane1 {
                 const double Vx = vx * cr - x0 * m.wr * sr, Vz = vzq * cz - z0 * m.wz * sz;
                 double Dd = m.aDx * Vx + m.aDz * Vz, dd = m.bDx * Vx + m.bDz * Vz;
                 if (m.doppler_z_legacy) { const double Vzt = vz * cz - z0 * m.wz * sz; Dd = m.aDz * Vzt; dd = m.bDz * Vzt; }
-                cb[(n * 6 + 4) * kstride] = m.Delta0 - m.dsign * Dd; cb[(n * 6 + 5) * kstride] = m.delta0 - m.dsign * dd;
+                cb[(n * kCB + 4) * kstride] = m.Delta0 - m.dsign * Dd; cb[(n * kCB + 5) * kstride] = m.delta0 - m.dsign * dd;
             }
         } else if (!(BEAMS == 1 || BEAMS == 2)) {   // (the free-flight variants read dpc / drc directly)
 #pragma unroll
-            for (int n = 0; n < 5; ++n) { cb[(n * 6 + 4) * kstride] = dpc; cb[(n * 6 + 5) * kstride] = drc; }
+            for (int n = 0; n < 5; ++n) { cb[(n * kCB + 4) * kstride] = dpc; cb[(n * kCB + 5) * kstride] = drc; }
         }
         // Gaussian pair: every |di| < 6e-3 (di⁶/720 < 7e-17), |dr| < 3e-4 (dr⁴/24 < 4e-16); else |di| < 0.1 (di¹⁰/3.6e6 < 3e-17), |dr| < 5e-3 (dr⁷/5040 < 2e-20)
 #if CA_ANCH_V2
@@ -1440,8 +1442,9 @@ struct Lane1 {
             for (int n = 0; n < 5; ++n) {
                 Coef c;
                 coefficients(m, stage_time(n, tt0, hh, tn), c);
-                double* o = cb + (size_t)n * 6 * kstride;
-                o[0] = c.Ar; o[kstride] = c.Ai; o[2 * kstride] = c.Br; o[3 * kstride] = c.Bi; o[4 * kstride] = c.dp; o[5 * kstride] = c.dr;
+                double* o = cb + (size_t)n * kCB * kstride;
+                o[0] = c.Ar; o[kstride] = c.Ai; o[2 * kstride] = c.Br; o[3 * kstride] = c.Bi;
+                if (kCB == 6) { o[4 * kstride] = c.dp; o[5 * kstride] = c.dr; }
             }
         }
     }
@@ -1581,7 +1584,7 @@ struct Lane1 {
                 for (int i = 0; i < NC; ++i) us[i] = fma(w, kp[i * kstride], us[i]);
             }
             {
-                const double* o = cb + (size_t)(s - 2) * 6 * kstride;
+                const double* o = cb + (size_t)(s - 2) * kCB * kstride;
                 cf.Ar = o[0]; cf.Ai = o[kstride]; cf.Br = o[2 * kstride]; cf.Bi = o[3 * kstride];
                 if (BEAMS == 1 || BEAMS == 2) { cf.dp = dpc; cf.dr = drc; }   // free flight: the detunings are constants of the trajectory
                 else { cf.dp = o[4 * kstride]; cf.dr = o[5 * kstride]; }

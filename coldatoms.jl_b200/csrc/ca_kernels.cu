@@ -373,10 +373,22 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
         if (phases_red) { if ((rc = upload(c, c->in_ph[0], phases_red, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_red = (const double*)c->in_ph[0].p; }
         if (phases_blue) { if ((rc = upload(c, c->in_ph[1], phases_blue, sizeof(double) * (size_t)nf * n_all))) return rc; P.phases_blue = (const double*)c->in_ph[1].p; }
     }
-    // grid: persistent warps, 3 (NS=9) / 2 / 1 CTAs of 128 threads per SM
+    // variant: NS from the rows of ψ0; the anchored-coefficient code is compiled per beam class (all points free-flight Gaussian pairs = 1 /
+    // free flight with other beams = 2 / Gaussian pairs oscillating in the trap = 3 / anything else or a mixed sweep = 0)
     const int ns_sel = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
-    const int wpb = (ns_sel == 9 ? threads_for<9>() : (ns_sel == 15 ? threads_for<15>() : threads_for<21>())) / 32;
-    const int bps = ns_sel == 9 ? blocks_per_sm<9>() : (ns_sel == 15 ? blocks_per_sm<15>() : blocks_per_sm<21>());
+    int n_gp = 0, n_free = 0;
+    for (int p = 0; p < n_points; ++p) {
+        n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
+        n_free += dm[p].free_motion != 0;
+    }
+    int beams_sel = 0;
+    if (n_gp == n_points && n_free == n_points) beams_sel = 1;
+    else if (ns_sel == 9 && n_gp == 0 && n_free == n_points) beams_sel = 2;
+    else if (ns_sel == 9 && n_gp == n_points && n_free == 0) beams_sel = 3;
+    if (ns_sel == 21) beams_sel = 0;
+    // grid: persistent warps, one CTA per SM
+    const int wpb = threads_for_rt(ns_sel, beams_sel) / 32;
+    const int bps = 1;
     long long blocks_needed = (P.n_groups + wpb - 1) / wpb;
     int grid = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)bps * c->sm_count));
     if (any_noise) {
@@ -394,22 +406,12 @@ static int run_r1(ca_ctx* c, const ca_model* models, const double* psi0s, const 
     int launches = 0;
     CA_CUDA(cudaEventRecord(c->ev[1], c->stream));
     if (n_all > 0) {
-        const int ns = rows == 0 ? 9 : (rows == 3 ? 21 : 15);
-        // the anchored-coefficient code of the NS = 9 kernel is compiled per beam class (all points Gaussian pairs / none / mixed sweep)
-        int n_gp = 0, n_free = 0;
-        for (int p = 0; p < n_points; ++p) {
-            n_gp += dm[p].red.kind == CA_BEAM_GAUSS && dm[p].blue.kind == CA_BEAM_GAUSS;
-            n_free += dm[p].free_motion != 0;
-        }
         cudaError_t le;
-        if (ns == 9) {
-            if (n_gp == n_points && n_free == n_points) le = launch_l1_9_1(sweep, c->stream, P, grid);
-            else if (n_gp == 0 && n_free == n_points) le = launch_l1_9_2(sweep, c->stream, P, grid);
-            else if (n_gp == n_points && n_free == 0) le = launch_l1_9_3(sweep, c->stream, P, grid);
-            else le = launch_l1_9_0(sweep, c->stream, P, grid);
-        } else if (ns == 15) {
-            if (n_gp == n_points && n_free == n_points) le = launch_l1_15_1(sweep, c->stream, P, grid);
-            else le = launch_l1_15_0(sweep, c->stream, P, grid);
+        if (ns_sel == 9) {
+            le = beams_sel == 1 ? launch_l1_9_1(sweep, c->stream, P, grid) : (beams_sel == 2 ? launch_l1_9_2(sweep, c->stream, P, grid)
+               : (beams_sel == 3 ? launch_l1_9_3(sweep, c->stream, P, grid) : launch_l1_9_0(sweep, c->stream, P, grid)));
+        } else if (ns_sel == 15) {
+            le = beams_sel == 1 ? launch_l1_15_1(sweep, c->stream, P, grid) : launch_l1_15_0(sweep, c->stream, P, grid);
         } else le = launch_l1_21_0(sweep, c->stream, P, grid);
         if (le != cudaSuccess) { set_error(std::string("k_lindblad1 launch: ") + cudaGetErrorString(le)); return CA_ERR_CUDA; }
         ++launches;

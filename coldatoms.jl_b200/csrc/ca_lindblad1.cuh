@@ -22,16 +22,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ----------------------------------------------------------------------------------------------------
 // K1+K2+K3: fused one-atom ensemble kernel
 // ----------------------------------------------------------------------------------------------------
-// NS = 15 (a |0> or |l> component in ψ0: four of the six fidelity basis states) spills ~0.5 KB per thread at 255 registers.  With two CTAs
-// of 96 threads the shared-memory carve-out (215 KB) left no L1 for those spills: they went to L2 and `long_scoreboard` on LDL was the
-// largest stall (profiles/r2/k_lindblad1_ns15_ncu_summary.txt).  One CTA of 128 threads (143 KB) leaves ~100 KB of L1: 404k -> 452k traj/s
-// although a third of the warps are gone (160 threads: 393k; y_new / error in two passes to cut the live vectors: 378k).
+// Threads per CTA (one CTA per SM).  NS = 9: 256 (the register file's limit at 255 registers per thread).  NS = 15 (a |0> or |l> component in
+// ψ0: four of the six fidelity basis states) keeps 6 x 15 stage derivatives per thread in shared memory, so shared memory sets the limit: the
+// free-flight Gaussian-pair variant (124 doubles per thread with the compact coefficient / anchor areas) runs 224 threads = 7 warps (222 KB);
+// its ~0.4 KB of register spills per thread then live in L2, and still 7 warps beat 4 warps with the spills in L1 (489k -> 536k traj/s;
+// 6 warps: 510k; profiles/r2/ab_ns15_threads.txt).  The generic NS = 15 variant (140 doubles) and NS = 21 (126, no anchors) stay at 128.
 #ifndef CA_NS15_THREADS
-#define CA_NS15_THREADS 128
-#define CA_NS15_BLOCKS 1
+#define CA_NS15_THREADS 224
 #endif
-template <int NS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : (NS == 15 ? CA_NS15_THREADS : 128); }
-template <int NS> __host__ __device__ constexpr int smem_doubles_per_thread() { return 6 * NS + 30 + (NS <= 15 ? 20 : 0); }   // k slots + stage coefficients + anchors (NS <= 15)
+template <int NS, int BEAMS> __host__ __device__ constexpr int threads_for() { return NS == 9 ? 256 : ((NS == 15 && BEAMS == 1) ? CA_NS15_THREADS : 128); }
+inline int threads_for_rt(int ns, int beams) { return ns == 9 ? 256 : ((ns == 15 && beams == 1) ? CA_NS15_THREADS : 128); }
+template <int BEAMS> __host__ __device__ constexpr int cb_doubles() { return 5 * ((BEAMS == 1 || BEAMS == 2) ? 4 : 6); }   // Lane1::kCB per stage
+template <int NS, int BEAMS> __host__ __device__ constexpr int smem_doubles_per_thread() {   // k slots + stage coefficients + anchors (NS <= 15)
+    return 6 * NS + cb_doubles<BEAMS>() + (NS <= 15 ? (BEAMS == 1 ? 14 : 20) : 0);   // (Lane1::kAB slots per beam)
+}
 
 struct R1Params {
     DevModel model;            // single-point runs: lives in the constant bank with the other params
@@ -51,17 +55,14 @@ struct R1Params {
     int n_points, nt, nf, n_nodes_max, n_coarse_max;
 };
 
-template <int NS>
-__host__ __device__ constexpr int blocks_per_sm() { return NS == 9 ? 1 : (NS == 15 ? CA_NS15_BLOCKS : 1); }
-
 template <int NS, bool SWEEP, int BEAMS>
-__global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lindblad1(const __grid_constant__ R1Params P) {
-    constexpr int T = threads_for<NS>();
+__global__ void __launch_bounds__(threads_for<NS, BEAMS>(), 1) k_lindblad1(const __grid_constant__ R1Params P) {
+    constexpr int T = threads_for<NS, BEAMS>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sk = reinterpret_cast<double*>(smem_raw);                                   // [6][NS][T] stage derivatives
     double* scb = sk + 6 * NS * T;                                                      // [5][6][T] stage coefficients
-    double* sab = scb + 30 * T;                                                         // [2][2][5][T] beam anchors (NS <= 15)
-    DevModel* sm_models = reinterpret_cast<DevModel*>(sk + smem_doubles_per_thread<NS>() * T);  // [warps] (sweeps only)
+    double* sab = scb + cb_doubles<BEAMS>() * T;                                                         // [2][2][5][T] beam anchors (NS <= 15)
+    DevModel* sm_models = reinterpret_cast<DevModel*>(sk + smem_doubles_per_thread<NS, BEAMS>() * T);  // [warps] (sweeps only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifndef CA_WARP_MAJOR
 #define CA_WARP_MAJOR 1
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(threads_for<NS>(), blocks_per_sm<NS>()) k_lind
 
 template <int NS, bool SWEEP, int BEAMS>
 static cudaError_t launch_lindblad1(cudaStream_t stream, const R1Params& P, int grid) {
-    constexpr int T = threads_for<NS>();
-    const size_t smem = sizeof(double) * smem_doubles_per_thread<NS>() * T + (SWEEP ? sizeof(DevModel) * (T / 32) : 0);
+    constexpr int T = threads_for<NS, BEAMS>();
+    const size_t smem = sizeof(double) * smem_doubles_per_thread<NS, BEAMS>() * T + (SWEEP ? sizeof(DevModel) * (T / 32) : 0);
     cudaError_t e = cudaFuncSetAttribute(k_lindblad1<NS, SWEEP, BEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_lindblad1<NS, SWEEP, BEAMS><<<grid, T, smem, stream>>>(P);

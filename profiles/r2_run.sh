@@ -12,7 +12,7 @@ if [ "$1" = "a" ]; then
 python bench.py --no-cpu --steps 2 --warmup 3 > $O/bench_plain.json 2> $O/bench_plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_py.csv python bench.py --no-cpu --steps 2 --warmup 3 > $O/ncu_launches.log 2>&1
 python profiles/prof_r1.py 37888 1 > $O/plain_r1.log 2>&1 && $NCU -k regex:k_lindblad1 -o $O/k_lindblad1_r1 python profiles/prof_r1.py 37888 1 > $O/ncu_r1.log 2>&1
-python profiles/prof_ns15.py 28416 > $O/plain_ns15.log 2>&1 && $NCU -k regex:k_lindblad1 -o $O/k_lindblad1_ns15 python profiles/prof_ns15.py 28416 > $O/ncu_ns15.log 2>&1
+python profiles/prof_ns15.py 33152 > $O/plain_ns15.log 2>&1 && $NCU -k regex:k_lindblad1 -o $O/k_lindblad1_ns15 python profiles/prof_ns15.py 33152 > $O/ncu_ns15.log 2>&1
 elif [ "$1" = "b" ]; then
 python profiles/prof_r2.py 37888 > $O/plain_r2.log 2>&1 && $NCU -k regex:k_lindblad1 -o $O/k_lindblad1_r2 python profiles/prof_r2.py 37888 > $O/ncu_r2.log 2>&1
 python profiles/prof_z1.py 1184 0.2 > $O/plain_z1.log 2>&1 && $NCU -k regex:k_lindblad2 -o $O/k_lindblad2_z1 python profiles/prof_z1.py 1184 0.2 > $O/ncu_z1.log 2>&1
