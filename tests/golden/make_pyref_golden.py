@@ -3,7 +3,8 @@ reference's one-atom and two-atom models from the INDEPENDENT numpy/scipy restat
 closures the way the Julia source reads), together with the host-side samples and phase draws that produced them.
 The C oracle (CPU suite) and the CUDA path (GPU suite) are both checked against these committed numbers.
 
-    python tests/golden/make_pyref_golden.py
+    python tests/golden/make_pyref_golden.py          # short windows -> pyref_trajectories.npz
+    python tests/golden/make_pyref_golden.py full     # the BENCHMARKED windows (R1 0:T0/20:5T0, Z1 [0, 2 tau]) -> pyref_full_window.npz (~1 min)
 """
 import os
 import sys
@@ -17,13 +18,41 @@ import __graft_entry__ as g  # noqa: E402
 import pyref  # noqa: E402
 
 pkg = g.load_package()
+σ = np.array([0.158, 0.158, 0.864, 0.0978, 0.0978, 0.0978])   # thermal widths of the default trap (SURVEY App. C)
+
+if len(sys.argv) > 1 and sys.argv[1] == "full":
+    # Full windows of the benchmarked configurations (BASELINE configs 2 and 4), one converged trajectory each: R1 |1> in free flight, R1 with
+    # a superposition ψ0 (the fidelity callers' case), Z1 with the default phase jump ξ at τ.  13 k (R1) / 11 k (Z1) DP5 steps lie between
+    # the initial state and the last output, so these pin the whole-window behaviour that the short-window file cannot.
+    rng = np.random.default_rng(20261021)
+    cfg, cz = pkg.get_default_configs()
+    cfg.laser_noise = True
+    fw_samples = rng.normal(size=(2, 6)) * σ
+    fw_phases = rng.uniform(0, 2 * np.pi, (2, 2, len(cfg.f)))
+    fw_psi = [pkg.ket_1, (pkg.ket_0 - 1j * pkg.ket_1) / np.sqrt(2)]
+    fw_rho = []
+    for i in range(2):
+        c = cfg.copy()
+        c.ψ0 = fw_psi[i]
+        ref, nfev = pyref.one_atom_traj(c, fw_samples[i], fw_phases[0, i], fw_phases[1, i], rtol=1e-12, atol=1e-14)
+        print("R1 full window", i, "nfev", nfev)
+        fw_rho.append(ref)
+    cz.laser_noise = True
+    fz_s = rng.normal(size=(2, 6)) * σ
+    fz_phases = rng.uniform(0, 2 * np.pi, (4, len(cz.f)))
+    fz_rho, nfev = pyref.two_atom_traj(cz, fz_s[0], fz_s[1], [fz_phases[q] for q in range(4)], rtol=1e-11, atol=1e-13)
+    print("Z1 full window nfev", nfev)
+    np.savez_compressed(os.path.join(HERE, "pyref_full_window.npz"), r1_tspan=cfg.tspan, r1_samples=fw_samples, r1_phases=fw_phases,
+                        r1_psi0=np.array(fw_psi), r1_rho=np.array(fw_rho), z1_tspan=cz.tspan, z1_s=fz_s, z1_phases=fz_phases, z1_rho=fz_rho)
+    print("written", os.path.join(HERE, "pyref_full_window.npz"))
+    sys.exit(0)
+
 rng = np.random.default_rng(20261020)
 cfg, cz = pkg.get_default_configs()
 
 # one atom: R1 model on a short window, free and trapped motion, |1> and a superposition with |0>
 cfg.laser_noise = True
 cfg.tspan = np.linspace(0.0, 0.1, 6)
-σ = np.array([0.158, 0.158, 0.864, 0.0978, 0.0978, 0.0978])   # thermal widths of the default trap (SURVEY App. C)
 r1_samples = rng.normal(size=(3, 6)) * σ * 0.7
 r1_phases = rng.uniform(0, 2 * np.pi, (2, 3, len(cfg.f)))
 r1_rho = []

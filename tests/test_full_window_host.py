@@ -93,3 +93,21 @@ def test_z1_full_window_device_source(pkg, oracle, he):
         o, o2, ost = oracle.rydberg2_run(model, cz.tspan, cz.ψ0, 1, seed=11, traj_offset=gi, ode=ode, **kw)
         assert st == [ost["n_rhs"], ost["n_accept"], ost["n_reject"]]
         assert max(np.abs(r - o).max(), np.abs(r2 - o2).max()) < 1e-7
+
+
+def test_device_source_reproduces_full_window_golden(pkg, he):
+    """The host-compiled DEVICE source against the committed scipy DOP853 trajectories over the benchmarked windows
+    (tests/golden/pyref_full_window.npz): the CPU-suite twin of test_cuda_path_reproduces_full_window_golden."""
+    from test_golden_trajectories import FW, fw_r1_case, fw_z1_case
+    for i in range(2):
+        cfg, model, kw = fw_r1_case(pkg, i)
+        for ode, tol, ptol in [(pkg._abi.ode_opts(1e-11, 1e-13, maxiters=10 ** 7), 1e-9, 1e-9), (pkg._abi.ode_opts(), 3e-5, 1e-6)]:
+            r1, r2, st = he_traj(he, model, cfg.tspan, cfg.ψ0, kw["samples"][0], kw["phases_red"][0], kw["phases_blue"][0], cfg.f, kw["amp_red"], kw["amp_blue"], ode)
+            assert np.abs(r1 - FW["r1_rho"][i]).max() < tol, i
+            assert np.abs(np.einsum("tii->ti", r1 - FW["r1_rho"][i])).max() < ptol, i
+    cz, model, kw = fw_z1_case(pkg)
+    for ode, tol, ptol in [(pkg._abi.ode_opts(1e-10, 1e-12, maxiters=10 ** 7), 5e-9, 5e-9), (pkg._abi.ode_opts(maxiters=10 ** 7), 5e-5, 1e-6)]:
+        rc, r, r2, st = he_traj2(he, model, cz.tspan, cz.ψ0, kw["samples1"][0], kw["samples2"][0], [p[0] for p in kw["phases4"]], cz.f, kw["amp_red"], kw["amp_blue"], ode)
+        assert rc == 0
+        assert np.abs(r - FW["z1_rho"]).max() < tol
+        assert np.abs(np.einsum("tii->ti", r - FW["z1_rho"])).max() < ptol
