@@ -32,6 +32,12 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         ts = np.array([0.0, float(os.environ.get("AB_TEND", cz.tspan[-1]))])
         run = lambda: ctx.rydberg2_run(m2, ts, cz.ψ0, n, seed=7, f=cz.f, amp_red=cz.red_laser_phase_amplitudes,   # noqa: E731
                                        amp_blue=cz.blue_laser_phase_amplitudes, ode=pkg._abi.ode_opts(maxiters=10 ** 7))
+    elif os.environ.get("AB_WORKLOAD") in ("trap", "ns15t"):   # atoms oscillating in the trap (free_motion = false): |1> / the superposition state
+        cfg.free_motion = False
+        model = pkg.model_from_config(cfg)
+        psi = cfg.ψ0 if os.environ.get("AB_WORKLOAD") == "trap" else (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2)
+        run = lambda: ctx.rydberg1_run(model, cfg.tspan, psi, n, seed=7, f=cfg.f, amp_red=cfg.red_laser_phase_amplitudes,   # noqa: E731
+                                       amp_blue=cfg.blue_laser_phase_amplitudes)
     elif os.environ.get("AB_WORKLOAD") in ("ns15", "ns21"):   # R1 with a superposition initial state (fidelity callers) / a general one
         model = pkg.model_from_config(cfg)
         psi = (pkg.ket_0 + 1j * pkg.ket_1) / np.sqrt(2)
