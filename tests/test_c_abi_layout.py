@@ -1,0 +1,107 @@
+"""The drop-in boundary seen from its three bindings: include/coldatoms_b200.h compiled as plain C (gcc -std=c11 -pedantic -Werror: no C++,
+no torch types), the ctypes structs of the Python mirror (_abi.py) and the `struct`s of the Julia shim (julia/NeutralAtomsB200.jl) must give
+every field of ca_beam / ca_model / ca_ode_opts / ca_stats the same offset and every struct the same size.  The probe is a C program generated
+from the ctypes field names (a name the header does not declare fails to compile); it also resolves the library's entry points from C and
+checks that ca_init refuses to run without a GPU (no CPU fallback behind the C ABI either)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STRUCTS = ["ca_beam", "ca_model", "ca_ode_opts", "ca_stats"]
+JULIA = {"CaBeam": "ca_beam", "CaModel": "ca_model", "CaOde": "ca_ode_opts", "CaStats": "ca_stats"}
+
+
+@pytest.fixture(scope="module")
+def probe(pkg, tmp_path_factory):
+    d = tmp_path_factory.mktemp("abi")
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include <dlfcn.h>', '#include "coldatoms_b200.h"', 'int main(int argc, char** argv) {',
+             '  printf("{");']
+    for s in STRUCTS:
+        st = getattr(pkg._abi, s)
+        lines.append('  printf("\\"%s\\": {\\"size\\": %%zu, \\"fields\\": {", sizeof(%s));' % (s, s))
+        for i, (name, _) in enumerate(st._fields_):
+            lines.append('  printf("%s\\"%s\\": %%zu", offsetof(%s, %s));' % ("" if i == 0 else ", ", name, s, name))
+        lines.append('  printf("}}, ");')
+    lines += ['  void* h = dlopen(argv[1], RTLD_NOW);',
+              '  if (!h) { printf("\\"dlopen\\": \\"%s\\"}", dlerror()); return 0; }',
+              '  int (*version)(void); int (*init)(int, ca_ctx**); const char* (*last_error)(void);',
+              '  *(void**)(&version) = dlsym(h, "ca_version"); *(void**)(&init) = dlsym(h, "ca_init"); *(void**)(&last_error) = dlsym(h, "ca_last_error");',
+              '  (void)sizeof(version == &ca_version); (void)sizeof(init == &ca_init); (void)sizeof(last_error == &ca_last_error);   /* prototypes as declared */',
+              '  ca_ctx* ctx = NULL;',
+              '  int rc = init(0, &ctx);',
+              '  printf("\\"version\\": %d, \\"init_rc\\": %d, \\"ctx_null\\": %d, \\"error_len\\": %zu}", version(), rc, ctx == NULL, strlen(last_error()));',
+              '  return 0; }']
+    src = d / "abi_probe.c"
+    src.write_text('#include <string.h>\n' + "\n".join(lines) + "\n")
+    exe = d / "abi_probe"
+    subprocess.check_call(["gcc", "-std=c11", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src), "-ldl"])
+    out = subprocess.run([str(exe), pkg._lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    return json.loads(out)
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_mirror(pkg, probe):
+    for s in STRUCTS:
+        st = getattr(pkg._abi, s)
+        assert probe[s]["size"] == C.sizeof(st), s
+        for name, _ in st._fields_:
+            assert probe[s]["fields"][name] == getattr(st, name).offset, (s, name)
+
+
+def test_entry_points_resolve_from_c_and_refuse_without_a_gpu(pkg, probe):
+    import torch
+    assert "dlopen" not in probe, probe.get("dlopen")
+    assert probe["version"] == 200
+    if torch.cuda.is_available():
+        assert probe["init_rc"] == 0 and not probe["ctx_null"]
+    else:
+        assert probe["init_rc"] == pkg._abi.CA_ERR_NODEVICE and probe["ctx_null"] and probe["error_len"] > 0
+
+
+def _julia_structs():
+    src = open(os.path.join(ROOT, "coldatoms.jl_b200", "julia", "NeutralAtomsB200.jl")).read()
+    out = {}
+    for m in re.finditer(r"^(?:mutable )?struct (\w+)\n(.*?)^end", src, re.S | re.M):
+        if m.group(1) not in JULIA:
+            continue
+        fields = []
+        for line in m.group(2).splitlines():
+            line = line.split("#")[0]
+            if "=" in line and "::" not in line.split("=")[0]:
+                continue   # inner constructor
+            for f in line.split(";"):
+                fm = re.match(r"\s*(\w+)::([\w{},]+)\s*$", f)
+                if fm:
+                    fields.append((fm.group(1), fm.group(2)))
+        out[m.group(1)] = fields
+    return out
+
+
+def test_julia_shim_structs_have_the_c_layout(probe):
+    """C-compatible layout of the Julia `struct`s (natural alignment, nested isbits structs inline) against the C compiler's offsets."""
+    js = _julia_structs()
+    assert set(js) == set(JULIA)
+    prim = {"Float64": (8, 8), "Int64": (8, 8), "UInt64": (8, 8), "Int32": (4, 4), "NTuple{3,Float64}": (24, 8)}
+
+    def layout(name):
+        off, align, offs = 0, 1, []
+        for fname, ftype in js[name]:
+            size, al = prim[ftype] if ftype in prim else layout(ftype)[:2]
+            off = (off + al - 1) // al * al
+            offs.append((fname, off))
+            off += size
+            align = max(align, al)
+        return (off + align - 1) // align * align, align, offs
+
+    for jname, cname in JULIA.items():
+        size, _, offs = layout(jname)
+        assert size == probe[cname]["size"], jname
+        c_offsets = sorted(probe[cname]["fields"].values())
+        assert [o for _, o in offs] == c_offsets, jname
+        for fname, o in offs:   # same names wherever the shim keeps the header's name
+            if fname in probe[cname]["fields"]:
+                assert probe[cname]["fields"][fname] == o, (jname, fname)
