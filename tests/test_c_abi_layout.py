@@ -105,3 +105,82 @@ def test_julia_shim_structs_have_the_c_layout(probe):
         for fname, o in offs:   # same names wherever the shim keeps the header's name
             if fname in probe[cname]["fields"]:
                 assert probe[cname]["fields"][fname] == o, (jname, fname)
+
+
+def _c_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "coldatoms_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = {}
+    for m in re.finditer(r"\b(ca_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", hdr, re.S):
+        params = [p.strip() for p in m.group(2).split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        kinds = []
+        for p in params:
+            if "*" in p:
+                kinds.append("ptr")
+            elif re.search(r"\buint64_t\b|unsigned long long", p):
+                kinds.append("u64")
+            elif re.search(r"\bint64_t\b|\blong long\b", p):
+                kinds.append("i64")
+            elif re.search(r"\bdouble\b", p):
+                kinds.append("f64")
+            elif re.search(r"\bu?int32_t\b|\bint\b|\bunsigned\b", p):
+                kinds.append("i32")
+            else:
+                kinds.append("?" + p)
+        protos[m.group(1)] = kinds
+    return protos
+
+
+def _julia_kind(t):
+    t = t.strip()
+    if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+        return "ptr"
+    return {"Int32": "i32", "Cint": "i32", "UInt32": "i32", "Int64": "i64", "UInt64": "u64", "Float64": "f64"}.get(t, "?" + t)
+
+
+def _split_top(s):   # split on commas outside braces / parentheses
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "{(":
+            depth += 1
+        elif ch in "})":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return out
+
+
+def test_julia_ccall_signatures_match_the_header():
+    """The shim cannot run here (no Julia), so every `ccall` in it is checked statically: the argument-type tuple must have the arity of the C
+    prototype it binds and the same kind (pointer / 32-bit / 64-bit signed / 64-bit unsigned / double) in every position.  Call sites that go
+    through `entry(:single, :multi)` are checked against both prototypes."""
+    src = open(os.path.join(ROOT, "coldatoms.jl_b200", "julia", "NeutralAtomsB200.jl")).read()
+    protos = _c_prototypes()
+    assert all(not k.startswith("?") for ks in protos.values() for k in ks), protos
+    checked = 0
+    for m in re.finditer(r"ccall\(\s*(sym\(:(\w+)\)|fp)\s*,\s*(\w+)\s*,\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:   # the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        kinds = [_julia_kind(t) for t in _split_top(src[m.end():i - 1]) if t.strip()]
+        assert all(not k.startswith("?") for k in kinds), kinds
+        if m.group(2):
+            names = [m.group(2)]
+        else:   # fp, h = entry(:ca_x, :ca_x_multi) earlier in the same function
+            e = list(re.finditer(r"entry\(:(\w+),\s*:(\w+)\)", src[:m.start()]))[-1]
+            names = [e.group(1), e.group(2)]
+        for name in names:
+            assert name in protos, name
+            assert kinds == protos[name], (name, kinds, protos[name])
+            checked += 1
+        assert (m.group(3) == "Cstring") == (names == ["ca_last_error"])   # every other entry returns the int status
+    assert checked >= 17
