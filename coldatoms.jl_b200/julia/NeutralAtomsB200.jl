@@ -68,6 +68,11 @@ const BEAM_GAUSS, BEAM_HG, BEAM_LG, BEAM_UNIFORM = Int32(0), Int32(1), Int32(2),
 const DOPPLER_XZ, DOPPLER_Z = Int32(0), Int32(1)
 const SIGN_RYDBERG1, SIGN_CZ = Int32(0), Int32(1)
 const COMPAT_DEFAULT = Int32(1)
+const TWOATOM_PER_ATOM_LASERS, TWOATOM_CONST_VRR, TWOATOM_SHIFT_AFTER_MOTION, TWOATOM_DIRECT = Int32(1), Int32(2), Int32(4), Int32(8)   # CA_2A_*
+
+# The rydberg_model.jl / cz_model.jl parameterisation (29 leading fields): the legacy two-atom fields of two_atom_model.jl are zeroed.
+const NOBEAM = CaBeam(0.0, 1.0, 1.0, 0.0, 1.0, 1.0, BEAM_GAUSS, 0, 0, 0, 0)
+CaModel(a::Vararg{Any,29}) = CaModel(a..., Int32(0), Int32(0), NOBEAM, NOBEAM, 0.0, 0.0, 0.0, 0.0)
 
 const LIB = Ref{Ptr{Cvoid}}(C_NULL)
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)

@@ -184,3 +184,32 @@ def test_julia_ccall_signatures_match_the_header():
             checked += 1
         assert (m.group(3) == "Cstring") == (names == ["ca_last_error"])   # every other entry returns the int status
     assert checked >= 17
+
+
+def test_julia_struct_constructor_calls_have_a_matching_arity():
+    """Julia's default constructor takes exactly one argument per field: every `CaXxx(...)` call in the shim must have that arity, or the
+    arity of an outer constructor the shim defines (`CaModel(a::Vararg{Any,N}) = ...`)."""
+    src = open(os.path.join(ROOT, "coldatoms.jl_b200", "julia", "NeutralAtomsB200.jl")).read()
+    nfields = {k: len(v) for k, v in _julia_structs().items()}
+    outer = {k: set() for k in nfields}
+    for m in re.finditer(r"^(Ca\w+)\(\w+::Vararg\{Any,\s*(\d+)\}\)\s*=", src, re.M):
+        outer[m.group(1)].add(int(m.group(2)))
+    assert outer["CaModel"], "the 29-argument constructor of the cz_model.jl parameterisation is missing"
+    calls = 0
+    for m in re.finditer(r"(?<![\w{.:])(Ca(?:Beam|Model|Ode|Stats))\(", src):
+        line_start = src.rfind("\n", 0, m.start()) + 1
+        if re.match(r"\s*(?:mutable )?struct ", src[line_start:m.start() + 1]) or "::Vararg" in src[m.end():m.end() + 20]:
+            continue
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1, "[": 1, "]": -1}.get(src[i], 0)
+            i += 1
+        args = [a for a in _split_top(src[m.end():i - 1].replace("[", "(").replace("]", ")")) if a.strip()]
+        if m.group(1) == "CaStats" and not args:
+            continue   # inner zero-argument constructor
+        n = len(args)
+        if any(a.strip().endswith("...") for a in args):
+            continue   # splatted call (the outer constructor itself)
+        assert n == nfields[m.group(1)] or n in outer[m.group(1)], (m.group(1), n, src[m.start():m.start() + 80])
+        calls += 1
+    assert calls >= 9
