@@ -362,6 +362,79 @@ function get_rydberg_infidelity(cfg::NeutralAtoms.RydbergConfig;
     return infidelities
 end
 
+# F(ϕ) = <Φ+| Had RZZ(ϕ) ρ (Had RZZ(ϕ))† |Φ+> of src/fidelity.jl:166 for all ϕ: RZ(ϕ) ⊗ RZ(ϕ) is diagonal, so with h = Had† Φ+ (four non-zero
+# qubit components) F(ϕ) = v(ϕ)' ρ v(ϕ), v = conj(d(ϕ)) .* h -- 62 832 four-term forms instead of 62 832 products of 25×25 operators.
+function parity_scan(ρ1, ϕ_list)
+    Had = NeutralAtoms.Id ⊗ NeutralAtoms.Hadamard
+    Φp = (NeutralAtoms.ket_0 ⊗ NeutralAtoms.ket_0 + NeutralAtoms.ket_1 ⊗ NeutralAtoms.ket_1) / sqrt(2)
+    h = (dagger(Had) * Φp).data
+    nz = findall(x -> abs(x) > 0, h)
+    R = ρ1.data[nz, nz]
+    F = zeros(Float64, length(ϕ_list))
+    for (k, ϕ) in enumerate(ϕ_list)
+        d1 = [NeutralAtoms.RZ(ϕ).data[i, i] for i in 1:5]
+        d = kron(d1, d1)                      # diagonal of RZ(ϕ) ⊗ RZ(ϕ) (both factors equal: the ⊗ ordering does not matter)
+        v = conj.(d[nz]) .* h[nz]
+        F[k] = real(v' * R * v)
+    end
+    return F
+end
+
+"`get_parity_fidelity(cfg::CZLPConfig; ode_kwargs...)` -- src/fidelity.jl:147-176 -> (ϕ_list, F_list, ϕ at the maximum); the scan in closed form"
+function get_parity_fidelity(cfg::NeutralAtoms.CZLPConfig; ode_kwargs...)
+    c = deepcopy(cfg)
+    ket_pos = (NeutralAtoms.ket_0 + NeutralAtoms.ket_1) / sqrt(2)
+    c.ψ0 = ket_pos ⊗ ket_pos
+    ρ1 = simulation_czlp(c; ode_kwargs...)[1][end]
+    ϕ_list = [0.0:0.0001:2π;]
+    F = parity_scan(ρ1, ϕ_list)
+    return ϕ_list, F, ϕ_list[argmax(F)]
+end
+
+"""
+`get_cz_infidelity(cfg::CZLPConfig; n_samples=1, ode_kwargs...)` -- src/fidelity.jl:193-240 with its seven `simulation_czlp` ensembles (the
+parity-scan run that fixes ϕ_RZ (:205), the calibration-error run (:209), the five error-budget configurations (:218-231)) in ONE
+`ca_rydberg2_sweep` launch, trajectories of all of them handed out longest first.  Returns `(infidelities::Dict, calibration_error)`.
+"""
+function get_cz_infidelity(cfg::NeutralAtoms.CZLPConfig; n_samples = 1, ode_kwargs...)
+    configs = NeutralAtoms.get_rydberg_fidelity_configs(cfg, n_samples)
+    names = collect(keys(configs))
+    ket_pos = (NeutralAtoms.ket_0 + NeutralAtoms.ket_1) / sqrt(2)
+    ψ0 = ket_pos ⊗ ket_pos
+    cfg_t = deepcopy(cfg)
+    cfg_t.spontaneous_decay_intermediate = false
+    cfg_t.spontaneous_decay_rydberg = false
+    cfg_t.laser_noise = false
+    cfg_t.atom_params[2] = 1.0
+    cfg_t.n_samples = 1
+    pts = vcat([cfg_t, deepcopy(cfg_t)], [deepcopy(configs[name]) for name in names])
+    models = [model(c; two_atom = true) for c in pts]
+    psis = repeat(ComplexF64.(ψ0.data), length(pts))
+    tends = Float64[c.tspan[end] for c in pts]
+    counts = Int64[c.n_samples for c in pts]
+    ρ = zeros(ComplexF64, 625 * length(pts)); ρ2 = similar(ρ)
+    st = CaStats()
+    f, ar, ab = Float64.(cfg.f), Float64.(cfg.red_laser_phase_amplitudes), Float64.(cfg.blue_laser_phase_amplitudes)
+    GC.@preserve models psis tends counts f ar ab check(ccall(sym(:ca_rydberg2_sweep), Cint,
+        (Ptr{Cvoid}, Ptr{CaModel}, Ptr{ComplexF64}, Ptr{Float64}, Int32, Ptr{Int64}, Int64, UInt64, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Int32, Ref{CaOde}, Int32, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{CaStats}),
+        CTX[], models, psis, tends, length(pts), counts, 0, next_seed(), f, ar, ab, length(f), ode(; ode_kwargs...), 0, ρ, ρ2, st))
+    b = ψ0.basis
+    ρend = [Operator(b, b, reshape(ρ[(k-1)*625+1:k*625], 25, 25)) for k in 1:length(pts)]
+    ϕ_list = [0.0:0.0001:2π;]
+    ϕ_RZ = ϕ_list[argmax(parity_scan(ρend[1], ϕ_list))]
+    Had = NeutralAtoms.Id ⊗ NeutralAtoms.Hadamard
+    global_RZ = NeutralAtoms.RZ(ϕ_RZ) ⊗ NeutralAtoms.RZ(ϕ_RZ)
+    Φp = (NeutralAtoms.ket_0 ⊗ NeutralAtoms.ket_0 + NeutralAtoms.ket_1 ⊗ NeutralAtoms.ket_1) / sqrt(2)
+    infid(ρk) = 1.0 - real(dagger(Φp) * (Had * global_RZ * ρk * dagger(Had * global_RZ)) * Φp)
+    calibration_error = infid(ρend[2])
+    infidelities = Dict()
+    for (k, name) in enumerate(names)
+        infidelities[name] = maximum([infid(ρend[k+2]) - calibration_error, 0.0])
+    end
+    return infidelities, calibration_error
+end
+
 "Route the reference's own entry points through the GPU path (fidelity.jl and user scripts keep working unchanged)."
 function override!()
     @eval NeutralAtoms begin
@@ -371,6 +444,10 @@ function override!()
         calibrate_two_photon(cfg::RydbergConfig, n_samples=1000) = Main.NeutralAtomsB200.calibrate_two_photon(cfg, n_samples)
         get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples=10000) =
             Main.NeutralAtomsB200.get_blockade_stark_shift_factor(trap_params, atom_params, atom_centers, Ω, c6, n_samples)
+        # the fidelity callers as batched launches (src/fidelity.jl:67-95, 147-176, 193-240)
+        get_rydberg_infidelity(cfg::RydbergConfig; kw...) = Main.NeutralAtomsB200.get_rydberg_infidelity(cfg; kw...)
+        get_parity_fidelity(cfg::CZLPConfig; kw...) = Main.NeutralAtomsB200.get_parity_fidelity(cfg; kw...)
+        get_cz_infidelity(cfg::CZLPConfig; kw...) = Main.NeutralAtomsB200.get_cz_infidelity(cfg; kw...)
     end
     return nothing
 end
