@@ -163,10 +163,11 @@ def test_julia_ccall_signatures_match_the_header():
     prototype it binds and the same kind (pointer / 32-bit / 64-bit signed / 64-bit unsigned / double) in every position.  Call sites that go
     through `entry(:single, :multi)` are checked against both prototypes."""
     src = open(os.path.join(ROOT, "coldatoms.jl_b200", "julia", "NeutralAtomsB200.jl")).read()
+    src += open(os.path.join(ROOT, "tests", "julia_parity.jl")).read()   # the off-box parity script binds ca_rydberg1_run itself
     protos = _c_prototypes()
     assert all(not k.startswith("?") for ks in protos.values() for k in ks), protos
     checked = 0
-    for m in re.finditer(r"ccall\(\s*(sym\(:(\w+)\)|fp)\s*,\s*(\w+)\s*,\s*\(", src):
+    for m in re.finditer(r"ccall\(\s*((?:\w+\.)?sym\(:(\w+)\)|fp)\s*,\s*(\w+)\s*,\s*\(", src):
         i, depth = m.end(), 1
         while depth:   # the argument-type tuple
             depth += {"(": 1, ")": -1}.get(src[i], 0)
@@ -183,7 +184,7 @@ def test_julia_ccall_signatures_match_the_header():
             assert kinds == protos[name], (name, kinds, protos[name])
             checked += 1
         assert (m.group(3) == "Cstring") == (names == ["ca_last_error"])   # every other entry returns the int status
-    assert checked >= 17
+    assert checked >= 19
 
 
 def test_julia_struct_constructor_calls_have_a_matching_arity():
