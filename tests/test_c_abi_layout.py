@@ -214,3 +214,29 @@ def test_julia_struct_constructor_calls_have_a_matching_arity():
         assert n == nfields[m.group(1)] or n in outer[m.group(1)], (m.group(1), n, src[m.start():m.start() + 80])
         calls += 1
     assert calls >= 9
+
+
+def test_python_mirror_call_sites_match_the_header(pkg):
+    """Every `load().ca_xxx(...)` call in _lib.py against the header: arity, and the kind of each argument as far as the expression shows
+    it (explicit ctypes scalar wrappers; pointers come from byref / _p / data_as / cast / None / array variables)."""
+    src = open(os.path.join(ROOT, "coldatoms.jl_b200", "_lib.py")).read()
+    protos = _c_prototypes()
+    scalar = {"C.c_int32(": "i32", "C.c_int(": "i32", "C.c_int64(": "i64", "C.c_longlong(": "i64", "C.c_uint64(": "u64", "C.c_ulonglong(": "u64",
+              "C.c_double(": "f64", "int(": "i32"}
+    seen = set()
+    for m in re.finditer(r"\.(ca_[a-z0-9_]+)\(", src):
+        name = m.group(1)
+        if src[m.start() - 4:m.start()] == "_abi":
+            continue   # a ctypes struct constructor (_abi.ca_stats()), not a library call
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1, "[": 1, "]": -1}.get(src[i], 0)
+            i += 1
+        args = [a.strip() for a in _split_top(src[m.end():i - 1].replace("[", "(").replace("]", ")")) if a.strip()]
+        assert name in protos, name
+        assert len(args) == len(protos[name]), (name, len(args), len(protos[name]))
+        for a, kind in zip(args, protos[name]):
+            got = next((k for pre, k in scalar.items() if a.startswith(pre)), "ptr")
+            assert got == kind, (name, a, got, kind)
+        seen.add(name)
+    assert seen >= set(pkg._lib.EXPORTS) - {"ca_version", "ca_multi_context"}, set(pkg._lib.EXPORTS) - seen
